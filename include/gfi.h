@@ -1,0 +1,172 @@
+/*
+ * gfi.h -- C ABI of libgfi.so, the B200-native GpuFlatIndex.
+ *
+ * Drop-in boundary: this is what a Rust `gpu-flat-index-sys` crate binds
+ *  so that `GpuFlatIndex: Index` can replace `FlatIndex`
+ * behind the reference's unchanged `trait Index` (reference src/index.rs:11-35).
+ * Every entry point names the reference interface it replaces.  No torch or C++
+ * types cross this boundary: plain pointers, sizes and integer status codes.
+ *
+ * Conventions
+ *   - every function returns an int32 status (GFI_OK = 0) unless stated;
+ *     nothing throws or aborts across the boundary; gfi_last_error() returns a
+ *     thread-local message for the last non-zero status on the calling thread.
+ *   - the caller owns all host buffers; the library owns device memory behind
+ *     the opaque handle.
+ *   - threading mirrors the reference server (src/server/mod.rs:13-16):
+ *     gfi_search* are re-entrant and may run concurrently from any OS thread
+ *     (they are `&self` under RwLock::read); gfi_add/remove/flush/compact are
+ *     exclusive (`&mut self` under RwLock::write).
+ *   - results are ordered by (distance ascending, then lower internal id); the
+ *     reference's own tie order is unspecified (HashMap iteration order under a
+ *     stable sort, src/flat_index.rs:53-62), so this is one of its legal outputs.
+ *   - distances are bit-identical to the reference's arithmetic (sequential f32
+ *     sums, separately rounded multiply/add; src/distance.rs:37-73).
+ */
+#ifndef GFI_H_
+#define GFI_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gfi_index gfi_index;
+
+/* status codes <-> reference src/error.rs:10-31 */
+#define GFI_OK 0
+#define GFI_ERR_DIMENSION_MISMATCH 1 /* VectorDbError::DimensionMismatch{expected, actual}: see gfi_last_mismatch */
+#define GFI_ERR_INVALID_VECTOR 2     /* VectorDbError::InvalidVector (cosine with a zero-norm query or row) */
+#define GFI_ERR_INDEX 3              /* VectorDbError::IndexError(String): CUDA failure, bad argument, ... */
+#define GFI_ERR_NAN 4                /* a distance is NaN: the reference panics (flat_index.rs:62); we report */
+
+/* DistanceMetric, reference src/distance.rs:9-16 */
+#define GFI_METRIC_EUCLIDEAN 0
+#define GFI_METRIC_COSINE 1
+#define GFI_METRIC_DOT 2
+
+/* gfi_create flags */
+#define GFI_FLAG_NO_TENSOR 1u /* never use the tcgen05 batched path (scan path only, no fp16 shadow copy) */
+
+/* data kinds for gfi_add_generated (identical generator in oracle/flat_oracle.c) */
+#define GFI_GEN_UNIFORM 0
+#define GFI_GEN_NORMAL 1
+
+/*
+ * FlatIndex::new(metric), reference src/flat_index.rs:19-24.
+ * dim = 0 latches the dimension at the first gfi_add (FlatIndex has no dimension
+ * of its own); device = CUDA ordinal.
+ */
+int32_t gfi_create(gfi_index **out, int32_t metric, int64_t dim, int32_t device, uint32_t flags);
+int32_t gfi_destroy(gfi_index *h);
+
+/*
+ * Index::add, reference src/index.rs:13 / src/flat_index.rs:38-41, for n rows at
+ * once (n = 1 from Index::add; large n for bulk load).  An existing id is
+ * overwritten.  Rows are staged in pinned host memory and reach the GPU at the
+ * next gfi_flush / gfi_search.  Like FlatIndex::add this never fails on a
+ * dimension: a row whose `dim` differs from the index dimension is recorded and
+ * makes every later search return GFI_ERR_DIMENSION_MISMATCH, exactly as the
+ * per-pair check in DistanceMetric::distance does (src/distance.rs:21-26).
+ */
+int32_t gfi_add(gfi_index *h, const uint64_t *ids, const float *rows, int64_t n, int64_t dim);
+
+/* Bench/bulk helper: rows first_row..first_row+n of the synthetic generator are created
+ * directly in HBM (ids first_id..), so 100M-row shards never cross PCIe. */
+int32_t gfi_add_generated(gfi_index *h, uint32_t seed, uint64_t first_row, int64_t n, int32_t kind,
+                          uint64_t first_id);
+
+/* Index::remove, src/index.rs:16 / src/flat_index.rs:43-46: idempotent (tombstone). */
+int32_t gfi_remove(gfi_index *h, uint64_t id);
+
+/* Index::len / Index::metric, src/index.rs:26-29.  gfi_dim: 0 while unlatched. */
+int64_t gfi_len(const gfi_index *h);
+int32_t gfi_metric(const gfi_index *h);
+int64_t gfi_dim(const gfi_index *h);
+
+/* Index::get_vector, src/index.rs:23: copies the stored row to `out` (cap floats). Returns
+ * GFI_OK and *out_dim = row dimension, or GFI_ERR_INDEX if the id is absent (Option::None).
+ * (A Rust wrapper that must lend `&Vector` keeps its own host mirror; see INTEGRATION.md.) */
+int32_t gfi_get_vector(gfi_index *h, uint64_t id, float *out, int64_t cap, int64_t *out_dim);
+
+/* Push staged rows to the GPU now (searches do it implicitly). */
+int32_t gfi_flush(gfi_index *h);
+/* Pre-size device storage for n rows (avoids regrowth during bulk load). */
+int32_t gfi_reserve(gfi_index *h, int64_t n_rows);
+/* Drop tombstoned slots and restore slot order == id order. */
+int32_t gfi_compact(gfi_index *h);
+
+/*
+ * Index::search (src/index.rs:20, src/flat_index.rs:52-65) for a batch of q queries with
+ * per-query k (VectorStore::search_batch, src/storage.rs:302-310; q = 1 is Index::search).
+ *   queries  : q x dim, row-major host floats
+ *   ks       : q per-query k (k = 0 => no results)
+ *   mask     : NULL, or eligibility bits indexed by INTERNAL ID (bit id%64 of word id/64,
+ *              mask_bits bits long; ids >= mask_bits are ineligible).  A masked search is
+ *              FlatIndex::search over the eligible rows (filter push-down; the reference's
+ *              own post-filter, src/storage.rs:249-290, needs no mask: the caller over-fetches).
+ *   out_ids / out_dist : q x kstride, out_counts[i] = min(ks[i], eligible rows)
+ * The first failing query fails the batch (collect::<Result<_>>(), storage.rs:306-309).
+ */
+int32_t gfi_search(gfi_index *h, const float *queries, int64_t q, int64_t dim, const uint32_t *ks,
+                   const uint64_t *mask, int64_t mask_bits, uint64_t *out_ids, float *out_dist,
+                   uint32_t *out_counts, int64_t kstride);
+
+/*
+ * Same search with every buffer already in device memory (HBM) and asynchronous on
+ * `stream` (a cudaStream_t passed as void*; NULL = the index's own stream): no host
+ * synchronisation.  d_ks/d_mask/d_* are device pointers.  Call gfi_search_status to
+ * collect the status of the last device search issued on this handle by this thread
+ * (synchronises the stream).  Used by multi-GPU callers that all-gather the per-shard
+ * results and by the HBM-resident benchmark.
+ */
+int32_t gfi_search_device(gfi_index *h, const float *d_queries, int64_t q, const uint32_t *d_ks,
+                          uint32_t kmax, const uint64_t *d_mask, int64_t mask_bits,
+                          uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_counts,
+                          int64_t kstride, void *stream);
+int32_t gfi_search_status(gfi_index *h);
+
+/*
+ * Merge G per-shard result lists (each sorted by (distance, id)) into the global top-k
+ * per query, on device, asynchronously on `stream`.  Inputs are laid out [G][q][kstride]
+ * (the layout an all-gather of per-shard gfi_search_device outputs produces).
+ */
+int32_t gfi_merge_topk_device(const uint64_t *d_ids, const float *d_dist, const uint32_t *d_counts,
+                              int32_t G, int64_t q, int64_t kstride, const uint32_t *d_ks,
+                              uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_counts,
+                              int64_t out_kstride, void *stream);
+
+/* DimensionMismatch payload of the last GFI_ERR_DIMENSION_MISMATCH on this thread. */
+void gfi_last_mismatch(int64_t *expected, int64_t *actual);
+/* Thread-local message for the last error on this thread ("" if none). */
+const char *gfi_last_error(void);
+
+/* Counters for the benchmark harness (not part of the reference interface). */
+typedef struct gfi_stats {
+  int64_t n_slots;          /* device rows incl. tombstones */
+  int64_t n_live;           /* live rows */
+  int64_t searches;         /* search calls */
+  int64_t queries;          /* queries served */
+  int64_t scan_queries;     /* queries answered by the streaming scan kernel */
+  int64_t tensor_queries;   /* queries answered by the tcgen05 kernel */
+  int64_t fallback_queries; /* tensor-path queries re-run on the scan kernel (not certified) */
+  int64_t kernel_launches;  /* CUDA kernels launched by this handle */
+  int64_t bytes_fp32;       /* device bytes of the fp32 rows */
+  int64_t bytes_fp16;       /* device bytes of the fp16 shadow rows */
+  /* with option "profile"=1: CUDA-event time of the dominant kernel of each search, summed */
+  int64_t scan_kernel_ns, scan_kernel_count;     /* K1 flat_scan_topk launches */
+  int64_t tensor_kernel_ns, tensor_kernel_count; /* K2 flat_gemm_topk main-pass launches */
+} gfi_stats;
+int32_t gfi_get_stats(gfi_index *h, gfi_stats *out);
+
+/* Tuning knobs for experiments (name/value); returns GFI_ERR_INDEX for unknown names. */
+int32_t gfi_set_option(gfi_index *h, const char *name, int64_t value);
+
+/* Library/ABI version (major*100 + minor). */
+int32_t gfi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GFI_H_ */

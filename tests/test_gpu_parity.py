@@ -1,0 +1,381 @@
+"""GPU parity tests: every call goes through the C ABI (libgfi.so via ctypes) and is checked
+against the CPU oracle on the same seeded inputs.  Bar: identical ids in (distance, lower id)
+order and BIT-IDENTICAL distances (libgfi re-scores survivors with the reference's arithmetic);
+id swaps are tolerated only between distances closer than 1e-5 relative (north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+import vectordb_from_scratch_b200 as gfi
+from vectordb_from_scratch_b200 import DistanceMetric as DM
+from helpers import KATS, assert_topk_matches, numpy_merge
+
+pytestmark = pytest.mark.gpu
+M = {"euclidean": DM.Euclidean, "cosine": DM.Cosine, "dot": DM.DotProduct}
+
+
+def build(metric, rows, ids=None, flags=0):
+    idx = gfi.GpuFlatIndex(M[metric], flags=flags)
+    n = rows.shape[0]
+    idx.add_batch(np.arange(n, dtype=np.uint64) if ids is None else ids, rows)
+    return idx
+
+
+def check_batch(idx, metric, rows, queries, ks, ids=None, eligible=None, mask=None, ctx=""):
+    got_ids, got_d, cnt = idx.search_arrays(queries, ks, mask=mask)
+    exp = oracle.search_batch(metric, rows, queries, ks, ids=ids, eligible=eligible, threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert cnt[i] == len(eids), f"{ctx} q{i}: count {cnt[i]} != {len(eids)}"
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"{ctx} q{i}")
+
+
+# ---------------------------------------------------------------- reference KATs via the ABI
+@pytest.mark.parametrize("kat", KATS["distance"], ids=lambda k: k["src"])
+def test_reference_distance_kats_through_abi(kat):
+    metric = "dot" if kat["metric"] == "rawdot" else kat["metric"]
+    idx = gfi.GpuFlatIndex(M[metric])
+    idx.add(0, kat["b"])
+    (rid, dist), = idx.search(kat["a"], 1)
+    got = -dist if kat["metric"] == "rawdot" else dist
+    assert rid == 0 and abs(got - kat["expect"]) <= kat["tol"] * max(1.0, abs(kat["expect"]))
+    assert np.float32(dist) == oracle.distance(metric, kat["a"], kat["b"])  # bit-identical
+
+
+def test_reference_flat_index_kats():
+    k = KATS["flat_index_basic"]
+    idx = gfi.GpuFlatIndex(DM.Euclidean)
+    for i, v in k["rows"].items():
+        idx.add(int(i), v)
+    res = idx.search(k["query"], k["k"])
+    assert len(res) == k["expect_len"] and res[0][0] == k["expect_first_id"] and res[0][1] < 1e-6
+    # get_vector hit/miss (flat_index.rs:96-103)
+    assert np.array_equal(idx.get_vector(0), np.array(k["rows"]["0"], dtype=np.float32))
+    assert idx.get_vector(99) is None
+    # remove => len (flat_index.rs:106-114)
+    r = KATS["flat_index_remove"]
+    idx2 = gfi.GpuFlatIndex(DM.Euclidean)
+    for i, v in r["rows"].items():
+        idx2.add(int(i), v)
+    assert idx2.len() == 2
+    idx2.remove(r["remove"])
+    assert idx2.len() == r["expect_len"]
+    idx2.remove(r["remove"])  # idempotent
+    assert idx2.len() == r["expect_len"]
+    assert idx2.metric() == DM.Euclidean
+
+
+def test_reference_store_kats():
+    s = KATS["store_search"]
+    store = gfi.VectorStore(DM.Euclidean)
+    assert store.search([1, 2, 3], 5) == []  # storage.rs:399-404 empty store
+    for sid, v in s["rows"].items():
+        store.insert(sid, v)
+    res = store.search(s["query"], s["k"])
+    assert len(res) == 2 and res[0].id == "v1" and res[0].distance == 0.0
+    with pytest.raises(gfi.DimensionMismatch):
+        store.insert("bad", [1.0, 2.0])  # dimension latch, storage.rs:145-154
+    with pytest.raises(gfi.DimensionMismatch):
+        store.search([1.0, 2.0], 1)
+    w = KATS["integration_workflow"]
+    store = gfi.VectorStore(DM.Euclidean)
+    for sid, v in w["rows"].items():
+        store.insert(sid, v)
+    assert store.len() == 3
+    res = store.search(w["query"], w["k"])
+    assert len(res) == 2 and res[0].id == "v1"
+    deleted = store.delete("v2")
+    assert np.array_equal(deleted, np.array([0, 1, 0], dtype=np.float32)) and store.len() == 2
+    k = KATS["integration_metrics_self_match"]
+    for m in k["metrics"]:
+        st = gfi.VectorStore(M[m])
+        st.insert("v1", k["rows"]["v1"])
+        res = st.search(k["query"], 1)
+        assert len(res) == 1 and res[0].id == "v1"
+
+
+@pytest.mark.parametrize("pushdown", [False, True])
+def test_reference_filter_and_batch_kats(pushdown):
+    def mk(case):
+        st = gfi.VectorStore(DM.Euclidean)
+        for sid, (v, md) in case["rows"].items():
+            m = gfi.Metadata()
+            for a, b in md.items():
+                m.insert(a, b)
+            st.insert_with_metadata(sid, v, m)
+        return st
+    c = KATS["filter_matching"]
+    res = mk(c).search_with_filter(c["query"], c["k"], gfi.MetadataFilter.from_json(c["filter"]), pushdown=pushdown)
+    assert [r.id for r in res] == c["expect_ids"]
+    c = KATS["filter_none_matching"]
+    assert mk(c).search_with_filter(c["query"], c["k"], gfi.MetadataFilter.from_json(c["filter"]),
+                                    pushdown=pushdown) == []
+    c = KATS["filter_all_matching"]
+    assert len(mk(c).search_with_filter(c["query"], c["k"], gfi.MetadataFilter.from_json(c["filter"]),
+                                        pushdown=pushdown)) == 2
+    c = KATS["batch_search_with_filter"]
+    res = mk(c).search_batch_with_filter([(q, k) for q, k in c["queries"]],
+                                         gfi.MetadataFilter.from_json(c["filter"]), pushdown=pushdown)
+    assert [[r.id for r in rr] for rr in res] == c["expect_ids"]
+    c = KATS["batch_search"]
+    st = gfi.VectorStore(DM.Euclidean)
+    for sid, v in c["rows"].items():
+        st.insert(sid, v)
+    for batched in (False, True):
+        res = st.search_batch([(q, k) for q, k in c["queries"]], batched=batched)
+        assert [r[0].id for r in res] == c["expect_first_ids"]
+
+
+# ---------------------------------------------------------------- scan path vs oracle
+SCAN_CASES = [  # n, d, kind, q, k
+    (10000, 128, 0, 3, 10),    # C1 (benches/search_bench.rs:18-33)
+    (3000, 768, 1, 2, 100),    # C3 scaled down (column-segmented rows)
+    (4000, 384, 0, 5, 10),     # C4 scaled down
+    (700, 3, 1, 4, 5),         # tiny d (padding path)
+    (900, 17, 0, 9, 33),       # odd d, q > 8 (two passes), k -> K=64
+    (1200, 1000, 1, 1, 10),    # d > 256 and not a multiple of 256
+    (257, 64, 1, 2, 300),      # k > n
+]
+
+
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot"])
+@pytest.mark.parametrize("case", SCAN_CASES, ids=lambda c: "n%d_d%d_q%d_k%d" % (c[0], c[1], c[3], c[4]))
+def test_scan_path_matches_oracle(metric, case):
+    n, d, kind, q, k = case
+    rows = oracle.gen_rows(100 + d, 0, n, d, kind)
+    queries = oracle.gen_rows(200 + d, 0, q, d, kind)
+    idx = build(metric, rows, flags=1)  # GFI_FLAG_NO_TENSOR: scan kernel only
+    check_batch(idx, metric, rows, queries, k, ctx=f"{metric} {case}")
+    st = idx.stats()
+    assert st["scan_queries"] == q and st["tensor_queries"] == 0 and st["kernel_launches"] > 0
+
+
+def test_bench_query_constant_half(tmp_path):
+    # benches/search_bench.rs:27: query = 0.5 * ones, x ~ U[0,1)
+    rows = oracle.gen_rows(1, 0, 10000, 128, 0)
+    idx = build("euclidean", rows)
+    check_batch(idx, "euclidean", rows, np.full((1, 128), 0.5, np.float32), 10, ctx="C1 bench query")
+
+
+def test_per_query_k_and_edge_ks():
+    rows = oracle.gen_rows(5, 0, 500, 32, 1)
+    queries = oracle.gen_rows(6, 0, 6, 32, 1)
+    idx = build("dot", rows)
+    check_batch(idx, "dot", rows, queries, [1, 0, 7, 500, 600, 3], ctx="per-query k")
+
+
+def test_generated_rows_equal_oracle_generator():
+    for kind in (0, 1):
+        idx = gfi.GpuFlatIndex(DM.Euclidean, dim=40)
+        idx.add_generated(77, (1 << 33) + 10, 1000, kind, 5000)
+        exp = oracle.gen_rows(77, (1 << 33) + 10, 1000, 40, kind)
+        for i in (0, 1, 499, 999):
+            assert np.array_equal(idx.get_vector(5000 + i), exp[i])
+        q = oracle.gen_rows(78, 0, 2, 40, kind)
+        check_batch(idx, "euclidean", exp, q, 10, ids=np.arange(5000, 6000, dtype=np.uint64), ctx="generated")
+
+
+# ---------------------------------------------------------------- mutation semantics
+def test_remove_overwrite_out_of_order_and_compact():
+    rng = np.random.default_rng(3)
+    rows = rng.standard_normal((400, 24)).astype(np.float32)
+    ids = np.arange(400, dtype=np.uint64) * 3 + 10
+    idx = build("euclidean", rows, ids=ids)
+    q = rng.standard_normal((3, 24)).astype(np.float32)
+    live = np.ones(400, dtype=bool)
+    for r in (0, 5, 399, 200):
+        idx.remove(int(ids[r]))
+        live[r] = False
+    idx.remove(123456)  # missing id: Ok(())
+    assert idx.len() == 396
+    check_batch(idx, "euclidean", rows[live], q, 10, ids=ids[live], ctx="after remove")
+    # overwrite (HashMap::insert semantics) and an id below the current maximum
+    new_row = rng.standard_normal(24).astype(np.float32)
+    idx.add(int(ids[7]), new_row)
+    rows2 = rows.copy()
+    rows2[7] = new_row
+    low = rng.standard_normal(24).astype(np.float32)
+    idx.add(1, low)
+    assert idx.len() == 397
+    all_rows = np.concatenate([low[None], rows2[live]])
+    all_ids = np.concatenate([[1], ids[live]]).astype(np.uint64)
+    check_batch(idx, "euclidean", all_rows, q, 397, ids=all_ids, ctx="after overwrite")
+    assert np.array_equal(idx.get_vector(int(ids[7])), new_row) and idx.get_vector(int(ids[0])) is None
+    idx.compact()
+    assert idx.stats()["n_slots"] == 397
+    check_batch(idx, "euclidean", all_rows, q, 20, ids=all_ids, ctx="after compact")
+
+
+def test_duplicate_rows_tie_break_by_lower_id():
+    base = oracle.gen_rows(9, 0, 50, 16, 1)
+    rows = np.concatenate([base] * 40)  # 2000 rows, every vector 40 times
+    idx = build("cosine", rows)
+    check_batch(idx, "cosine", rows, base[:3], 60, ctx="duplicates")
+    # signed zeros: -dot = -0.0 ties with +0.0, lower id wins
+    idx = gfi.GpuFlatIndex(DM.DotProduct)
+    idx.add(2, [0.0, 1.0])
+    idx.add(1, [0.0, -1.0])
+    assert [i for i, _ in idx.search([1.0, 0.0], 2)] == [1, 2]
+
+
+def test_error_semantics():
+    idx = gfi.GpuFlatIndex(DM.Cosine)
+    idx.add(0, [1.0, 0.0])
+    idx.add(1, [0.0, 0.0])
+    with pytest.raises(gfi.InvalidVector):   # distance.rs:51-55 via flat_index.rs:57-60
+        idx.search([1.0, 1.0], 1)
+    idx.remove(1)
+    assert idx.search([1.0, 1.0], 1)[0][0] == 0
+    with pytest.raises(gfi.InvalidVector):
+        idx.search([0.0, 0.0], 1)
+    nan = gfi.GpuFlatIndex(DM.Euclidean)
+    nan.add(0, [float("nan"), 0.0])
+    nan.add(1, [1.0, 0.0])
+    with pytest.raises(gfi.NaNDistance):
+        nan.search([0.0, 0.0], 1)
+    mixed = gfi.GpuFlatIndex(DM.Euclidean)
+    mixed.add(0, [1.0, 2.0, 3.0])
+    with pytest.raises(gfi.DimensionMismatch) as e:  # distance.rs:21-26: expected = query dim
+        mixed.search([1.0, 2.0], 1)
+    assert (e.value.expected, e.value.actual) == (2, 3)
+    mixed.add(1, [1.0, 2.0])  # FlatIndex::add never checks dimensions
+    assert mixed.len() == 2
+    with pytest.raises(gfi.DimensionMismatch):
+        mixed.search([1.0, 2.0, 3.0], 1)
+    mixed.remove(1)
+    assert mixed.search([1.0, 2.0, 3.0], 1)[0] == (0, 0.0)
+    empty = gfi.GpuFlatIndex(DM.Euclidean)
+    assert empty.search([1.0, 2.0], 3) == [] and empty.is_empty()
+
+
+# ---------------------------------------------------------------- filters
+@pytest.mark.parametrize("sel", [0.01, 0.5])
+def test_mask_pushdown_and_post_filter(sel):
+    n, d, k = 20000, 96, 10
+    rows = oracle.gen_rows(6, 0, n, d, 0)
+    queries = oracle.gen_rows(7, 0, 4, d, 0)
+    rng = np.random.default_rng(1)
+    elig = rng.random(n) < sel
+    idx = build("euclidean", rows, flags=1)
+    check_batch(idx, "euclidean", rows, queries, k, eligible=elig, mask=elig, ctx=f"mask {sel}")
+    # reference post-filter (fetch_k = 3k) through the unchanged single-query trait
+    for qi in range(2):
+        fetch = idx.search(queries[qi], 3 * k)
+        got = [(i, dd) for i, dd in fetch if elig[i]][:k]
+        eids, ed = oracle.search_post_filter("euclidean", rows, queries[qi], k, elig)
+        assert [i for i, _ in got] == [int(x) for x in eids]
+        assert np.array_equal(np.array([x for _, x in got], np.float32), ed)
+
+
+# ---------------------------------------------------------------- tensor (tcgen05) path vs oracle
+TENSOR_CASES = [  # metric, n, d, kind, q, k
+    ("cosine", 20000, 768, 1, 64, 10),     # C2 scaled down
+    ("euclidean", 30000, 128, 0, 130, 10),  # C5 scaled down, 2 query tiles (one partial)
+    ("dot", 16384, 768, 1, 32, 100),       # C3b scaled down
+    ("euclidean", 25000, 200, 1, 40, 10),  # d not a multiple of 64 (TMA zero fill along K)
+    ("cosine", 9000, 72, 0, 16, 5),        # concentrated cosines (uniform data), n not a tile multiple
+]
+
+
+@pytest.mark.parametrize("case", TENSOR_CASES, ids=lambda c: "%s_n%d_d%d_q%d_k%d" % (c[0], c[1], c[2], c[4], c[5]))
+def test_tensor_path_matches_oracle(case):
+    metric, n, d, kind, q, k = case
+    rows = oracle.gen_rows(300 + d, 0, n, d, kind)
+    queries = oracle.gen_rows(400 + d, 0, q, d, kind)
+    idx = build(metric, rows)
+    check_batch(idx, metric, rows, queries, k, ctx=str(case))
+    st = idx.stats()
+    assert st["tensor_queries"] == q, st
+    assert st["fallback_queries"] <= q // 4, st   # certification normally succeeds
+
+
+def test_tensor_path_with_mask_and_tombstones():
+    n, d, q, k = 20000, 256, 48, 10
+    rows = oracle.gen_rows(31, 0, n, d, 1)
+    queries = oracle.gen_rows(32, 0, q, d, 1)
+    idx = build("euclidean", rows)
+    rng = np.random.default_rng(2)
+    live = np.ones(n, dtype=bool)
+    for r in rng.choice(n, 500, replace=False):
+        idx.remove(int(r))
+        live[r] = False
+    elig = rng.random(n) < 0.5
+    ids = np.arange(n, dtype=np.uint64)
+    got_ids, got_d, cnt = idx.search_arrays(queries, k, mask=elig)
+    exp = oracle.search_batch("euclidean", rows[live], queries, k, ids=ids[live], eligible=elig[live], threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"tensor mask q{i}")
+    assert idx.stats()["tensor_queries"] == q
+
+
+def test_tensor_path_falls_back_when_not_certifiable():
+    # 64 copies of every vector: the top-k boundary is an exact tie, which can never be certified
+    base = oracle.gen_rows(41, 0, 256, 128, 1)
+    rows = np.concatenate([base] * 64)  # 16384 rows
+    queries = oracle.gen_rows(42, 0, 32, 128, 1)
+    idx = build("euclidean", rows)
+    check_batch(idx, "euclidean", rows, queries, 10, ctx="fallback")
+    st = idx.stats()
+    assert st["tensor_queries"] == 32 and st["fallback_queries"] > 0, st
+
+
+# ---------------------------------------------------------------- device-pointer API + merge kernel
+def test_device_search_and_merge_kernel():
+    import torch
+    n, d, q, k, G = 6000, 64, 5, 10, 3
+    rows = oracle.gen_rows(51, 0, n, d, 1)
+    queries = oracle.gen_rows(52, 0, q, d, 1)
+    bounds = [0, 1500, 4200, n]
+    dq = torch.from_numpy(queries).cuda()
+    dks = torch.full((q,), k, dtype=torch.int32, device="cuda")
+    all_ids = torch.zeros((G, q, k), dtype=torch.int64, device="cuda")
+    all_d = torch.zeros((G, q, k), dtype=torch.float32, device="cuda")
+    all_c = torch.zeros((G, q), dtype=torch.int32, device="cuda")
+    shards = []
+    stream = torch.cuda.current_stream().cuda_stream
+    for g in range(G):
+        lo, hi = bounds[g], bounds[g + 1]
+        idx = build("euclidean", rows[lo:hi], ids=np.arange(lo, hi, dtype=np.uint64))
+        shards.append(idx)
+        idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, all_ids[g].data_ptr(), all_d[g].data_ptr(),
+                          all_c[g].data_ptr(), k, stream=stream)
+        idx.search_status()
+    out_ids = torch.zeros((q, k), dtype=torch.int64, device="cuda")
+    out_d = torch.zeros((q, k), dtype=torch.float32, device="cuda")
+    out_c = torch.zeros((q,), dtype=torch.int32, device="cuda")
+    shards[0].merge_topk_device(all_ids.data_ptr(), all_d.data_ptr(), all_c.data_ptr(), G, q, k, dks.data_ptr(),
+                                out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr(), k, stream=stream)
+    torch.cuda.synchronize()
+    exp = oracle.search_batch("euclidean", rows, queries, k, threads=4)
+    ref_merge = numpy_merge(all_ids.cpu().numpy(), all_d.cpu().numpy(), all_c.cpu().numpy(), [k] * q)
+    for i in range(q):
+        assert out_c[i].item() == k
+        assert [int(x) for x in out_ids[i].cpu()] == [p[1] for p in ref_merge[i]] == [int(x) for x in exp[i][0]]
+        assert np.array_equal(out_d[i].cpu().numpy(), exp[i][1])
+
+
+# ---------------------------------------------------------------- full-size checks (BASELINE.json configs)
+def test_full_size_c2_cosine_batch_against_oracle_subset():
+    """C2: 1M x 768 cosine, batch 1024, k = 10.  The whole batch runs on the tcgen05 path; the oracle
+    (about 1 s per query on a host core) checks a subset of the queries bit for bit, and
+    size-independent properties are checked for all of them."""
+    n, d, q, k = 1_000_000, 768, 1024, 10
+    idx = gfi.GpuFlatIndex(DM.Cosine, dim=d)
+    idx.reserve(n)
+    idx.add_generated(3, 0, n, 1, 0)
+    queries = oracle.gen_rows(4, 0, q, d, 1)
+    ids, dist, cnt = idx.search_arrays(queries, k)
+    assert np.all(cnt == k)
+    assert np.all(np.diff(dist, axis=1) >= 0) and np.all((dist >= 0) & (dist <= 2))
+    st = idx.stats()
+    assert st["tensor_queries"] == q and st["fallback_queries"] <= 8, st
+    # idempotence and agreement of the two independent GPU paths (tensor vs exact scan) on 8 queries
+    ids2, dist2, _ = idx.search_arrays(queries, k)
+    assert np.array_equal(ids, ids2) and np.array_equal(dist, dist2)
+    idx.set_option("tensor_min_q", 1 << 30)
+    ids_s, dist_s, _ = idx.search_arrays(queries[:8], k)
+    assert np.array_equal(ids_s, ids[:8]) and np.array_equal(dist_s, dist[:8])
+    # bit-exact oracle parity on 4 queries at full size
+    rows = oracle.gen_rows(3, 0, n, d, 1)
+    exp = oracle.search_batch("cosine", rows, queries[:4], k, threads=4)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(ids[i], dist[i], eids, ed, ctx=f"C2 full q{i}")

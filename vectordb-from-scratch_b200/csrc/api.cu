@@ -1,0 +1,1239 @@
+// api.cu -- host runtime of libgfi.so and its C ABI (include/gfi.h).
+//
+// GpuFlatIndex keeps the database resident in HBM as a dense, append-ordered slot array
+// (slot order == internal-id order, tombstones for removed ids):
+//     x32  [slots][dpad]    fp32 rows (exact scan + reference-exact rerank)
+//     x16  [slots][dpad16]  per-row power-of-two scaled fp16 shadow (tcgen05 candidate pass)
+//     ids / norm / sumsq / coef / live bitmap
+// Adds are staged in pinned host memory and flushed lazily; searches borrow a context
+// (stream + workspace) from a pool so concurrent `&self` callers never share state.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/gfi.h"
+#include "kernels.h"
+
+using namespace gfi;
+
+namespace {
+
+thread_local std::string tl_error;
+thread_local int64_t tl_expected = 0, tl_actual = 0;
+
+int32_t fail(int32_t code, const std::string& msg) {
+  tl_error = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                             \
+  do {                                                                                           \
+    cudaError_t e__ = (expr);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return fail(GFI_ERR_INDEX, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
+  } while (0)
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
+    if (e == cudaSuccess) bytes = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  cudaError_t ensure(size_t need) {
+    if (need <= bytes) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+    cudaError_t e = cudaMallocHost(&p, need + need / 4 + 256);
+    if (e == cudaSuccess) bytes = need + need / 4 + 256;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// control block of one search call (device memory, zeroed per call)
+struct Ctrl {
+  uint32_t flags;
+  uint32_t fb_count;
+  uint32_t uncertified;
+  uint32_t qmaxabs_bits;
+};
+
+struct SearchCtx {
+  cudaStream_t stream = nullptr;
+  DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
+      fb_list, out_ids, out_dist, out_counts;
+  PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl;
+  bool pending_status = false;  // device search issued, status not yet collected
+  // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
+  struct EvPair { cudaEvent_t a, b; int kind; };
+  std::vector<EvPair> evs;
+  size_t ev_used = 0;
+  void release() {
+    for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &cand_fb, &cand_fb_cnt,
+                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts})
+      b->release();
+    for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl}) b->release();
+    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+    evs.clear();
+    ev_used = 0;
+    if (stream) cudaStreamDestroy(stream);
+    stream = nullptr;
+  }
+};
+
+struct Run {  // ids[slot0 + i] == id0 + i for i < n
+  uint32_t slot0;
+  uint32_t n;
+};
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace
+
+struct gfi_index {
+  int metric = 0;
+  int64_t dim = 0;
+  int dpad = 0, dpad16 = 0;
+  int device = 0;
+  uint32_t flags = 0;
+  int sm_count = 148;
+
+  mutable std::shared_mutex mu;  // writers: add/remove/flush/compact; readers: search
+  std::mutex pool_mu;
+  std::vector<std::unique_ptr<SearchCtx>> pool;
+
+  // device storage
+  int64_t cap = 0, n_slots = 0, n_live = 0;
+  DevBuf x32, x16, ids, norm, sumsq, coef, live, rowflags, counters;
+  cudaStream_t ingest_stream = nullptr;
+  bool use_x16 = true;
+  int64_t zero_rows_ever = 0, unsafe_rows_ever = 0;
+  float xnorm_max = 0.f;
+
+  // host bookkeeping
+  std::map<uint64_t, Run> runs;          // id0 -> run (disjoint id ranges)
+  std::vector<uint32_t> h_live;          // host mirror of the live bitmap
+  int64_t live_dirty_lo = -1, live_dirty_hi = -1;
+  bool ids_identity = true;
+  bool needs_reorder = false;
+  uint64_t max_id_seen = 0;
+  bool any_id = false;
+  std::unordered_map<uint64_t, int64_t> odd_dim_rows;  // id -> dim of rows whose dim != index dim
+
+  // staging (pinned)
+  PinBuf st_rows, st_ids;
+  int64_t st_n = 0, st_cap = 0;
+
+  // stats / options
+  std::atomic<int64_t> n_search{0}, n_queries{0}, n_scan_q{0}, n_tensor_q{0}, n_fallback_q{0}, n_launch{0};
+  int opt_tensor_min_q = 16;
+  int opt_kp = 0;          // 0 = auto
+  int opt_hits = 0;        // 0 = auto
+  int opt_scan_qt = 0;     // 0 = auto
+  int opt_grid = 0;        // 0 = sm_count
+  int opt_tensor_min_rows = 8192;
+  int opt_seed_rank = 8;
+  int opt_profile = 0;
+  std::atomic<int64_t> prof_ns[2] = {{0}, {0}}, prof_cnt[2] = {{0}, {0}};
+
+  IndexView view() const {
+    IndexView v;
+    v.x32 = x32.as<float>();
+    v.x16 = use_x16 ? x16.as<__half>() : nullptr;
+    v.ids = ids.as<uint64_t>();
+    v.norm = norm.as<float>();
+    v.sumsq = sumsq.as<float>();
+    v.coef = use_x16 ? coef.as<float2>() : nullptr;
+    v.live = live.as<uint32_t>();
+    v.n_slots = n_slots;
+    v.d = (int)dim;
+    v.dpad = dpad;
+    v.dpad16 = dpad16;
+    v.metric = metric;
+    v.ids_identity = ids_identity ? 1 : 0;
+    return v;
+  }
+};
+
+namespace {
+
+int32_t set_device(const gfi_index* h) {
+  CU_TRY(cudaSetDevice(h->device));
+  return GFI_OK;
+}
+
+void latch_dim(gfi_index* h, int64_t dim) {
+  h->dim = dim;
+  h->dpad = (int)((dim + 3) / 4 * 4);
+  h->dpad16 = (int)((dim + 7) / 8 * 8);
+}
+
+// grow device storage to hold at least `need` rows (keeps contents)
+int32_t grow(gfi_index* h, int64_t need) {
+  if (need <= h->cap) return GFI_OK;
+  int64_t ncap = std::max<int64_t>(need, h->cap + h->cap / 2);
+  ncap = std::max<int64_t>(ncap, 1024);
+  ncap = (ncap + 255) / 256 * 256;
+  if (ncap > 0xFFFFFFF0ll) return fail(GFI_ERR_INDEX, "too many rows for 32-bit slots");
+  struct Item { DevBuf* b; size_t per_row; };
+  std::vector<Item> items = {{&h->x32, (size_t)h->dpad * 4}, {&h->ids, 8}, {&h->norm, 4}, {&h->sumsq, 4},
+                             {&h->rowflags, 4}};
+  if (h->use_x16) {
+    items.push_back({&h->x16, (size_t)h->dpad16 * 2});
+    items.push_back({&h->coef, 8});
+  }
+  for (auto& it : items) {
+    void* np = nullptr;
+    size_t nbytes = it.per_row * (size_t)ncap + 256;
+    CU_TRY(cudaMalloc(&np, nbytes));
+    if (h->n_slots > 0 && it.b->p)
+      CU_TRY(cudaMemcpyAsync(np, it.b->p, it.per_row * (size_t)h->n_slots, cudaMemcpyDeviceToDevice,
+                             h->ingest_stream));
+    CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+    if (it.b->p) cudaFree(it.b->p);
+    it.b->p = np;
+    it.b->bytes = nbytes;
+  }
+  {
+    size_t words = (size_t)(ncap + 31) / 32;
+    void* np = nullptr;
+    CU_TRY(cudaMalloc(&np, words * 4 + 256));
+    CU_TRY(cudaMemsetAsync(np, 0, words * 4 + 256, h->ingest_stream));
+    if (h->live.p && h->n_slots > 0)
+      CU_TRY(cudaMemcpyAsync(np, h->live.p, ((size_t)h->n_slots + 31) / 32 * 4, cudaMemcpyDeviceToDevice,
+                             h->ingest_stream));
+    CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+    if (h->live.p) cudaFree(h->live.p);
+    h->live.p = np;
+    h->live.bytes = words * 4 + 256;
+    h->h_live.resize(words, 0u);
+  }
+  h->cap = ncap;
+  return GFI_OK;
+}
+
+bool lookup_slot(const gfi_index* h, uint64_t id, uint32_t* slot) {
+  auto it = h->runs.upper_bound(id);
+  if (it == h->runs.begin()) return false;
+  --it;
+  const uint64_t off = id - it->first;
+  if (off >= it->second.n) return false;
+  const uint32_t s = it->second.slot0 + (uint32_t)off;
+  if (!((h->h_live[s >> 5] >> (s & 31)) & 1u)) return false;
+  *slot = s;
+  return true;
+}
+
+void mark_live_dirty(gfi_index* h, int64_t word) {
+  if (h->live_dirty_lo < 0 || word < h->live_dirty_lo) h->live_dirty_lo = word;
+  if (word > h->live_dirty_hi) h->live_dirty_hi = word;
+}
+
+void tombstone(gfi_index* h, uint32_t slot) {
+  h->h_live[slot >> 5] &= ~(1u << (slot & 31));
+  mark_live_dirty(h, slot >> 5);
+  --h->n_live;
+}
+
+// registers ids for slots [slot0, slot0+n): consecutive ids extend the last run
+void register_ids(gfi_index* h, const uint64_t* ids, uint64_t first_id, int64_t n, uint32_t slot0) {
+  int64_t i = 0;
+  while (i < n) {
+    const uint64_t id = ids ? ids[i] : first_id + (uint64_t)i;
+    int64_t len = 1;
+    if (ids) {
+      while (i + len < n && ids[i + len] == id + (uint64_t)len) ++len;
+    } else {
+      len = n - i;
+    }
+    if (h->any_id && id <= h->max_id_seen) h->needs_reorder = true;  // out of order / overwrite
+    if (id != (uint64_t)(slot0 + i)) h->ids_identity = false;
+    // extend the previous run if contiguous in both id and slot space
+    bool merged = false;
+    if (!h->runs.empty()) {
+      auto last = std::prev(h->runs.end());
+      if (last->first + last->second.n == id && last->second.slot0 + last->second.n == slot0 + (uint32_t)i) {
+        last->second.n += (uint32_t)len;
+        merged = true;
+      }
+    }
+    if (!merged) h->runs[id] = Run{slot0 + (uint32_t)i, (uint32_t)len};
+    h->max_id_seen = std::max(h->max_id_seen, id + (uint64_t)len - 1);
+    h->any_id = true;
+    for (int64_t j = 0; j < len; ++j) {
+      const uint32_t s = slot0 + (uint32_t)(i + j);
+      h->h_live[s >> 5] |= 1u << (s & 31);
+    }
+    mark_live_dirty(h, (slot0 + i) >> 5);
+    mark_live_dirty(h, (slot0 + i + len - 1) >> 5);
+    h->n_live += len;
+    i += len;
+  }
+}
+
+// removes `id` from the run map (splitting its run) and tombstones its slot; false if absent
+bool erase_id(gfi_index* h, uint64_t id) {
+  auto it = h->runs.upper_bound(id);
+  if (it == h->runs.begin()) return false;
+  --it;
+  const uint64_t id0 = it->first;
+  const Run r = it->second;
+  const uint64_t off = id - id0;
+  if (off >= r.n) return false;
+  const uint32_t s = r.slot0 + (uint32_t)off;
+  const bool was_live = (h->h_live[s >> 5] >> (s & 31)) & 1u;
+  h->runs.erase(it);
+  if (off > 0) h->runs[id0] = Run{r.slot0, (uint32_t)off};
+  if (off + 1 < r.n) h->runs[id + 1] = Run{s + 1, (uint32_t)(r.n - off - 1)};
+  if (was_live) tombstone(h, s);
+  return was_live;
+}
+
+int32_t upload_live(gfi_index* h) {
+  if (h->live_dirty_lo < 0) return GFI_OK;
+  const int64_t lo = h->live_dirty_lo, hi = h->live_dirty_hi;
+  CU_TRY(cudaMemcpyAsync(h->live.as<uint32_t>() + lo, h->h_live.data() + lo, (size_t)(hi - lo + 1) * 4,
+                         cudaMemcpyHostToDevice, h->ingest_stream));
+  CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  h->live_dirty_lo = h->live_dirty_hi = -1;
+  return GFI_OK;
+}
+
+int32_t read_counters(gfi_index* h) {
+  struct { uint32_t zero, unsafe, maxnorm_bits, pad; } c;
+  CU_TRY(cudaMemcpyAsync(&c, h->counters.p, sizeof(c), cudaMemcpyDeviceToHost, h->ingest_stream));
+  CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  h->zero_rows_ever = c.zero;
+  h->unsafe_rows_ever = c.unsafe;
+  float m;
+  memcpy(&m, &c.maxnorm_bits, 4);
+  h->xnorm_max = m;
+  return GFI_OK;
+}
+
+}  // namespace
+
+// implemented in ingest.cu (kept here to avoid widening kernels.h): folds per-row flags into counters
+namespace gfi {
+cudaError_t launch_fold_rowflags(const uint32_t* rowflags, const float* norm, int64_t first, int64_t n,
+                                 uint32_t* counters, cudaStream_t st);
+}
+
+namespace {
+
+int32_t ingest_slots(gfi_index* h, int64_t first_slot, int64_t n, bool gen, uint32_t seed, uint64_t first_row,
+                     int kind) {
+  IngestParams p{};
+  p.x32 = h->x32.as<float>();
+  p.x16 = h->use_x16 ? h->x16.as<__half>() : nullptr;
+  p.norm = h->norm.as<float>();
+  p.sumsq = h->sumsq.as<float>();
+  p.coef = h->use_x16 ? h->coef.as<float2>() : nullptr;
+  p.zero_flags = h->rowflags.as<uint32_t>();
+  p.first_slot = first_slot;
+  p.n = n;
+  p.d = (int)h->dim;
+  p.dpad = h->dpad;
+  p.dpad16 = h->dpad16;
+  p.metric = h->metric;
+  p.gen = gen ? 1 : 0;
+  p.seed = seed;
+  p.first_row = first_row;
+  p.kind = kind;
+  CU_TRY(launch_ingest(p, h->ingest_stream));
+  CU_TRY(launch_fold_rowflags(h->rowflags.as<uint32_t>(), h->norm.as<float>(), first_slot, n,
+                              h->counters.as<uint32_t>(), h->ingest_stream));
+  h->n_launch += gen ? 3 : 2;
+  return GFI_OK;
+}
+
+// flush staged rows: H2D + row_stats.  Caller holds the unique lock.
+int32_t flush_locked(gfi_index* h) {
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  if (h->st_n > 0) {
+    const int64_t n = h->st_n;
+    if ((rc = grow(h, h->n_slots + n)) != GFI_OK) return rc;
+    const uint32_t slot0 = (uint32_t)h->n_slots;
+    CU_TRY(cudaMemcpyAsync(h->x32.as<float>() + (size_t)slot0 * h->dpad, h->st_rows.p,
+                           (size_t)n * h->dpad * 4, cudaMemcpyHostToDevice, h->ingest_stream));
+    CU_TRY(cudaMemcpyAsync(h->ids.as<uint64_t>() + slot0, h->st_ids.p, (size_t)n * 8, cudaMemcpyHostToDevice,
+                           h->ingest_stream));
+    // overwrite semantics of FlatIndex::add (HashMap::insert): drop any previous row with the same id
+    const uint64_t* sid = h->st_ids.as<uint64_t>();
+    for (int64_t i = 0; i < n; ++i) {
+      if (h->any_id && sid[i] <= h->max_id_seen) erase_id(h, sid[i]);
+      h->odd_dim_rows.erase(sid[i]);
+    }
+    h->n_slots += n;
+    register_ids(h, sid, 0, n, slot0);
+    if ((rc = ingest_slots(h, slot0, n, false, 0, 0, 0)) != GFI_OK) return rc;
+    CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+    h->st_n = 0;
+    if ((rc = read_counters(h)) != GFI_OK) return rc;
+  }
+  if ((rc = upload_live(h)) != GFI_OK) return rc;
+  return GFI_OK;
+}
+
+int32_t compact_locked(gfi_index* h);
+
+SearchCtx* acquire_ctx(gfi_index* h) {
+  std::lock_guard<std::mutex> g(h->pool_mu);
+  if (!h->pool.empty()) {
+    SearchCtx* c = h->pool.back().release();
+    h->pool.pop_back();
+    return c;
+  }
+  SearchCtx* c = new SearchCtx();
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return nullptr;
+  }
+  return c;
+}
+
+void release_ctx(gfi_index* h, SearchCtx* c) {
+  std::lock_guard<std::mutex> g(h->pool_mu);
+  h->pool.emplace_back(c);
+}
+
+int pow2_at_least(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+bool make_tmap_2d(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t rows, uint64_t row_pitch_bytes,
+                  uint32_t box_inner, uint32_t box_rows) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {inner, rows};
+  cuuint64_t gstride[1] = {row_pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+void prof_begin(gfi_index* h, SearchCtx* c, int kind, cudaStream_t st) {
+  if (!h->opt_profile) return;
+  if (c->ev_used == c->evs.size()) {
+    if (c->evs.size() >= 4096) return;  // collect with gfi_search_status before issuing more
+    SearchCtx::EvPair e{nullptr, nullptr, kind};
+    cudaEventCreate(&e.a);
+    cudaEventCreate(&e.b);
+    c->evs.push_back(e);
+  }
+  c->evs[c->ev_used].kind = kind;
+  cudaEventRecord(c->evs[c->ev_used].a, st);
+}
+void prof_end(gfi_index* h, SearchCtx* c, cudaStream_t st) {
+  if (!h->opt_profile || c->ev_used >= c->evs.size()) return;
+  cudaEventRecord(c->evs[c->ev_used].b, st);
+  ++c->ev_used;
+}
+// call after the stream has been synchronised
+void prof_collect(gfi_index* h, SearchCtx* c) {
+  for (size_t i = 0; i < c->ev_used; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->evs[i].a, c->evs[i].b) == cudaSuccess) {
+      h->prof_ns[c->evs[i].kind] += (int64_t)((double)ms * 1e6);
+      h->prof_cnt[c->evs[i].kind] += 1;
+    }
+  }
+  c->ev_used = 0;
+}
+
+struct SearchArgs {
+  const float* d_queries;  // device, [q][dim] unpadded
+  int64_t q;
+  const uint32_t* d_ks;
+  uint32_t kmax;
+  const uint64_t* d_mask;
+  int64_t mask_bits;
+  uint64_t* d_out_ids;
+  float* d_out_dist;
+  uint32_t* d_out_counts;
+  int64_t kstride;
+};
+
+// Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
+int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStream_t st) {
+  const int q = (int)a.q;
+  const int grid_sm = h->opt_grid > 0 ? h->opt_grid : h->sm_count;
+  IndexView iv = h->view();
+  MaskView mv{a.d_mask, a.mask_bits};
+
+  const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
+                         !(h->metric == GFI_METRIC_COSINE && h->zero_rows_ever > 0) &&
+                         q >= h->opt_tensor_min_q && h->n_slots >= h->opt_tensor_min_rows && a.kmax <= 256 &&
+                         get_encode_fn() != nullptr;
+
+  // ---- workspace ----
+  const int qpad = (q + 127) / 128 * 128;
+  CU_TRY(c->q32.ensure((size_t)q * h->dpad * 4));
+  CU_TRY(c->qnorm.ensure((size_t)q * 4));
+  CU_TRY(c->qsumsq.ensure((size_t)q * 4));
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  CU_TRY(c->fb_list.ensure((size_t)q * 4));
+  if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
+  CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+  Ctrl* ctrl = c->ctrl.as<Ctrl>();
+
+  PrepQueriesParams pq{};
+  pq.q_in = a.d_queries;
+  pq.q32 = c->q32.as<float>();
+  pq.q16 = tensor_ok ? c->q16.as<__half>() : nullptr;
+  pq.qnorm = c->qnorm.as<float>();
+  pq.qsumsq = c->qsumsq.as<float>();
+  pq.qmaxabs = reinterpret_cast<float*>(&ctrl->qmaxabs_bits);
+  pq.q = q;
+  pq.qpad = qpad;
+  pq.d = (int)h->dim;
+  pq.dpad = h->dpad;
+  pq.dpad16 = h->dpad16;
+  CU_TRY(launch_prep_queries(pq, st));
+  h->n_launch += tensor_ok ? 2 : 1;
+
+  // ---- scan geometry (also used by the tensor path's fallback) ----
+  const int K = std::min(1024, pow2_at_least(std::max<int>(32, (int)a.kmax + 8)));
+  if ((int)a.kmax > K) return fail(GFI_ERR_INDEX, "k too large: the scan path supports k <= 1024");
+  int QT = 8;
+  while (QT > 1 && ((int64_t)QT * h->dpad > 8192 || QT * K > 1024)) QT >>= 1;
+  if ((int64_t)QT * h->dpad > 16384) return fail(GFI_ERR_INDEX, "dimension too large (max 16384)");
+  if (h->opt_scan_qt > 0) QT = std::min(QT, h->opt_scan_qt);
+  if (!tensor_ok) { while (QT > 1 && QT / 2 >= q) QT >>= 1; }
+  int R, segf, nseg;
+  if (h->dpad * 32 <= kScanStageFloats) {
+    R = (kScanStageFloats / h->dpad) / 32 * 32;
+    segf = h->dpad;
+    nseg = 1;
+  } else {
+    R = 32;
+    segf = kScanSegFloats;
+    nseg = (h->dpad + kScanSegFloats - 1) / kScanSegFloats;
+  }
+  const int64_t nblocks = (h->n_slots + R - 1) / R;
+  const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
+  const int64_t scan_stride = (int64_t)scan_grid * K;
+
+  auto fill_scan = [&](ScanParams& sp, DevBuf& cand, DevBuf& cnt) {
+    sp.iv = iv;
+    sp.mask = mv;
+    sp.q32 = c->q32.as<float>();
+    sp.qnorm = c->qnorm.as<float>();
+    sp.K = K;
+    sp.floor64 = nullptr;
+    sp.cand = cand.as<uint64_t>();
+    sp.cand_cnt = cnt.as<uint32_t>();
+    sp.cand_stride = scan_stride;
+    sp.flags = &ctrl->flags;
+    sp.rows_per_stage = R;
+    sp.seg_floats = segf;
+    sp.nseg = nseg;
+  };
+  auto fill_select = [&](SelectParams& s, DevBuf& cand, DevBuf& cnt, int64_t stride, int KP) {
+    s.iv = iv;
+    s.q32 = c->q32.as<float>();
+    s.qnorm = c->qnorm.as<float>();
+    s.qsumsq = c->qsumsq.as<float>();
+    s.ks = a.d_ks;
+    s.cand = cand.as<uint64_t>();
+    s.cand_cnt = cnt.as<uint32_t>();
+    s.cand_stride = stride;
+    s.KP = KP;
+    s.qmaxabs = reinterpret_cast<const float*>(&ctrl->qmaxabs_bits);
+    s.xnorm_max = h->xnorm_max;
+    s.fb_count = &ctrl->fb_count;
+    s.fb_list = c->fb_list.as<uint32_t>();
+    s.out_ids = a.d_out_ids;
+    s.out_dist = a.d_out_dist;
+    s.out_counts = a.d_out_counts;
+    s.kstride = a.kstride;
+    s.flags = &ctrl->flags;
+    s.uncertified = &ctrl->uncertified;
+  };
+
+  if (!tensor_ok) {
+    CU_TRY(c->cand.ensure((size_t)q * scan_stride * 8));
+    CU_TRY(c->cand_cnt.ensure((size_t)q * 4));
+    ScanParams sp{};
+    fill_scan(sp, c->cand, c->cand_cnt);
+    sp.qlist = nullptr;
+    sp.nq_dev = nullptr;
+    sp.nq = q;
+    prof_begin(h, c, 0, st);
+    CU_TRY(launch_scan(sp, QT, scan_grid, st));
+    prof_end(h, c, st);
+    SelectParams s{};
+    fill_select(s, c->cand, c->cand_cnt, scan_stride, K);
+    s.qlist = nullptr;
+    s.nq_dev = nullptr;
+    s.nq = q;
+    s.certify = 0;
+    CU_TRY(launch_select_rerank(s, std::min(q, grid_sm * 8), st));
+    h->n_launch += 2;
+    h->n_scan_q += q;
+    return GFI_OK;
+  }
+
+  // ---- tensor path: seed thresholds -> tcgen05 filter -> select/rerank/certify -> scan fallback ----
+  const int KP = h->opt_kp > 0 ? std::min(1024, pow2_at_least(h->opt_kp))
+                               : std::min(1024, pow2_at_least(std::max<int>(64, 4 * (int)a.kmax)));
+  const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
+  const uint32_t cap = (uint32_t)std::min<int64_t>(4ll * hits, 1 << 16);
+  const int64_t num_n_tiles = (h->n_slots + 255) / 256;
+  const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
+  // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`
+  int64_t seed_tiles = (int64_t)std::ceil((double)rank * (double)h->n_slots / (double)hits / 256.0);
+  seed_tiles = std::max<int64_t>(1, std::min<int64_t>(seed_tiles, std::min<int64_t>(num_n_tiles, 256)));
+  const int64_t seed_stride = std::max<int64_t>(1, num_n_tiles / seed_tiles);
+  const int num_m_tiles = qpad / 128;
+
+  CU_TRY(c->cand.ensure((size_t)q * cap * 8));
+  CU_TRY(c->cand_cnt.ensure((size_t)q * 4));
+  CU_TRY(c->cand_fb.ensure((size_t)q * scan_stride * 8));
+  CU_TRY(c->cand_fb_cnt.ensure((size_t)q * 4));
+  CU_TRY(c->thresh.ensure((size_t)q * 4));
+  CU_TRY(c->seeds.ensure((size_t)q * seed_tiles * kSeedR * 4));
+  CU_TRY(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)q * 4, st));
+
+  CUtensorMap tmx, tmq;
+  if (!make_tmap_2d(&tmx, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 256) ||
+      !make_tmap_2d(&tmq, c->q16.p, (uint64_t)h->dpad16, (uint64_t)qpad, (uint64_t)h->dpad16 * 2, 64, 128))
+    return fail(GFI_ERR_INDEX, "cuTensorMapEncodeTiled failed");
+
+  GemmParams gp{};
+  gp.iv = iv;
+  gp.mask = mv;
+  gp.qmaxabs = reinterpret_cast<const float*>(&ctrl->qmaxabs_bits);
+  gp.qsumsq = c->qsumsq.as<float>();
+  gp.q = q;
+  gp.num_m_tiles = num_m_tiles;
+  gp.num_n_tiles = num_n_tiles;
+  gp.seeds = c->seeds.as<float>();
+  gp.thresh = c->thresh.as<float>();
+  gp.cand = c->cand.as<uint64_t>();
+  gp.cand_cnt = c->cand_cnt.as<uint32_t>();
+  gp.cand_stride = cap;
+  gp.cand_cap = cap;
+  gp.flags = &ctrl->flags;
+  gp.seed_tiles = seed_tiles;
+  gp.seed_stride = seed_stride;
+  // seed pass
+  gp.seed_mode = 1;
+  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, seed_tiles * num_m_tiles), st));
+  SeedFinalizeParams sf{c->seeds.as<float>(), q, seed_tiles, rank, c->thresh.as<float>()};
+  CU_TRY(launch_seed_finalize(sf, st));
+  // main pass
+  gp.seed_mode = 0;
+  prof_begin(h, c, 1, st);
+  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, num_n_tiles * num_m_tiles), st));
+  prof_end(h, c, st);
+  // select + exact rerank + certification
+  SelectParams s{};
+  fill_select(s, c->cand, c->cand_cnt, cap, KP);
+  s.qlist = nullptr;
+  s.nq_dev = nullptr;
+  s.nq = q;
+  s.certify = 1;
+  s.thresh = c->thresh.as<float>();
+  const float dd = (float)h->dim;
+  s.eps_rel = 9.765625e-4f + 9.5367432e-07f + 2.f * std::sqrt(dd) * 1.4901161e-08f + (dd + 8.f) * 1.1920929e-07f;
+  CU_TRY(launch_select_rerank(s, std::min(q, grid_sm * 8), st));
+  // predicated exact fallback for uncertified queries (device-side count; no host sync)
+  ScanParams sp{};
+  fill_scan(sp, c->cand_fb, c->cand_fb_cnt);
+  sp.qlist = c->fb_list.as<uint32_t>();
+  sp.nq_dev = &ctrl->fb_count;
+  sp.nq = 0;
+  CU_TRY(launch_scan(sp, QT, scan_grid, st));
+  SelectParams s2{};
+  fill_select(s2, c->cand_fb, c->cand_fb_cnt, scan_stride, K);
+  s2.qlist = c->fb_list.as<uint32_t>();
+  s2.nq_dev = &ctrl->fb_count;
+  s2.nq = 0;
+  s2.certify = 0;
+  CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
+  h->n_launch += 6;
+  h->n_tensor_q += q;
+  return GFI_OK;
+}
+
+int32_t flags_to_status(uint32_t fl) {
+  if (fl & kFlagZeroNorm)
+    return fail(GFI_ERR_INVALID_VECTOR, "Cannot compute cosine distance with zero vector");
+  if (fl & kFlagNaN) return fail(GFI_ERR_NAN, "a distance is NaN (the reference panics in sort_by)");
+  if (fl & kFlagInternal) return fail(GFI_ERR_INDEX, "internal kernel error");
+  return GFI_OK;
+}
+
+// validation shared by host and device searches; *empty is set when the answer is trivially empty
+int32_t precheck(gfi_index* h, int64_t qdim, bool* empty) {
+  *empty = false;
+  if (h->n_live + (int64_t)h->odd_dim_rows.size() == 0) {  // FlatIndex::search on an empty map: Ok(vec![])
+    *empty = true;
+    return GFI_OK;
+  }
+  if (!h->odd_dim_rows.empty()) {
+    tl_expected = qdim;
+    tl_actual = h->odd_dim_rows.begin()->second;
+    for (auto& kv : h->odd_dim_rows)
+      if (kv.second != qdim) { tl_actual = kv.second; break; }
+    if (tl_actual != qdim || (h->n_live > 0 && h->dim != qdim)) {
+      if (tl_actual == qdim) tl_actual = h->dim;
+      return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
+    }
+    // every stored row has the query's dimension only if the index itself is empty: fall through
+  }
+  if (h->n_live > 0 && qdim != h->dim) {
+    tl_expected = qdim;
+    tl_actual = h->dim;
+    return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
+  }
+  if (h->n_live == 0) *empty = true;  // only odd rows of the right dimension... cannot happen, be safe
+  return GFI_OK;
+}
+
+}  // namespace
+
+// ======================================= C ABI =======================================
+extern "C" {
+
+int32_t gfi_version(void) { return 100; }
+
+const char* gfi_last_error(void) { return tl_error.c_str(); }
+
+void gfi_last_mismatch(int64_t* expected, int64_t* actual) {
+  if (expected) *expected = tl_expected;
+  if (actual) *actual = tl_actual;
+}
+
+int32_t gfi_create(gfi_index** out, int32_t metric, int64_t dim, int32_t device, uint32_t flags) {
+  if (!out) return fail(GFI_ERR_INDEX, "null out pointer");
+  *out = nullptr;
+  if (metric < 0 || metric > 2) return fail(GFI_ERR_INDEX, "unknown metric");
+  if (dim < 0) return fail(GFI_ERR_INDEX, "negative dimension");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(GFI_ERR_INDEX, "no CUDA device: libgfi has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(GFI_ERR_INDEX, "bad device ordinal");
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) return fail(GFI_ERR_INDEX, "libgfi is built for sm_100a (B200) only");
+  std::unique_ptr<gfi_index> h(new gfi_index());
+  h->metric = metric;
+  h->device = device;
+  h->flags = flags;
+  h->sm_count = prop.multiProcessorCount;
+  h->use_x16 = !(flags & GFI_FLAG_NO_TENSOR);
+  if (dim > 0) latch_dim(h.get(), dim);
+  CU_TRY(cudaSetDevice(device));
+  CU_TRY(cudaStreamCreateWithFlags(&h->ingest_stream, cudaStreamNonBlocking));
+  CU_TRY(h->counters.ensure(16));
+  CU_TRY(cudaMemset(h->counters.p, 0, 16));
+  *out = h.release();
+  return GFI_OK;
+}
+
+int32_t gfi_destroy(gfi_index* h) {
+  if (!h) return GFI_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (auto& c : h->pool) c->release();
+  h->pool.clear();
+  for (DevBuf* b : {&h->x32, &h->x16, &h->ids, &h->norm, &h->sumsq, &h->coef, &h->live, &h->rowflags, &h->counters})
+    b->release();
+  h->st_rows.release();
+  h->st_ids.release();
+  if (h->ingest_stream) cudaStreamDestroy(h->ingest_stream);
+  delete h;
+  return GFI_OK;
+}
+
+int64_t gfi_len(const gfi_index* h) {
+  if (!h) return 0;
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  // staged rows that overwrite existing ids are resolved at flush; count them pessimistically unique
+  return h->n_live + h->st_n + (int64_t)h->odd_dim_rows.size();
+}
+int32_t gfi_metric(const gfi_index* h) { return h ? h->metric : -1; }
+int64_t gfi_dim(const gfi_index* h) { return h ? h->dim : 0; }
+
+int32_t gfi_reserve(gfi_index* h, int64_t n_rows) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  if (h->dim == 0) return fail(GFI_ERR_INDEX, "reserve before the dimension is known");
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  return grow(h, n_rows);
+}
+
+int32_t gfi_add(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n, int64_t dim) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (n < 0 || (n > 0 && (!ids || (!rows && dim > 0)))) return fail(GFI_ERR_INDEX, "bad arguments");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  if (h->dim == 0 && n > 0) {
+    if (dim <= 0) return fail(GFI_ERR_INDEX, "zero-dimensional vectors are not supported");
+    latch_dim(h, dim);
+  }
+  if (dim != h->dim) {
+    // FlatIndex::add never checks dimensions (flat_index.rs:38-41); remember the row so that searches
+    // fail with DimensionMismatch exactly as the per-pair check would (distance.rs:21-26).
+    int32_t rc = flush_locked(h);
+    if (rc != GFI_OK) return rc;
+    for (int64_t i = 0; i < n; ++i) {
+      erase_id(h, ids[i]);
+      h->odd_dim_rows[ids[i]] = dim;
+    }
+    return GFI_OK;
+  }
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  const int64_t chunk_rows = std::max<int64_t>(1, (64ll << 20) / ((int64_t)h->dpad * 4));
+  int64_t done = 0;
+  while (done < n) {
+    if (h->st_cap == 0) {
+      CU_TRY(h->st_rows.ensure((size_t)chunk_rows * h->dpad * 4));
+      CU_TRY(h->st_ids.ensure((size_t)chunk_rows * 8));
+      h->st_cap = chunk_rows;
+    }
+    const int64_t take = std::min(n - done, h->st_cap - h->st_n);
+    float* dst = h->st_rows.as<float>() + (size_t)h->st_n * h->dpad;
+    if (h->dpad == h->dim) {
+      memcpy(dst, rows + (size_t)done * dim, (size_t)take * dim * 4);
+    } else {
+      for (int64_t i = 0; i < take; ++i) {
+        memcpy(dst + (size_t)i * h->dpad, rows + (size_t)(done + i) * dim, (size_t)dim * 4);
+        memset(dst + (size_t)i * h->dpad + dim, 0, (size_t)(h->dpad - dim) * 4);
+      }
+    }
+    memcpy(h->st_ids.as<uint64_t>() + h->st_n, ids + done, (size_t)take * 8);
+    // an id staged twice in one batch must keep only the last copy: flush between duplicates is
+    // handled by erase_id at flush time only for already-flushed ids, so flush eagerly when the
+    // staging buffer is full or ids are not strictly increasing within the staged batch.
+    bool increasing = true;
+    const uint64_t* sid = h->st_ids.as<uint64_t>();
+    for (int64_t i = std::max<int64_t>(1, h->st_n); i < h->st_n + take; ++i)
+      if (sid[i] <= sid[i - 1]) { increasing = false; break; }
+    h->st_n += take;
+    done += take;
+    if (!increasing) {
+      // flush row by row segments so duplicates inside the staged batch resolve in order
+      const int64_t total = h->st_n;
+      std::vector<uint64_t> ids_copy(sid, sid + total);
+      std::vector<float> rows_copy(h->st_rows.as<float>(), h->st_rows.as<float>() + (size_t)total * h->dpad);
+      h->st_n = 0;
+      int64_t s0 = 0;
+      while (s0 < total) {
+        int64_t s1 = s0 + 1;
+        while (s1 < total && ids_copy[s1] > ids_copy[s1 - 1]) ++s1;
+        memcpy(h->st_rows.p, rows_copy.data() + (size_t)s0 * h->dpad, (size_t)(s1 - s0) * h->dpad * 4);
+        memcpy(h->st_ids.p, ids_copy.data() + s0, (size_t)(s1 - s0) * 8);
+        h->st_n = s1 - s0;
+        if ((rc = flush_locked(h)) != GFI_OK) return rc;
+        s0 = s1;
+      }
+    } else if (h->st_n == h->st_cap) {
+      if ((rc = flush_locked(h)) != GFI_OK) return rc;
+    }
+  }
+  return GFI_OK;
+}
+
+int32_t gfi_add_generated(gfi_index* h, uint32_t seed, uint64_t first_row, int64_t n, int32_t kind,
+                          uint64_t first_id) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (n <= 0) return GFI_OK;
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  if (h->dim == 0) return fail(GFI_ERR_INDEX, "gfi_add_generated needs an index created with a dimension");
+  int32_t rc;
+  if ((rc = flush_locked(h)) != GFI_OK) return rc;
+  if ((rc = grow(h, h->n_slots + n)) != GFI_OK) return rc;
+  const uint32_t slot0 = (uint32_t)h->n_slots;
+  // ids: first_id + i, written on device by a tiny fill via host chunks
+  {
+    const int64_t chunk = 1 << 20;
+    std::vector<uint64_t> tmp((size_t)std::min(chunk, n));
+    for (int64_t o = 0; o < n; o += chunk) {
+      const int64_t m = std::min(chunk, n - o);
+      for (int64_t i = 0; i < m; ++i) tmp[(size_t)i] = first_id + (uint64_t)(o + i);
+      CU_TRY(cudaMemcpyAsync(h->ids.as<uint64_t>() + slot0 + o, tmp.data(), (size_t)m * 8,
+                             cudaMemcpyHostToDevice, h->ingest_stream));
+      CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+    }
+  }
+  if (h->any_id && first_id <= h->max_id_seen)
+    return fail(GFI_ERR_INDEX, "gfi_add_generated: ids must be above every id already stored");
+  h->n_slots += n;
+  register_ids(h, nullptr, first_id, n, slot0);
+  if ((rc = ingest_slots(h, slot0, n, true, seed, first_row, kind)) != GFI_OK) return rc;
+  CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  if ((rc = read_counters(h)) != GFI_OK) return rc;
+  return upload_live(h);
+}
+
+int32_t gfi_remove(gfi_index* h, uint64_t id) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  if (h->odd_dim_rows.erase(id)) return GFI_OK;
+  if (h->st_n > 0) {
+    int32_t rc = flush_locked(h);
+    if (rc != GFI_OK) return rc;
+  }
+  erase_id(h, id);  // idempotent: FlatIndex::remove of a missing id is Ok(())
+  return GFI_OK;
+}
+
+int32_t gfi_flush(gfi_index* h) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  int32_t rc = flush_locked(h);
+  if (rc != GFI_OK) return rc;
+  if (h->needs_reorder) return compact_locked(h);
+  return GFI_OK;
+}
+
+int32_t gfi_compact(gfi_index* h) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  int32_t rc = flush_locked(h);
+  if (rc != GFI_OK) return rc;
+  return compact_locked(h);
+}
+
+int32_t gfi_get_vector(gfi_index* h, uint64_t id, float* out, int64_t cap, int64_t* out_dim) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  int32_t rc = flush_locked(h);
+  if (rc != GFI_OK) return rc;
+  uint32_t slot;
+  if (!lookup_slot(h, id, &slot)) return fail(GFI_ERR_INDEX, "vector not found");
+  if (out_dim) *out_dim = h->dim;
+  if (cap < h->dim) return fail(GFI_ERR_INDEX, "output buffer too small");
+  CU_TRY(cudaSetDevice(h->device));
+  CU_TRY(cudaMemcpy(out, h->x32.as<float>() + (size_t)slot * h->dpad, (size_t)h->dim * 4, cudaMemcpyDeviceToHost));
+  return GFI_OK;
+}
+
+static int32_t ensure_flushed(gfi_index* h) {
+  bool need;
+  {
+    std::shared_lock<std::shared_mutex> g(h->mu);
+    need = h->st_n > 0 || h->live_dirty_lo >= 0 || h->needs_reorder;
+  }
+  if (!need) return GFI_OK;
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  int32_t rc = flush_locked(h);
+  if (rc != GFI_OK) return rc;
+  if (h->needs_reorder) return compact_locked(h);
+  return GFI_OK;
+}
+
+int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                   const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
+                   uint32_t* out_counts, int64_t kstride) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (q < 0 || (q > 0 && (!queries || !ks || !out_counts))) return fail(GFI_ERR_INDEX, "bad arguments");
+  if (q == 0) return GFI_OK;
+  int32_t rc = ensure_flushed(h);
+  if (rc != GFI_OK) return rc;
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  ++h->n_search;
+  h->n_queries += q;
+  bool empty;
+  if ((rc = precheck(h, dim, &empty)) != GFI_OK) return rc;
+  uint32_t kmax = 0;
+  for (int64_t i = 0; i < q; ++i) kmax = std::max(kmax, ks[i]);
+  if (empty || kmax == 0) {
+    for (int64_t i = 0; i < q; ++i) out_counts[i] = 0;
+    return GFI_OK;
+  }
+  if ((int64_t)kmax > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
+  if (!out_ids || !out_dist) return fail(GFI_ERR_INDEX, "null output buffers");
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  SearchCtx* c = acquire_ctx(h);
+  if (!c) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
+  struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
+  cudaStream_t st = c->stream;
+  const uint32_t kout = std::min<uint32_t>(kmax, (uint32_t)std::min<int64_t>(kstride, 1 << 20));
+  const size_t mask_words = mask ? (size_t)((mask_bits + 63) / 64) : 0;
+  CU_TRY(c->q_in.ensure((size_t)q * dim * 4));
+  CU_TRY(c->ks.ensure((size_t)q * 4));
+  CU_TRY(c->out_ids.ensure((size_t)q * kout * 8));
+  CU_TRY(c->out_dist.ensure((size_t)q * kout * 4));
+  CU_TRY(c->out_counts.ensure((size_t)q * 4));
+  CU_TRY(c->h_q.ensure((size_t)q * dim * 4));
+  CU_TRY(c->h_ks.ensure((size_t)q * 4));
+  CU_TRY(c->h_ids.ensure((size_t)q * kout * 8));
+  CU_TRY(c->h_dist.ensure((size_t)q * kout * 4));
+  CU_TRY(c->h_counts.ensure((size_t)q * 4));
+  CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl)));
+  if (mask) CU_TRY(c->mask.ensure(mask_words * 8));
+  memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
+  memcpy(c->h_ks.p, ks, (size_t)q * 4);
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, c->h_q.p, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
+  if (mask) CU_TRY(cudaMemcpyAsync(c->mask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, st));
+  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax, mask ? c->mask.as<uint64_t>() : nullptr,
+               mask_bits, c->out_ids.as<uint64_t>(), c->out_dist.as<float>(), c->out_counts.as<uint32_t>(),
+               (int64_t)kout};
+  if ((rc = enqueue_search(h, c, a, st)) != GFI_OK) { cudaStreamSynchronize(st); return rc; }
+  CU_TRY(cudaMemcpyAsync(c->h_ids.p, c->out_ids.p, (size_t)q * kout * 8, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)q * kout * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(c->h_counts.p, c->out_counts.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(c->h_ctrl.p, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  prof_collect(h, c);
+  const Ctrl* hc = c->h_ctrl.as<Ctrl>();
+  h->n_fallback_q += hc->fb_count;
+  if ((rc = flags_to_status(hc->flags)) != GFI_OK) return rc;
+  const uint32_t* hcnt = c->h_counts.as<uint32_t>();
+  for (int64_t i = 0; i < q; ++i) {
+    out_counts[i] = hcnt[i];
+    memcpy(out_ids + i * kstride, c->h_ids.as<uint64_t>() + (size_t)i * kout, (size_t)hcnt[i] * 8);
+    memcpy(out_dist + i * kstride, c->h_dist.as<float>() + (size_t)i * kout, (size_t)hcnt[i] * 4);
+  }
+  return GFI_OK;
+}
+
+static thread_local SearchCtx* tl_dev_ctx = nullptr;
+static thread_local gfi_index* tl_dev_owner = nullptr;
+
+int32_t gfi_search_device(gfi_index* h, const float* d_queries, int64_t q, const uint32_t* d_ks, uint32_t kmax,
+                          const uint64_t* d_mask, int64_t mask_bits, uint64_t* d_out_ids, float* d_out_dist,
+                          uint32_t* d_out_counts, int64_t kstride, void* stream) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (q <= 0) return GFI_OK;
+  int32_t rc = ensure_flushed(h);
+  if (rc != GFI_OK) return rc;
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  ++h->n_search;
+  h->n_queries += q;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  if ((int64_t)kmax > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
+  if (tl_dev_ctx && tl_dev_owner != h) return fail(GFI_ERR_INDEX, "collect gfi_search_status first");
+  if (!tl_dev_ctx) {
+    tl_dev_ctx = acquire_ctx(h);
+    tl_dev_owner = h;
+    if (!tl_dev_ctx) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
+  }
+  SearchCtx* c = tl_dev_ctx;
+  cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  if (h->n_live == 0 || kmax == 0) {
+    CU_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)q * 4, st));
+    c->pending_status = true;
+    CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+    CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+    return GFI_OK;
+  }
+  SearchArgs a{d_queries, q, d_ks, kmax, d_mask, mask_bits, d_out_ids, d_out_dist, d_out_counts, kstride};
+  rc = enqueue_search(h, c, a, st);
+  c->pending_status = true;
+  // remember which stream to synchronise when the status is collected
+  c->h_ctrl.ensure(sizeof(Ctrl) + sizeof(cudaStream_t));
+  memcpy(c->h_ctrl.as<char>() + sizeof(Ctrl), &st, sizeof(cudaStream_t));
+  return rc;
+}
+
+int32_t gfi_search_status(gfi_index* h) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  SearchCtx* c = tl_dev_ctx;
+  if (!c || tl_dev_owner != h) return GFI_OK;
+  tl_dev_ctx = nullptr;
+  tl_dev_owner = nullptr;
+  struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  cudaStream_t st = c->stream;
+  if (c->h_ctrl.bytes >= sizeof(Ctrl) + sizeof(cudaStream_t))
+    memcpy(&st, c->h_ctrl.as<char>() + sizeof(Ctrl), sizeof(cudaStream_t));
+  CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl) + sizeof(cudaStream_t)));
+  CU_TRY(cudaMemcpyAsync(c->h_ctrl.p, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  c->pending_status = false;
+  prof_collect(h, c);
+  const Ctrl* hc = c->h_ctrl.as<Ctrl>();
+  h->n_fallback_q += hc->fb_count;
+  return flags_to_status(hc->flags);
+}
+
+int32_t gfi_merge_topk_device(const uint64_t* d_ids, const float* d_dist, const uint32_t* d_counts, int32_t G,
+                              int64_t q, int64_t kstride, const uint32_t* d_ks, uint64_t* d_out_ids,
+                              float* d_out_dist, uint32_t* d_out_counts, int64_t out_kstride, void* stream) {
+  CU_TRY(launch_merge(d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids, d_out_dist, d_out_counts,
+                      out_kstride, (cudaStream_t)stream));
+  return GFI_OK;
+}
+
+int32_t gfi_get_stats(gfi_index* h, gfi_stats* out) {
+  if (!h || !out) return fail(GFI_ERR_INDEX, "null argument");
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  out->n_slots = h->n_slots;
+  out->n_live = h->n_live;
+  out->searches = h->n_search;
+  out->queries = h->n_queries;
+  out->scan_queries = h->n_scan_q;
+  out->tensor_queries = h->n_tensor_q;
+  out->fallback_queries = h->n_fallback_q;
+  out->kernel_launches = h->n_launch;
+  out->bytes_fp32 = h->n_slots * (int64_t)h->dpad * 4;
+  out->bytes_fp16 = h->use_x16 ? h->n_slots * (int64_t)h->dpad16 * 2 : 0;
+  out->scan_kernel_ns = h->prof_ns[0];
+  out->scan_kernel_count = h->prof_cnt[0];
+  out->tensor_kernel_ns = h->prof_ns[1];
+  out->tensor_kernel_count = h->prof_cnt[1];
+  return GFI_OK;
+}
+
+int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
+  if (!h || !name) return fail(GFI_ERR_INDEX, "null argument");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  const std::string n(name);
+  if (n == "tensor_min_q") h->opt_tensor_min_q = (int)value;
+  else if (n == "tensor_min_rows") h->opt_tensor_min_rows = (int)value;
+  else if (n == "kp") h->opt_kp = (int)value;
+  else if (n == "hits") h->opt_hits = (int)value;
+  else if (n == "scan_qt") h->opt_scan_qt = (int)value;
+  else if (n == "grid") h->opt_grid = (int)value;
+  else if (n == "seed_rank") h->opt_seed_rank = (int)value;
+  else if (n == "profile") h->opt_profile = (int)value;
+  else return fail(GFI_ERR_INDEX, "unknown option: " + n);
+  return GFI_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+// Rebuilds the slot array: live rows only, ordered by internal id.  Caller holds the unique lock.
+int32_t compact_locked(gfi_index* h) {
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  if (h->n_slots == 0) { h->needs_reorder = false; return GFI_OK; }
+  // permutation: runs are keyed by id0 and disjoint, so walking the map yields ids in order
+  std::vector<uint32_t> perm;
+  perm.reserve((size_t)h->n_live);
+  std::map<uint64_t, Run> nruns;
+  bool identity = true;
+  for (auto& kv : h->runs) {
+    uint64_t id = kv.first;
+    for (uint32_t i = 0; i < kv.second.n; ++i, ++id) {
+      const uint32_t s = kv.second.slot0 + i;
+      if (!((h->h_live[s >> 5] >> (s & 31)) & 1u)) continue;
+      const uint32_t ns = (uint32_t)perm.size();
+      perm.push_back(s);
+      if (id != ns) identity = false;
+      if (!nruns.empty()) {
+        auto last = std::prev(nruns.end());
+        if (last->first + last->second.n == id && last->second.slot0 + last->second.n == ns) {
+          ++last->second.n;
+          continue;
+        }
+      }
+      nruns[id] = Run{ns, 1};
+    }
+  }
+  const int64_t n_out = (int64_t)perm.size();
+  const int64_t ncap = std::max<int64_t>(1024, (n_out + 255) / 256 * 256);
+  DevBuf d_perm, nx32, nx16, nids, nnorm, nsumsq, ncoef, nflags, nlive;
+  CU_TRY(d_perm.ensure((size_t)std::max<int64_t>(n_out, 1) * 4));
+  CU_TRY(nx32.ensure((size_t)ncap * h->dpad * 4));
+  CU_TRY(nids.ensure((size_t)ncap * 8));
+  CU_TRY(nnorm.ensure((size_t)ncap * 4));
+  CU_TRY(nsumsq.ensure((size_t)ncap * 4));
+  CU_TRY(nflags.ensure((size_t)ncap * 4));
+  if (h->use_x16) {
+    CU_TRY(nx16.ensure((size_t)ncap * h->dpad16 * 2));
+    CU_TRY(ncoef.ensure((size_t)ncap * 8));
+  }
+  const size_t words = (size_t)(ncap + 31) / 32;
+  CU_TRY(nlive.ensure(words * 4));
+  if (n_out > 0) {
+    CU_TRY(cudaMemcpyAsync(d_perm.p, perm.data(), (size_t)n_out * 4, cudaMemcpyHostToDevice, h->ingest_stream));
+    CU_TRY(launch_gather_rows(h->view(), d_perm.as<uint32_t>(), n_out, nx32.as<float>(),
+                              h->use_x16 ? nx16.as<__half>() : nullptr, nids.as<uint64_t>(), nnorm.as<float>(),
+                              nsumsq.as<float>(), h->use_x16 ? ncoef.as<float2>() : nullptr, h->ingest_stream));
+  }
+  std::vector<uint32_t> nh_live(words, 0u);
+  for (int64_t s = 0; s < n_out; ++s) nh_live[(size_t)s >> 5] |= 1u << (s & 31);
+  CU_TRY(cudaMemcpyAsync(nlive.p, nh_live.data(), words * 4, cudaMemcpyHostToDevice, h->ingest_stream));
+  CU_TRY(cudaMemsetAsync(nflags.p, 0, (size_t)ncap * 4, h->ingest_stream));
+  CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  d_perm.release();
+  auto swap_in = [](DevBuf& dst, DevBuf& src) { dst.release(); dst = src; src.p = nullptr; src.bytes = 0; };
+  swap_in(h->x32, nx32);
+  swap_in(h->ids, nids);
+  swap_in(h->norm, nnorm);
+  swap_in(h->sumsq, nsumsq);
+  swap_in(h->rowflags, nflags);
+  swap_in(h->live, nlive);
+  if (h->use_x16) { swap_in(h->x16, nx16); swap_in(h->coef, ncoef); }
+  h->cap = ncap;
+  h->n_slots = n_out;
+  h->n_live = n_out;
+  h->h_live.swap(nh_live);
+  h->runs.swap(nruns);
+  h->ids_identity = identity;
+  h->needs_reorder = false;
+  h->live_dirty_lo = h->live_dirty_hi = -1;
+  ++h->n_launch;
+  return GFI_OK;
+}
+
+}  // namespace

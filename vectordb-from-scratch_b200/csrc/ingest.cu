@@ -1,0 +1,217 @@
+// ingest.cu -- K4 `row_stats` (run once per stored row at flush time) and query preparation.
+//
+// The reference recomputes ||x|| for every (query,row) pair (src/distance.rs:48-49 calling
+// src/vector.rs:35-37); here it is computed once per row, with the reference's exact
+// sequential arithmetic so that the cosine epilogue can reuse it bit for bit.  The same
+// pass writes the fp16 shadow row used by the tcgen05 path (per-row power-of-two scale, so
+// conversion error is purely relative) and the per-row epilogue coefficients.
+#include <algorithm>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace gfi {
+
+namespace {
+
+constexpr uint32_t kRowZeroNorm = 1u, kRowUnsafe16 = 2u, kRowNonFinite = 4u;
+
+__device__ __forceinline__ int f32_exponent(float a) {  // floor(log2(a)) for finite a > 0
+  const int e = (int)((__float_as_uint(a) >> 23) & 0xffu);
+  return e == 0 ? -126 : e - 127;
+}
+
+__global__ void gen_rows_kernel(float* x32, int64_t first_slot, int64_t n, int d, int dpad, uint32_t seed,
+                                uint64_t first_row, int kind) {
+  const int64_t total = n * dpad;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / dpad;
+    const int c = (int)(i - r * dpad);
+    x32[(first_slot + r) * dpad + c] = c < d ? gen_elem(seed, first_row + (uint64_t)r, (uint32_t)c, kind) : 0.f;
+  }
+}
+
+__global__ void row_stats_kernel(const IngestParams p) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= p.n) return;
+  const int64_t slot = p.first_slot + r;
+  const float* x = p.x32 + slot * p.dpad;
+  float acc = -0.0f, maxabs = 0.f;
+  bool finite = true;
+  for (int i = 0; i < p.d; ++i) {
+    const float v = x[i];
+    acc = __fadd_rn(acc, __fmul_rn(v, v));
+    maxabs = fmaxf(maxabs, fabsf(v));
+    finite = finite && (fabsf(v) <= 3.4028234664e38f);
+  }
+  const float nrm = __fsqrt_rn(acc);
+  p.sumsq[slot] = acc;
+  p.norm[slot] = nrm;
+  uint32_t fl = 0;
+  if (nrm == 0.f) fl |= kRowZeroNorm;
+  if (!finite) fl |= kRowNonFinite | kRowUnsafe16;
+  float s_row = 1.f;
+  if (finite && maxabs > 0.f) {
+    const int se = 14 - f32_exponent(maxabs);
+    if (se > 100) fl |= kRowUnsafe16;  // too small for a representable power-of-two scale
+    s_row = __uint_as_float((uint32_t)(min(max(se, -100), 100) + 127) << 23);
+  }
+  p.zero_flags[slot] = fl;
+  if (p.x16) {
+    __half* h = p.x16 + slot * p.dpad16;
+    for (int i = 0; i < p.dpad16; ++i) {
+      float v = i < p.d ? x[i] * s_row : 0.f;
+      if (fabsf(v) < 6.103515625e-05f) v = 0.f;  // below 2^-14: flush (no fp16 subnormals on the MMA path)
+      h[i] = __float2half_rn(v);
+    }
+  }
+  if (p.coef) {
+    float2 c;
+    const float inv_s = 1.0f / s_row;  // exact: power of two
+    if (p.metric == kMetricL2) c = make_float2(-2.f * inv_s, acc);
+    else if (p.metric == kMetricCos) c = make_float2(nrm > 0.f ? -inv_s / nrm : 0.f, 0.f);
+    else c = make_float2(-inv_s, 0.f);
+    p.coef[slot] = c;
+  }
+}
+
+// One warp per query: pad/copy, batch max|q|, reference-exact sum of squares and norm.
+__global__ void prep_queries_kernel(const PrepQueriesParams p) {
+  const int qi = blockIdx.x;
+  const int lane = threadIdx.x;
+  const float* src = p.q_in + (size_t)qi * p.d;
+  float* dst = p.q32 + (size_t)qi * p.dpad;
+  float m = 0.f;
+  for (int c = lane; c < p.dpad; c += 32) {
+    const float v = c < p.d ? src[c] : 0.f;
+    dst[c] = v;
+    m = fmaxf(m, fabsf(v));  // NaN is ignored by fmaxf; NaN queries surface as NaN distances later
+  }
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if (lane == 0) {
+    if (p.qmaxabs) atomicMax(reinterpret_cast<unsigned int*>(p.qmaxabs), __float_as_uint(m));
+    float acc = -0.0f;
+    for (int i = 0; i < p.d; ++i) {
+      const float v = src[i];
+      acc = __fadd_rn(acc, __fmul_rn(v, v));
+    }
+    p.qsumsq[qi] = acc;
+    p.qnorm[qi] = __fsqrt_rn(acc);
+  }
+}
+
+__global__ void convert_queries16_kernel(const PrepQueriesParams p) {
+  const float qmax = *p.qmaxabs;
+  float s = 1.f;
+  if (qmax > 0.f && qmax <= 3.4028234664e38f)
+    s = __uint_as_float((uint32_t)(min(max(14 - f32_exponent(qmax), -100), 100) + 127) << 23);
+  const int64_t total = (int64_t)p.qpad * p.dpad16;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / p.dpad16), c = (int)(i - (int64_t)r * p.dpad16);
+    float v = (r < p.q && c < p.d) ? p.q32[(size_t)r * p.dpad + c] * s : 0.f;
+    if (fabsf(v) < 6.103515625e-05f) v = 0.f;
+    p.q16[i] = __float2half_rn(v);
+  }
+}
+
+__global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    p[i] = v;
+}
+
+// Compaction / re-ordering: out slot j <- in slot perm[j] (one warp per row).
+__global__ void gather_rows_kernel(const IndexView src, const uint32_t* perm, int64_t n_out, float* x32,
+                                   __half* x16, uint64_t* ids, float* norm, float* sumsq, float2* coef) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nw = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t j = w; j < n_out; j += nw) {
+    const int64_t s = perm[j];
+    for (int c = lane; c < src.dpad; c += 32) x32[j * src.dpad + c] = src.x32[s * src.dpad + c];
+    if (x16)
+      for (int c = lane; c < src.dpad16; c += 32) x16[j * src.dpad16 + c] = src.x16[s * src.dpad16 + c];
+    if (lane == 0) {
+      ids[j] = src.ids[s];
+      norm[j] = src.norm[s];
+      sumsq[j] = src.sumsq[s];
+      if (coef) coef[j] = src.coef[s];
+    }
+  }
+}
+
+// Folds the per-row flags of newly ingested rows into {zero-norm rows, fp16-unsafe rows, max ||x||}.
+__global__ void fold_rowflags_kernel(const uint32_t* rowflags, const float* norm, int64_t first, int64_t n,
+                                     uint32_t* counters) {
+  uint32_t z = 0, u = 0;
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t f = rowflags[first + i];
+    z += (f & kRowZeroNorm) ? 1u : 0u;
+    u += (f & kRowUnsafe16) ? 1u : 0u;
+    const float v = norm[first + i];
+    if (v == v && v <= 3.4028234664e38f) m = fmaxf(m, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    z += __shfl_xor_sync(0xffffffffu, z, o);
+    u += __shfl_xor_sync(0xffffffffu, u, o);
+    m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (z) atomicAdd(&counters[0], z);
+    if (u) atomicAdd(&counters[1], u);
+    atomicMax(&counters[2], __float_as_uint(m));
+  }
+}
+
+}  // namespace
+
+cudaError_t launch_fold_rowflags(const uint32_t* rowflags, const float* norm, int64_t first, int64_t n,
+                                 uint32_t* counters, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  fold_rowflags_kernel<<<blocks, 256, 0, st>>>(rowflags, norm, first, n, counters);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_ingest(const IngestParams& p, cudaStream_t st) {
+  if (p.n <= 0) return cudaSuccess;
+  if (p.gen) {
+    const int64_t total = p.n * p.dpad;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 16);
+    gen_rows_kernel<<<blocks, 256, 0, st>>>(p.x32, p.first_slot, p.n, p.d, p.dpad, p.seed, p.first_row, p.kind);
+  }
+  const int64_t blocks = (p.n + 127) / 128;
+  row_stats_kernel<<<(unsigned)blocks, 128, 0, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st) {
+  if (p.q <= 0) return cudaSuccess;
+  prep_queries_kernel<<<p.q, 32, 0, st>>>(p);
+  if (p.q16) {
+    const int64_t total = (int64_t)p.qpad * p.dpad16;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
+    convert_queries16_kernel<<<blocks, 256, 0, st>>>(p);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+  fill_u32_kernel<<<blocks, 256, 0, st>>>(p, v, n);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_gather_rows(const IndexView& src, const uint32_t* perm, int64_t n_out, float* x32,
+                               __half* x16, uint64_t* ids, float* norm, float* sumsq, float2* coef,
+                               cudaStream_t st) {
+  if (n_out <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((n_out + 7) / 8, 148 * 8);
+  gather_rows_kernel<<<blocks, 256, 0, st>>>(src, perm, n_out, x32, x16, ids, norm, sumsq, coef);
+  return cudaGetLastError();
+}
+
+}  // namespace gfi

@@ -1,0 +1,143 @@
+// kernels.h -- host-visible launch wrappers and shared parameter structs of libgfi.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace gfi {
+
+constexpr int kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2;
+
+// ---- error word shared by all kernels of one search call ---------------------------
+constexpr uint32_t kFlagNaN = 1u;        // a distance is NaN (reference: panic at flat_index.rs:62)
+constexpr uint32_t kFlagZeroNorm = 2u;   // cosine with a zero-norm eligible row / query (distance.rs:51-55)
+constexpr uint32_t kFlagOverflow = 4u;   // a candidate buffer overflowed (tensor path -> scan fallback)
+constexpr uint32_t kFlagInternal = 8u;   // watchdog / internal inconsistency
+
+// Read-only device view of the index, passed by value to kernels.
+struct IndexView {
+  const float* x32;      // [n_slots][dpad]   fp32 rows, zero padded to dpad (multiple of 4)
+  const __half* x16;     // [n_slots][dpad16] per-row power-of-two scaled fp16 shadow (tensor path) or null
+  const uint64_t* ids;   // [n_slots]         internal id of each slot (slot order == id order)
+  const float* norm;     // [n_slots]         reference-exact ||x||   (src/vector.rs:35-37)
+  const float* sumsq;    // [n_slots]         reference-exact sum x^2 (pre-sqrt)
+  const float2* coef;    // [n_slots]         tensor epilogue: score = acc * coef.x * inv_qscale + coef.y
+  const uint32_t* live;  // [ceil(n_slots/32)] 1 = live, 0 = tombstone
+  int64_t n_slots;
+  int d, dpad, dpad16;
+  int metric;
+  int ids_identity;      // ids[s] == s for every slot (mask can be indexed by slot)
+};
+
+struct MaskView {
+  const uint64_t* bits;  // eligibility by INTERNAL ID, or null
+  int64_t nbits;
+};
+
+// ---- K1: streaming scan + per-warp top-K ---------------------------------------------
+constexpr int kScanConsumerWarps = 8;
+constexpr int kScanThreads = (kScanConsumerWarps + 1) * 32;
+constexpr int kScanStages = 4;
+constexpr int kScanStageFloats = 8192;  // 32 KB per stage
+constexpr int kScanSegFloats = 256;     // column segment when a 32-row block does not fit a stage
+
+struct ScanParams {
+  IndexView iv;
+  MaskView mask;
+  const float* q32;         // [*, dpad] padded queries
+  const float* qnorm;       // exact ||q|| per query (cosine zero check)
+  const uint32_t* qlist;    // indices of the queries to process, or null (= 0..nq-1)
+  const uint32_t* nq_dev;   // device-side query count (predicated fallback launch), or null
+  int nq;                   // host-side query count (used when nq_dev == null)
+  int K;                    // per-query list length: power of two, 32..1024
+  const uint64_t* floor64;  // per-query exclusive lower bound on keys (paged large-k), or null
+  uint64_t* cand;           // [q][cand_stride] packed keys out (gridDim.x * K per query)
+  uint32_t* cand_cnt;       // [q]
+  int64_t cand_stride;
+  uint32_t* flags;
+  int rows_per_stage, seg_floats, nseg;
+};
+// QT = queries sharing one pass over the database (1,2,4,8).
+cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st);
+size_t scan_smem_bytes(int QT, int dpad, int K);
+
+// ---- ingest / query preparation ------------------------------------------------------
+struct IngestParams {
+  float* x32; __half* x16; float* norm; float* sumsq; float2* coef; uint32_t* zero_flags;
+  int64_t first_slot, n;
+  int d, dpad, dpad16, metric;
+  // generated rows (x32 is written by the kernel) when gen != 0
+  int gen; uint32_t seed; uint64_t first_row; int kind;
+};
+cudaError_t launch_ingest(const IngestParams& p, cudaStream_t st);
+
+struct PrepQueriesParams {
+  const float* q_in;   // [q][d] unpadded
+  float* q32;          // [q][dpad]
+  __half* q16;         // [qpad][dpad16] (rows >= q zeroed) or null
+  float* qnorm; float* qsumsq;
+  float* qmaxabs;      // [1] max |q| over the batch (for the common fp16 scale)
+  int q, qpad, d, dpad, dpad16;
+};
+cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st);
+
+// ---- K3: select + reference-exact rerank + certification -----------------------------
+struct SelectParams {
+  IndexView iv;
+  const float* q32; const float* qnorm; const float* qsumsq;
+  const uint32_t* ks;         // per-query k
+  const uint32_t* qlist;      // null = all
+  const uint32_t* nq_dev; int nq;
+  const uint64_t* cand; const uint32_t* cand_cnt; int64_t cand_stride;
+  int KP;                     // candidates reranked per query (power of two <= 1024)
+  // certification (tensor path): every row that is not a candidate has approx score >= cutoff
+  int certify;                // 0 = scan path (never falls back), 1 = tensor path
+  const float* thresh;        // per-query score threshold used by the tensor kernel
+  float eps_rel;              // relative error bound of the approximate dot product
+  const float* qmaxabs;       // batch max |q| (fp16 common scale), tensor path
+  float xnorm_max;            // max ||x|| over rows ever inserted
+  uint32_t* fb_count; uint32_t* fb_list;  // uncertified queries are appended here
+  uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
+  uint32_t* flags;
+  uint32_t* uncertified;      // counter (stats)
+};
+cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st);
+
+// ---- K5: merge of per-shard results ---------------------------------------------------
+cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t* counts, int G, int64_t q,
+                         int64_t kstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,
+                         uint32_t* out_counts, int64_t out_kstride, cudaStream_t st);
+
+// ---- K2: tcgen05 GEMM + fused threshold filter ----------------------------------------
+struct GemmParams {
+  IndexView iv;
+  MaskView mask;
+  const void* tmap_x;   // CUtensorMap (device-visible copy lives in kernel param space)
+  const void* tmap_q;
+  const float* qmaxabs; // batch max |q|
+  const float* qsumsq;
+  int q, num_m_tiles;
+  int64_t num_n_tiles;
+  // seed mode: per (sample tile, query) the R smallest scores; main mode: threshold filter
+  int seed_mode; int64_t seed_tiles, seed_stride;
+  float* seeds;         // [q][seed_tiles][R]
+  const float* thresh;  // [q]
+  uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
+  uint32_t* flags;
+};
+constexpr int kSeedR = 8;
+cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
+                             cudaStream_t st);
+struct SeedFinalizeParams {
+  const float* seeds; int q; int64_t seed_tiles; int rank; float* thresh;
+};
+cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st);
+size_t gemm_smem_bytes();
+
+// misc
+cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st);
+cudaError_t launch_gather_rows(const IndexView& src, const uint32_t* perm, int64_t n_out, float* x32,
+                               __half* x16, uint64_t* ids, float* norm, float* sumsq, float2* coef,
+                               cudaStream_t st);
+
+}  // namespace gfi

@@ -1,0 +1,193 @@
+"""GpuFlatIndex -- ctypes mirror of the reference's `Index` trait implemented by libgfi.
+
+Method names, argument meaning and error behaviour follow `trait Index`
+(reference src/index.rs:11-35) and `FlatIndex` (src/flat_index.rs:12-74); the two additive
+batch/mask methods are the defaulted trait extensions SURVEY.md section 8(b) B5 describes.
+"""
+import ctypes
+import enum
+
+import numpy as np
+
+from . import native
+from .errors import DimensionMismatch, InvalidVector, IndexError_, NaNDistance
+
+
+class DistanceMetric(enum.IntEnum):
+    """reference src/distance.rs:9-16"""
+    Euclidean = 0
+    Cosine = 1
+    DotProduct = 2
+
+
+def _raise(L, rc):
+    msg = (L.gfi_last_error() or b"").decode()
+    if rc == 1:
+        e, a = ctypes.c_int64(), ctypes.c_int64()
+        L.gfi_last_mismatch(ctypes.byref(e), ctypes.byref(a))
+        raise DimensionMismatch(e.value, a.value)
+    if rc == 2:
+        raise InvalidVector(msg)
+    if rc == 4:
+        raise NaNDistance(msg)
+    raise IndexError_(msg)
+
+
+def pack_mask(bits):
+    """bool[n] indexed by internal id -> u64 words (bit id%64 of word id//64)."""
+    bits = np.asarray(bits, dtype=bool)
+    n = bits.shape[0]
+    pad = (-n) % 64
+    b = np.concatenate([bits, np.zeros(pad, dtype=bool)]).reshape(-1, 64)
+    w = (b.astype(np.uint64) << np.arange(64, dtype=np.uint64)).sum(axis=1, dtype=np.uint64)
+    return np.ascontiguousarray(w, dtype=np.uint64), n
+
+
+class GpuFlatIndex:
+    """Drop-in for FlatIndex behind `trait Index`.  All compute runs in libgfi.so on a B200."""
+
+    def __init__(self, metric=DistanceMetric.Euclidean, dim=0, device=0, flags=0):
+        self._L = native.lib()
+        self._h = ctypes.c_void_p()
+        rc = self._L.gfi_create(ctypes.byref(self._h), int(metric), int(dim), int(device), int(flags))
+        if rc:
+            self._h = None
+            _raise(self._L, rc)
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.gfi_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc):
+        if rc:
+            _raise(self._L, rc)
+
+    # -- trait Index --
+    def add(self, id, vector):
+        """Index::add(&mut self, id, vector) (src/index.rs:13)."""
+        v = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        ids = np.array([id], dtype=np.uint64)
+        self._chk(self._L.gfi_add(self._h, ids.ctypes.data, v.ctypes.data if v.size else None, 1, v.size))
+
+    def add_batch(self, ids, rows):
+        """Bulk form of Index::add (one C-ABI call for n rows)."""
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        if rows.ndim != 2:
+            raise ValueError("rows must be n x d")
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        assert ids.shape[0] == rows.shape[0]
+        self._chk(self._L.gfi_add(self._h, ids.ctypes.data, rows.ctypes.data, rows.shape[0], rows.shape[1]))
+
+    def add_generated(self, seed, first_row, n, kind, first_id):
+        self._chk(self._L.gfi_add_generated(self._h, seed, first_row, n, kind, first_id))
+
+    def remove(self, id):
+        """Index::remove (src/index.rs:16): idempotent."""
+        self._chk(self._L.gfi_remove(self._h, int(id)))
+
+    def get_vector(self, id):
+        """Index::get_vector (src/index.rs:23): the stored row or None."""
+        d = max(int(self._L.gfi_dim(self._h)), 1)
+        out = np.empty(d, dtype=np.float32)
+        od = ctypes.c_int64()
+        rc = self._L.gfi_get_vector(self._h, int(id), out.ctypes.data, d, ctypes.byref(od))
+        if rc:
+            return None
+        return out[:od.value]
+
+    def metric(self):
+        return DistanceMetric(self._L.gfi_metric(self._h))
+
+    def len(self):
+        return int(self._L.gfi_len(self._h))
+
+    __len__ = len
+
+    def is_empty(self):
+        return self.len() == 0
+
+    def dim(self):
+        return int(self._L.gfi_dim(self._h))
+
+    def search(self, query, k):
+        """Index::search (src/index.rs:20): list of (id, distance), ascending distance."""
+        return self.search_batch([(query, k)])[0]
+
+    # -- additive, defaulted extensions --
+    def search_batch(self, queries, mask=None):
+        """queries: list of (vector, k).  One C-ABI call; per-query k as in
+        VectorStore::search_batch (src/storage.rs:302-310)."""
+        if len(queries) == 0:
+            return []
+        dims = {len(np.asarray(q).reshape(-1)) for q, _ in queries}
+        if len(dims) != 1:
+            # the reference checks each query separately; the first mismatching one fails the batch
+            out = []
+            for qv, k in queries:
+                out.append(self.search_batch([(qv, k)], mask=mask)[0])
+            return out
+        qs = np.ascontiguousarray(np.stack([np.asarray(q, dtype=np.float32).reshape(-1) for q, _ in queries]))
+        ks = np.array([int(k) for _, k in queries], dtype=np.uint32)
+        ids, dist, cnt = self.search_arrays(qs, ks, mask=mask)
+        return [[(int(ids[i, j]), float(dist[i, j])) for j in range(cnt[i])] for i in range(len(queries))]
+
+    def search_arrays(self, queries, ks, mask=None):
+        """Array form: queries [q,d] f32, ks [q] u32 (or int) -> (ids [q,kmax], dist [q,kmax], counts [q])."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        q, d = qs.shape
+        ks = np.ascontiguousarray(np.broadcast_to(np.asarray(ks, dtype=np.uint32), (q,)))
+        kmax = max(int(ks.max()) if q else 0, 1)
+        out_ids = np.zeros((q, kmax), dtype=np.uint64)
+        out_dist = np.zeros((q, kmax), dtype=np.float32)
+        cnt = np.zeros(q, dtype=np.uint32)
+        mptr, mbits = None, 0
+        if mask is not None:
+            words, mbits = pack_mask(mask)
+            mptr = words.ctypes.data
+        self._chk(self._L.gfi_search(self._h, qs.ctypes.data if qs.size else None, q, d, ks.ctypes.data, mptr,
+                                     mbits, out_ids.ctypes.data, out_dist.ctypes.data, cnt.ctypes.data, kmax))
+        return out_ids, out_dist, cnt
+
+    def search_masked(self, query, k, eligible):
+        """FlatIndex::search over the rows whose internal id is eligible (filter push-down)."""
+        return self.search_batch([(query, k)], mask=eligible)[0]
+
+    # -- device-pointer forms (multi-GPU plumbing, HBM-resident benchmark) --
+    def search_device(self, d_queries, q, d_ks, kmax, d_out_ids, d_out_dist, d_out_counts, kstride, stream=0,
+                      d_mask=0, mask_bits=0):
+        self._chk(self._L.gfi_search_device(self._h, d_queries, q, d_ks, kmax, d_mask or None, mask_bits,
+                                            d_out_ids, d_out_dist, d_out_counts, kstride, stream or None))
+
+    def search_status(self):
+        self._chk(self._L.gfi_search_status(self._h))
+
+    def merge_topk_device(self, d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids, d_out_dist, d_out_counts,
+                          out_kstride, stream=0):
+        self._chk(self._L.gfi_merge_topk_device(d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids,
+                                                d_out_dist, d_out_counts, out_kstride, stream or None))
+
+    # -- maintenance / introspection --
+    def flush(self):
+        self._chk(self._L.gfi_flush(self._h))
+
+    def reserve(self, n_rows):
+        self._chk(self._L.gfi_reserve(self._h, int(n_rows)))
+
+    def compact(self):
+        self._chk(self._L.gfi_compact(self._h))
+
+    def set_option(self, name, value):
+        self._chk(self._L.gfi_set_option(self._h, name.encode(), int(value)))
+
+    def stats(self):
+        s = native.GfiStats()
+        self._chk(self._L.gfi_get_stats(self._h, ctypes.byref(s)))
+        return {n: getattr(s, n) for n, _ in native.GfiStats._fields_}
