@@ -167,7 +167,10 @@ def main():
     out_d = torch.zeros((q, k), dtype=torch.float32, device=dev)
     out_c = torch.zeros((q,), dtype=torch.int32, device=dev)
     m_ids, m_d, m_c = torch.zeros_like(out_ids), torch.zeros_like(out_d), torch.zeros_like(out_c)
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-legacy) stream: libgfi launches on the handle it is given and torch events time that stream
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
 
     def local_search(_q, _k):
         idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, out_ids.data_ptr(), out_d.data_ptr(),

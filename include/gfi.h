@@ -160,6 +160,11 @@ typedef struct gfi_stats {
 } gfi_stats;
 int32_t gfi_get_stats(gfi_index *h, gfi_stats *out);
 
+/* Test hook: the raw approximate scores of the tcgen05 candidate pass for every (query, slot) pair,
+ * out[q][out_stride] with out_stride >= n_slots rounded up to 256 (small inputs only).  L2: ||x||^2 - 2 q.x
+ * (without ||q||^2); cosine: -q.x/||x||; dot: -q.x.  Ineligible slots read +inf. */
+int32_t gfi_debug_tensor_scores(gfi_index *h, const float *queries, int64_t q, float *out, int64_t out_stride);
+
 /* Tuning knobs for experiments (name/value); returns GFI_ERR_INDEX for unknown names. */
 int32_t gfi_set_option(gfi_index *h, const char *name, int64_t value);
 

@@ -331,7 +331,9 @@ def test_device_search_and_merge_kernel():
     all_d = torch.zeros((G, q, k), dtype=torch.float32, device="cuda")
     all_c = torch.zeros((G, q), dtype=torch.int32, device="cuda")
     shards = []
-    stream = torch.cuda.current_stream().cuda_stream
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    stream = ts.cuda_stream
     for g in range(G):
         lo, hi = bounds[g], bounds[g + 1]
         idx = build("euclidean", rows[lo:hi], ids=np.arange(lo, hi, dtype=np.uint64))

@@ -186,6 +186,7 @@ struct gfi_index {
   int opt_tensor_min_rows = 8192;
   int opt_seed_rank = 8;
   int opt_profile = 0;
+  int opt_gemm_debug = 0;
   std::atomic<int64_t> prof_ns[2] = {{0}, {0}}, prof_cnt[2] = {{0}, {0}};
 
   IndexView view() const {
@@ -675,6 +676,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   gp.flags = &ctrl->flags;
   gp.seed_tiles = seed_tiles;
   gp.seed_stride = seed_stride;
+  gp.debug = h->opt_gemm_debug;
   // seed pass
   gp.seed_mode = 1;
   CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, seed_tiles * num_m_tiles), st));
@@ -1121,6 +1123,59 @@ int32_t gfi_merge_topk_device(const uint64_t* d_ids, const float* d_dist, const 
   return GFI_OK;
 }
 
+int32_t gfi_debug_tensor_scores(gfi_index* h, const float* queries, int64_t q, float* out, int64_t out_stride) {
+  if (!h || !queries || !out || q <= 0) return fail(GFI_ERR_INDEX, "bad arguments");
+  int32_t rc = ensure_flushed(h);
+  if (rc != GFI_OK) return rc;
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  if (!h->use_x16 || h->n_slots == 0 || get_encode_fn() == nullptr) return fail(GFI_ERR_INDEX, "tensor path unavailable");
+  const int64_t npad = (h->n_slots + 255) / 256 * 256;
+  if (out_stride < npad) return fail(GFI_ERR_INDEX, "out_stride must be >= n_slots rounded up to 256");
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  SearchCtx* c = acquire_ctx(h);
+  if (!c) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
+  struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
+  cudaStream_t st = c->stream;
+  const int qi = (int)q, qpad = (qi + 127) / 128 * 128;
+  CU_TRY(c->q_in.ensure((size_t)q * h->dim * 4));
+  CU_TRY(c->q32.ensure((size_t)q * h->dpad * 4));
+  CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
+  CU_TRY(c->qnorm.ensure((size_t)q * 4));
+  CU_TRY(c->qsumsq.ensure((size_t)q * 4));
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  CU_TRY(c->seeds.ensure((size_t)q * out_stride * 4));
+  CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, queries, (size_t)q * h->dim * 4, cudaMemcpyHostToDevice, st));
+  Ctrl* ctrl = c->ctrl.as<Ctrl>();
+  PrepQueriesParams pq{};
+  pq.q_in = c->q_in.as<float>(); pq.q32 = c->q32.as<float>(); pq.q16 = c->q16.as<__half>();
+  pq.qnorm = c->qnorm.as<float>(); pq.qsumsq = c->qsumsq.as<float>();
+  pq.qmaxabs = reinterpret_cast<float*>(&ctrl->qmaxabs_bits);
+  pq.q = qi; pq.qpad = qpad; pq.d = (int)h->dim; pq.dpad = h->dpad; pq.dpad16 = h->dpad16;
+  CU_TRY(launch_prep_queries(pq, st));
+  IndexView iv = h->view();
+  CUtensorMap tmx, tmq;
+  if (!make_tmap_2d(&tmx, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 256) ||
+      !make_tmap_2d(&tmq, c->q16.p, (uint64_t)h->dpad16, (uint64_t)qpad, (uint64_t)h->dpad16 * 2, 64, 128))
+    return fail(GFI_ERR_INDEX, "cuTensorMapEncodeTiled failed");
+  GemmParams gp{};
+  gp.iv = iv;
+  gp.mask = MaskView{nullptr, 0};
+  gp.qmaxabs = reinterpret_cast<const float*>(&ctrl->qmaxabs_bits);
+  gp.qsumsq = c->qsumsq.as<float>();
+  gp.q = qi;
+  gp.num_m_tiles = qpad / 128;
+  gp.num_n_tiles = npad / 256;
+  gp.seed_mode = 2;
+  gp.seed_stride = out_stride;
+  gp.seeds = c->seeds.as<float>();
+  gp.flags = &ctrl->flags;
+  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(h->sm_count, gp.num_n_tiles * gp.num_m_tiles), st));
+  CU_TRY(cudaMemcpyAsync(out, c->seeds.p, (size_t)q * out_stride * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  return GFI_OK;
+}
+
 int32_t gfi_get_stats(gfi_index* h, gfi_stats* out) {
   if (!h || !out) return fail(GFI_ERR_INDEX, "null argument");
   std::shared_lock<std::shared_mutex> g(h->mu);
@@ -1153,6 +1208,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "grid") h->opt_grid = (int)value;
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "profile") h->opt_profile = (int)value;
+  else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
   else return fail(GFI_ERR_INDEX, "unknown option: " + n);
   return GFI_OK;
 }

@@ -82,7 +82,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const IndexView& iv = p.iv;
   const int num_kb = (iv.dpad16 + BK - 1) / BK;
-  const int64_t n_items = (p.seed_mode ? p.seed_tiles : p.num_n_tiles) * p.num_m_tiles;
+  const int64_t n_items = (p.seed_mode == 1 ? p.seed_tiles : p.num_n_tiles) * p.num_m_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -114,15 +114,20 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int64_t nt_idx = w / p.num_m_tiles;
       const int m_tile = (int)(w - nt_idx * p.num_m_tiles);
-      const int64_t n_tile = p.seed_mode ? nt_idx * p.seed_stride : nt_idx;
+      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         if (lane == 0) {
-          mbar_arrive_expect_tx(&full[s], kABytes + kBBytes);
-          tma_load_2d(sA + (size_t)s * kABytes, &tmq, kb * BK, m_tile * BM, &full[s]);
-          tma_load_2d(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN), &full[s]);
+          // p.debug (timing experiments only, results invalid): bit0 / bit1 stop re-loading A / B once the
+          // ring has been filled once, to separate the load path from the MMA and epilogue cost.
+          const bool ldA = !((p.debug & 1) && it >= (uint32_t)kStages);
+          const bool ldB = !((p.debug & 2) && it >= (uint32_t)kStages);
+          if (ldA || ldB) mbar_arrive_expect_tx(&full[s], (ldA ? kABytes : 0) + (ldB ? kBBytes : 0));
+          else mbar_arrive(&full[s]);
+          if (ldA) tma_load_2d(sA + (size_t)s * kABytes, &tmq, kb * BK, m_tile * BM, &full[s]);
+          if (ldB) tma_load_2d(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN), &full[s]);
         }
         __syncwarp();
       }
@@ -165,7 +170,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       const int64_t nt_idx = w / p.num_m_tiles;
       const int m_tile = (int)(w - nt_idx * p.num_m_tiles);
-      const int64_t n_tile = p.seed_mode ? nt_idx * p.seed_stride : nt_idx;
+      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
       // stage the per-row epilogue coefficients of this tile (2 rows per thread)
@@ -190,7 +195,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       }
       named_bar_sync(2, kEpiThreads);
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
-      if (!p.seed_mode && qidx < p.q) thr = p.thresh[qidx];
+      if (p.seed_mode == 0 && qidx < p.q) thr = p.thresh[qidx];
       float sd[kSeedR];
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = __int_as_float(0x7f800000);
@@ -199,11 +204,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         tmem_ld_wait();
-        if (p.seed_mode) {
+        if (p.seed_mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float2 cf = cs[c0 + j];
@@ -216,6 +221,16 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
                 sd[i - 1] = lo;
                 sd[i] = hi;
               }
+            }
+          }
+        } else if (p.seed_mode == 2) {
+          // debug dump of every approximate score (tests only; small inputs)
+          if (qidx < p.q) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float2 cf = cs[c0 + j];
+              p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + c0 + j)] =
+                  fmaf(__uint_as_float(r[j]), cf.x, cf.y);
             }
           }
         } else {
@@ -239,7 +254,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
-      if (p.seed_mode && qidx < p.q) {
+      if (p.seed_mode == 1 && qidx < p.q) {
         float* out = p.seeds + ((size_t)qidx * p.seed_tiles + nt_idx) * kSeedR;
 #pragma unroll
         for (int i = 0; i < kSeedR; ++i) out[i] = sd[i];

@@ -124,6 +124,7 @@ struct GemmParams {
   const float* thresh;  // [q]
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
   uint32_t* flags;
+  int debug;            // timing experiments only (see gemm_topk.cu)
 };
 constexpr int kSeedR = 8;
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,

@@ -187,6 +187,16 @@ class GpuFlatIndex:
     def set_option(self, name, value):
         self._chk(self._L.gfi_set_option(self._h, name.encode(), int(value)))
 
+    def debug_tensor_scores(self, queries):
+        """Raw approximate scores of the tcgen05 pass, [q, n_slots] (test hook)."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        self.flush()
+        n = self.stats()["n_slots"]
+        npad = (n + 255) // 256 * 256
+        out = np.empty((qs.shape[0], npad), dtype=np.float32)
+        self._chk(self._L.gfi_debug_tensor_scores(self._h, qs.ctypes.data, qs.shape[0], out.ctypes.data, npad))
+        return out[:, :n]
+
     def stats(self):
         s = native.GfiStats()
         self._chk(self._L.gfi_get_stats(self._h, ctypes.byref(s)))

@@ -34,10 +34,11 @@ class ShardedSearch:
         if self.world == 1:
             return ids, d, cnt
         G = self.world
-        all_ids = torch.empty((G,) + tuple(ids.shape), dtype=ids.dtype, device=ids.device)
-        all_d = torch.empty((G,) + tuple(d.shape), dtype=d.dtype, device=d.device)
-        all_c = torch.empty((G,) + tuple(cnt.shape), dtype=cnt.dtype, device=cnt.device)
-        dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_d, d.contiguous(), group=self.group)
-        dist.all_gather_into_tensor(all_c, cnt.contiguous(), group=self.group)
+        # concatenated along dim 0 (accepted by both NCCL and gloo), viewed as [G, q, ...] afterwards
+        def gather(t):
+            t = t.contiguous()
+            out = torch.empty((G * t.shape[0],) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            dist.all_gather_into_tensor(out, t, group=self.group)
+            return out.view((G,) + tuple(t.shape))
+        all_ids, all_d, all_c = gather(ids), gather(d), gather(cnt)
         return self.merge(all_ids, all_d, all_c, ks)
