@@ -559,16 +559,24 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   if ((int64_t)QT * h->dpad > 16384) return fail(GFI_ERR_INDEX, "dimension too large (max 16384)");
   if (h->opt_scan_qt > 0) QT = std::min(QT, h->opt_scan_qt);
   if (!tensor_ok) { while (QT > 1 && QT / 2 >= q) QT >>= 1; }
-  int R, segf, nseg;
-  if (h->dpad * 32 <= kScanStageFloats) {
-    R = (kScanStageFloats / h->dpad) / 32 * 32;
+  // Ring geometry.  A stage is one contiguous bulk copy whenever whole rows fit (the TMA engine's
+  // per-copy cost is what limits small copies): rows <= 1 KB use 8 lanes per row and 32*m rows per
+  // stage; longer rows use one warp per row and 8*m rows per stage; rows beyond 4 KB are cut into
+  // 4 KB column segments (8 copies per stage).
+  int R, segf, nseg, lpr;
+  if (h->dpad <= 256) {
+    lpr = 8;
+    R = std::max(32, (kScanStageFloats / h->dpad) / 32 * 32);
     segf = h->dpad;
     nseg = 1;
   } else {
-    R = 32;
-    segf = kScanSegFloats;
-    nseg = (h->dpad + kScanSegFloats - 1) / kScanSegFloats;
+    lpr = 32;
+    segf = std::min(h->dpad, 1024);
+    nseg = (h->dpad + segf - 1) / segf;
+    R = nseg == 1 ? 8 * std::max(1, std::min(4, kScanStageFloats / (8 * segf))) : 8;
   }
+  const size_t scan_fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
+  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(kScanMaxStages, (227 * 1024 - scan_fixed) / (kScanStageFloats * 4)));
   const int64_t nblocks = (h->n_slots + R - 1) / R;
   const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
   const int64_t scan_stride = (int64_t)scan_grid * K;
@@ -587,6 +595,8 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
     sp.rows_per_stage = R;
     sp.seg_floats = segf;
     sp.nseg = nseg;
+    sp.lanes_per_row = lpr;
+    sp.nstages = nstages;
   };
   auto fill_select = [&](SelectParams& s, DevBuf& cand, DevBuf& cnt, int64_t stride, int KP) {
     s.iv = iv;

@@ -165,6 +165,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     const int et = (warp - 2) * 32 + lane;    // 0..127 among epilogue threads
     const int mrow = quarter * 32 + lane;     // row of the 128-query tile owned by this thread
     const float inv_sq = pow2_scale_inv(*p.qmaxabs);
+    const float kInf = __int_as_float(0x7f800000);
+
+    // per-row epilogue coefficients (a, b) of rows et and et+128 of an item's tile; ineligible rows
+    // (beyond the index, tombstoned, filtered out) get (0, +inf) so they can never pass a threshold
+    auto load_coef = [&](int64_t w, float2 (&c)[2]) {
+      const int64_t nt_idx = w / p.num_m_tiles;
+      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+#pragma unroll
+      for (int rr = 0; rr < 2; ++rr) {
+        const int64_t slot = n_tile * BN + et + rr * kEpiThreads;
+        c[rr] = make_float2(0.f, kInf);
+        if (slot < iv.n_slots) {
+          bool elig = (iv.live[slot >> 5] >> (slot & 31)) & 1u;
+          if (elig && p.mask.bits) {
+            const uint64_t id = iv.ids_identity ? (uint64_t)slot : iv.ids[slot];
+            elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
+          }
+          if (elig) {
+            c[rr] = iv.coef[slot];
+            c[rr].x *= inv_sq;
+          }
+        }
+      }
+    };
+
+    float2 cnext[2];
+    if ((int64_t)blockIdx.x < n_items) load_coef(blockIdx.x, cnext);
     uint32_t ai = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
@@ -173,32 +200,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
-      // stage the per-row epilogue coefficients of this tile (2 rows per thread)
       float2* cs = sCoef + as * BN;
-#pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int r = et + rr * kEpiThreads;
-        const int64_t slot = n0 + r;
-        float2 c = make_float2(0.f, __int_as_float(0x7f800000));
-        if (slot < iv.n_slots) {
-          bool elig = (iv.live[slot >> 5] >> (slot & 31)) & 1u;
-          if (elig && p.mask.bits) {
-            const uint64_t id = iv.ids_identity ? (uint64_t)slot : iv.ids[slot];
-            elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
-          }
-          if (elig) {
-            c = iv.coef[slot];
-            c.x *= inv_sq;
-          }
-        }
-        cs[r] = c;
-      }
+      cs[et] = cnext[0];
+      cs[et + kEpiThreads] = cnext[1];
       named_bar_sync(2, kEpiThreads);
+      // the next item's coefficient loads stay in flight while this item is processed
+      if (w + gridDim.x < n_items) load_coef(w + gridDim.x, cnext);
+
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
       if (p.seed_mode == 0 && qidx < p.q) thr = p.thresh[qidx];
       float sd[kSeedR];
 #pragma unroll
-      for (int i = 0; i < kSeedR; ++i) sd[i] = __int_as_float(0x7f800000);
+      for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
 
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
@@ -207,14 +220,23 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
+        // 32 (a,b) pairs as 16 broadcast 128-bit shared loads, issued while the TMEM load is in flight
+        float4 cf[16];
+        const float4* c4 = reinterpret_cast<const float4*>(cs + c0);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cf[i] = c4[i];
         tmem_ld_wait();
+        float sc[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          sc[2 * i] = fmaf(__uint_as_float(r[2 * i]), cf[i].x, cf[i].y);
+          sc[2 * i + 1] = fmaf(__uint_as_float(r[2 * i + 1]), cf[i].z, cf[i].w);
+        }
         if (p.seed_mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float2 cf = cs[c0 + j];
-            const float score = fmaf(__uint_as_float(r[j]), cf.x, cf.y);
-            if (score < sd[kSeedR - 1]) {
-              sd[kSeedR - 1] = score;
+            if (sc[j] < sd[kSeedR - 1]) {
+              sd[kSeedR - 1] = sc[j];
 #pragma unroll
               for (int i = kSeedR - 1; i > 0; --i) {
                 const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
@@ -227,19 +249,24 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           // debug dump of every approximate score (tests only; small inputs)
           if (qidx < p.q) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float2 cf = cs[c0 + j];
-              p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + c0 + j)] =
-                  fmaf(__uint_as_float(r[j]), cf.x, cf.y);
-            }
+            for (int j = 0; j < 32; ++j) p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + c0 + j)] = sc[j];
           }
         } else {
+          // common case: no value of the block beats the threshold -> one min tree + one compare.
+          // (fminf drops NaN operands; a NaN query makes every score NaN, which still reaches the slow path.)
+          float m[16];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float2 cf = cs[c0 + j];
-            const float score = fmaf(__uint_as_float(r[j]), cf.x, cf.y);
-            if (!(score >= thr)) {
-              if (qidx < p.q) {
+          for (int i = 0; i < 16; ++i) m[i] = fminf(sc[2 * i], sc[2 * i + 1]);
+#pragma unroll
+          for (int w2 = 8; w2 > 0; w2 >>= 1) {
+#pragma unroll
+            for (int i = 0; i < w2; ++i) m[i] = fminf(m[i], m[i + w2]);
+          }
+          if (!(m[0] >= thr) && qidx < p.q) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float score = sc[j];
+              if (!(score >= thr)) {
                 if (score != score) {
                   atomicOr(p.flags, kFlagNaN);
                 } else {

@@ -37,9 +37,8 @@ struct MaskView {
 // ---- K1: streaming scan + per-warp top-K ---------------------------------------------
 constexpr int kScanConsumerWarps = 8;
 constexpr int kScanThreads = (kScanConsumerWarps + 1) * 32;
-constexpr int kScanStages = 4;
+constexpr int kScanMaxStages = 8;
 constexpr int kScanStageFloats = 8192;  // 32 KB per stage
-constexpr int kScanSegFloats = 256;     // column segment when a 32-row block does not fit a stage
 
 struct ScanParams {
   IndexView iv;
@@ -56,10 +55,12 @@ struct ScanParams {
   int64_t cand_stride;
   uint32_t* flags;
   int rows_per_stage, seg_floats, nseg;
+  int lanes_per_row;        // 8: 4 rows per warp at a time (dpad <= 256); 32: one row per warp (longer rows)
+  int nstages;              // ring depth (<= kScanMaxStages)
 };
 // QT = queries sharing one pass over the database (1,2,4,8).
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st);
-size_t scan_smem_bytes(int QT, int dpad, int K);
+size_t scan_smem_bytes(int QT, int dpad, int K, int nstages);
 
 // ---- ingest / query preparation ------------------------------------------------------
 struct IngestParams {

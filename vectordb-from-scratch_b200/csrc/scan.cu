@@ -62,24 +62,26 @@ __device__ __forceinline__ void consumers_bitonic_sort(uint64_t* arr, int N, int
   }
 }
 
-template <int METRIC, int QT>
+template <int METRIC, int QT, int LPR>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+  constexpr int G = 32 / LPR;  // rows processed concurrently by one warp (LPR lanes per row)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const IndexView& iv = p.iv;
   const int dpad = iv.dpad;
   const int K = p.K;
   float* stages = reinterpret_cast<float*>(smem_raw);
-  float* qs = stages + kScanStages * kScanStageFloats;
+  const int NS = p.nstages;
+  float* qs = stages + (size_t)NS * kScanStageFloats;
   uint64_t* lists = reinterpret_cast<uint64_t*>(qs + QT * dpad);  // [QT][8 warps][K]
   uint64_t* full = lists + (size_t)QT * kScanConsumerWarps * K;
-  uint64_t* empty = full + kScanStages;
+  uint64_t* empty = full + kScanMaxStages;
 
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
   if (nq <= 0) return;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) {
-    for (int s = 0; s < kScanStages; ++s) {
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], kScanConsumerWarps);
     }
@@ -113,8 +115,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         const int64_t row0 = blk * R;
         const int rows = (int)min((int64_t)R, n - row0);
         for (int seg = 0; seg < nseg; ++seg, ++it) {
-          const int s = it % kScanStages;
-          const uint32_t ph = (it / kScanStages) & 1u;
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1u;
           mbar_wait(&empty[s], ph ^ 1u);
           float* dst = stages + (size_t)s * kScanStageFloats;
           if (nseg == 1) {
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
       }
     } else {
       // ---------------- consumers ----------------
-      const int g = lane >> 3, j = lane & 7;
+      const int g = lane / LPR, j = lane % LPR;
       uint64_t T[QT];
       uint64_t floor64[QT];
       float qn[QT];
@@ -155,14 +157,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         const int64_t row0 = blk * R;
         const int rows = (int)min((int64_t)R, n - row0);
         for (int seg = 0; seg < nseg; ++seg, ++it) {
-          const int s = it % kScanStages;
-          const uint32_t ph = (it / kScanStages) & 1u;
+          const int s = it % NS;
+          const uint32_t ph = (it / NS) & 1u;
           mbar_wait(&full[s], ph);
           const float* sb = stages + (size_t)s * kScanStageFloats;
           const int segf = (nseg == 1) ? dpad : min(segw, dpad - seg * segw);
           const int nf4 = segf >> 2;
           const float4* qb = reinterpret_cast<const float4*>(qs + (size_t)seg * segw);
-          for (int i0 = warp * 4; i0 < rows; i0 += 32) {
+          for (int i0 = warp * G; i0 < rows; i0 += kScanConsumerWarps * G) {
             const int rl = i0 + g;
             const int64_t slot = row0 + rl;
             // eligibility + per-row scalars are fetched early so the loads overlap the FMA loop
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             }
             const float4* xr = reinterpret_cast<const float4*>(sb + (size_t)rl * rstride);
 #pragma unroll 4
-            for (int t = j; t < nf4; t += 8) {
+            for (int t = j; t < nf4; t += LPR) {
               const float4 x = xr[t];
 #pragma unroll
               for (int qi = 0; qi < QT; ++qi) {
@@ -207,9 +209,8 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
 #pragma unroll
               for (int qi = 0; qi < QT; ++qi) {
                 float v = acc[qi];
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
+#pragma unroll
+                for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
                 if (qi < nqp) {
                   const float score = (METRIC == kMetricL2) ? v : (METRIC == kMetricCos ? -v * inv : -v);
                   const bool mine = elig && j == 0;
@@ -255,11 +256,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
   }
 }
 
-template <int METRIC>
+template <int METRIC, int LPR>
 cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t smem, cudaStream_t st) {
 #define GFI_SCAN_CASE(Q)                                                                                  \
   case Q: {                                                                                               \
-    auto kern = scan_topk_kernel<METRIC, Q>;                                                              \
+    auto kern = scan_topk_kernel<METRIC, Q, LPR>;                                                              \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
     kern<<<grid, kScanThreads, smem, st>>>(p);                                                            \
@@ -277,17 +278,25 @@ cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t sme
 
 }  // namespace
 
-size_t scan_smem_bytes(int QT, int dpad, int K) {
-  return (size_t)kScanStages * kScanStageFloats * 4 + (size_t)QT * dpad * 4 +
-         (size_t)QT * kScanConsumerWarps * K * 8 + 2 * kScanStages * 8 + 16;
+size_t scan_smem_bytes(int QT, int dpad, int K, int nstages) {
+  return (size_t)nstages * kScanStageFloats * 4 + (size_t)QT * dpad * 4 +
+         (size_t)QT * kScanConsumerWarps * K * 8 + 2 * kScanMaxStages * 8 + 16;
 }
 
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st) {
-  const size_t smem = scan_smem_bytes(QT, p.iv.dpad, p.K);
-  switch (p.iv.metric) {
-    case kMetricL2: return launch_scan_metric<kMetricL2>(p, QT, grid, smem, st);
-    case kMetricCos: return launch_scan_metric<kMetricCos>(p, QT, grid, smem, st);
-    case kMetricDot: return launch_scan_metric<kMetricDot>(p, QT, grid, smem, st);
+  const size_t smem = scan_smem_bytes(QT, p.iv.dpad, p.K, p.nstages);
+  if (p.lanes_per_row == 8) {
+    switch (p.iv.metric) {
+      case kMetricL2: return launch_scan_metric<kMetricL2, 8>(p, QT, grid, smem, st);
+      case kMetricCos: return launch_scan_metric<kMetricCos, 8>(p, QT, grid, smem, st);
+      case kMetricDot: return launch_scan_metric<kMetricDot, 8>(p, QT, grid, smem, st);
+    }
+  } else if (p.lanes_per_row == 32) {
+    switch (p.iv.metric) {
+      case kMetricL2: return launch_scan_metric<kMetricL2, 32>(p, QT, grid, smem, st);
+      case kMetricCos: return launch_scan_metric<kMetricCos, 32>(p, QT, grid, smem, st);
+      case kMetricDot: return launch_scan_metric<kMetricDot, 32>(p, QT, grid, smem, st);
+    }
   }
   return cudaErrorInvalidValue;
 }
