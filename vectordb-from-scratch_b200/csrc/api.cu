@@ -187,6 +187,7 @@ struct gfi_index {
   int opt_seed_rank = 8;
   int opt_profile = 0;
   int opt_gemm_debug = 0;
+  int opt_scan_stages = 0;
   std::atomic<int64_t> prof_ns[2] = {{0}, {0}}, prof_cnt[2] = {{0}, {0}};
 
   IndexView view() const {
@@ -522,8 +523,8 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
 
   const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
                          !(h->metric == GFI_METRIC_COSINE && h->zero_rows_ever > 0) &&
-                         q >= h->opt_tensor_min_q && h->n_slots >= h->opt_tensor_min_rows && a.kmax <= 256 &&
-                         get_encode_fn() != nullptr;
+                         q >= h->opt_tensor_min_q && q <= kGemmMaxQueries && h->n_slots >= h->opt_tensor_min_rows &&
+                         a.kmax <= 256 && h->dpad16 >= 64 && get_encode_fn() != nullptr;
 
   // ---- workspace ----
   const int qpad = (q + 127) / 128 * 128;
@@ -554,29 +555,40 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   // ---- scan geometry (also used by the tensor path's fallback) ----
   const int K = std::min(1024, pow2_at_least(std::max<int>(32, (int)a.kmax + 8)));
   if ((int)a.kmax > K) return fail(GFI_ERR_INDEX, "k too large: the scan path supports k <= 1024");
-  int QT = 8;
-  while (QT > 1 && ((int64_t)QT * h->dpad > 8192 || QT * K > 1024)) QT >>= 1;
-  if ((int64_t)QT * h->dpad > 16384) return fail(GFI_ERR_INDEX, "dimension too large (max 16384)");
-  if (h->opt_scan_qt > 0) QT = std::min(QT, h->opt_scan_qt);
-  if (!tensor_ok) { while (QT > 1 && QT / 2 >= q) QT >>= 1; }
-  // Ring geometry.  A stage is one contiguous bulk copy whenever whole rows fit (the TMA engine's
-  // per-copy cost is what limits small copies): rows <= 1 KB use 8 lanes per row and 32*m rows per
-  // stage; longer rows use one warp per row and 8*m rows per stage; rows beyond 4 KB are cut into
-  // 4 KB column segments (8 copies per stage).
+  if (h->dpad > 16384) return fail(GFI_ERR_INDEX, "dimension too large (max 16384)");
+  // Ring geometry.  A stage is one contiguous bulk copy of whole rows whenever rows fit (<= 4 KB):
+  // rows <= 1 KB use 8 lanes per row (64 rows per round of the 16 consumer warps), longer rows one
+  // warp per row (16 rows per round); rows beyond 4 KB are cut into 4 KB column segments.
   int R, segf, nseg, lpr;
+  const int kTargetStageBytes = 48 * 1024;
   if (h->dpad <= 256) {
     lpr = 8;
-    R = std::max(32, (kScanStageFloats / h->dpad) / 32 * 32);
     segf = h->dpad;
     nseg = 1;
+    R = 64 * std::max(1, std::min(4, kTargetStageBytes / (64 * h->dpad * 4)));
   } else {
     lpr = 32;
     segf = std::min(h->dpad, 1024);
     nseg = (h->dpad + segf - 1) / segf;
-    R = nseg == 1 ? 8 * std::max(1, std::min(4, kScanStageFloats / (8 * segf))) : 8;
+    R = nseg == 1 ? 16 * std::max(1, std::min(4, kTargetStageBytes / (16 * h->dpad * 4))) : 16;
   }
-  const size_t scan_fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
-  const int nstages = (int)std::max<size_t>(2, std::min<size_t>(kScanMaxStages, (227 * 1024 - scan_fixed) / (kScanStageFloats * 4)));
+  const int stage_floats = R * (nseg == 1 ? h->dpad : segf);
+  // queries per pass: as many as shared memory allows next to a ring of at least 3 stages
+  int QT = 4, nstages = 0;
+  for (;; QT >>= 1) {
+    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
+    const size_t budget = 227 * 1024;
+    nstages = fixed < budget ? (int)std::min<size_t>(kScanMaxStages, (budget - fixed) / ((size_t)stage_floats * 4)) : 0;
+    if (nstages >= 3 || QT == 1) break;
+  }
+  if (nstages < 2) return fail(GFI_ERR_INDEX, "k and dimension too large for the scan kernel's shared memory");
+  if (h->opt_scan_qt > 0) QT = std::min(QT, pow2_at_least(h->opt_scan_qt));
+  if (!tensor_ok) { while (QT > 1 && QT / 2 >= q) QT >>= 1; }
+  {
+    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
+    nstages = (int)std::min<size_t>(kScanMaxStages, (227 * 1024 - fixed) / ((size_t)stage_floats * 4));
+    if (h->opt_scan_stages > 0) nstages = std::max(2, std::min(nstages, h->opt_scan_stages));
+  }
   const int64_t nblocks = (h->n_slots + R - 1) / R;
   const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
   const int64_t scan_stride = (int64_t)scan_grid * K;
@@ -597,6 +609,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
     sp.nseg = nseg;
     sp.lanes_per_row = lpr;
     sp.nstages = nstages;
+    sp.stage_floats = stage_floats;
   };
   auto fill_select = [&](SelectParams& s, DevBuf& cand, DevBuf& cnt, int64_t stride, int KP) {
     s.iv = iv;
@@ -647,7 +660,10 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   const int KP = h->opt_kp > 0 ? std::min(1024, pow2_at_least(h->opt_kp))
                                : std::min(1024, pow2_at_least(std::max<int>(64, 4 * (int)a.kmax)));
   const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
-  const uint32_t cap = (uint32_t)std::min<int64_t>(4ll * hits, 1 << 16);
+  const int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
+  // candidate slots per (query, CTA): 4x the expected hits of a slice (+ slack), power of two
+  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(32, 4 * hits / std::max(main_grid, 1) + 16)));
+  const int64_t cand_stride = (int64_t)main_grid * cap;  // per query
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
   // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`
@@ -656,13 +672,14 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   const int64_t seed_stride = std::max<int64_t>(1, num_n_tiles / seed_tiles);
   const int num_m_tiles = qpad / 128;
 
-  CU_TRY(c->cand.ensure((size_t)q * cap * 8));
+  CU_TRY(c->cand.ensure((size_t)q * cand_stride * 8));
   CU_TRY(c->cand_cnt.ensure((size_t)q * 4));
   CU_TRY(c->cand_fb.ensure((size_t)q * scan_stride * 8));
   CU_TRY(c->cand_fb_cnt.ensure((size_t)q * 4));
   CU_TRY(c->thresh.ensure((size_t)q * 4));
   CU_TRY(c->seeds.ensure((size_t)q * seed_tiles * kSeedR * 4));
-  CU_TRY(cudaMemsetAsync(c->cand_cnt.p, 0, (size_t)q * 4, st));
+  CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));  // sentinels
+  CU_TRY(launch_fill_u32(c->cand_cnt.as<uint32_t>(), (uint32_t)cand_stride, q, st));
 
   CUtensorMap tmx, tmq;
   if (!make_tmap_2d(&tmx, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 256) ||
@@ -681,7 +698,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   gp.thresh = c->thresh.as<float>();
   gp.cand = c->cand.as<uint64_t>();
   gp.cand_cnt = c->cand_cnt.as<uint32_t>();
-  gp.cand_stride = cap;
+  gp.cand_stride = cand_stride;
   gp.cand_cap = cap;
   gp.flags = &ctrl->flags;
   gp.seed_tiles = seed_tiles;
@@ -695,11 +712,11 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   // main pass
   gp.seed_mode = 0;
   prof_begin(h, c, 1, st);
-  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, num_n_tiles * num_m_tiles), st));
+  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, main_grid, st));
   prof_end(h, c, st);
   // select + exact rerank + certification
   SelectParams s{};
-  fill_select(s, c->cand, c->cand_cnt, cap, KP);
+  fill_select(s, c->cand, c->cand_cnt, cand_stride, KP);
   s.qlist = nullptr;
   s.nq_dev = nullptr;
   s.nq = q;
@@ -722,7 +739,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   s2.nq = 0;
   s2.certify = 0;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
-  h->n_launch += 6;
+  h->n_launch += 7;
   h->n_tensor_q += q;
   return GFI_OK;
 }
@@ -1219,6 +1236,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
+  else if (n == "scan_stages") h->opt_scan_stages = (int)value;
   else return fail(GFI_ERR_INDEX, "unknown option: " + n);
   return GFI_OK;
 }

@@ -41,7 +41,8 @@ constexpr size_t kOffA = 0;
 constexpr size_t kOffB = kOffA + (size_t)kStages * kABytes;
 constexpr size_t kOffCoef = kOffB + (size_t)kStages * kBBytes;
 constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
-constexpr size_t kSmemUsed = kOffBar + 16 * 8 + 16;
+constexpr size_t kOffCnt = kOffBar + 16 * 8 + 16;  // u8 hit counters, one per query of the batch
+constexpr size_t kSmemUsed = kOffCnt + 2 * kGemmMaxQueries;
 constexpr size_t kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
 
 // UMMA instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, N=256, M=128.
@@ -78,6 +79,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  // u16 hit counter per query, private to this CTA: no atomics on the hot path.  Items map to
+  // (row tile, query tile) with a rotation so that every CTA meets every query tile and a query's
+  // candidates spread evenly over all CTAs' slices.
+  unsigned short* hitcnt = reinterpret_cast<unsigned short*>(smem + kOffCnt);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const IndexView& iv = p.iv;
@@ -95,6 +100,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
     fence_mbar_init();
   }
+  for (int i = tid; i < p.num_m_tiles * BM; i += kGemmThreads) hitcnt[i] = 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmq);
@@ -113,7 +119,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     uint32_t it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       const int64_t nt_idx = w / p.num_m_tiles;
-      const int m_tile = (int)(w - nt_idx * p.num_m_tiles);
+      const int m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);  // rotated: see item_tiles note
       const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         const int s = it % kStages;
@@ -196,7 +202,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       const int64_t nt_idx = w / p.num_m_tiles;
-      const int m_tile = (int)(w - nt_idx * p.num_m_tiles);
+      const int m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);  // rotated: see item_tiles note
       const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
@@ -262,7 +268,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 #pragma unroll
             for (int i = 0; i < w2; ++i) m[i] = fminf(m[i], m[i + w2]);
           }
-          if (!(m[0] >= thr) && qidx < p.q) {
+          if (!(m[0] >= thr) && qidx < p.q && !(p.debug & 8)) {
+            // rare: append to this (query, CTA)'s private slice of the candidate buffer -- plain
+            // stores, no atomics, nothing to wait for
+            uint32_t cnt = hitcnt[qidx];
+            uint64_t* mine = p.cand + (size_t)qidx * p.cand_stride + (size_t)blockIdx.x * p.cand_cap;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const float score = sc[j];
@@ -270,12 +280,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
                 if (score != score) {
                   atomicOr(p.flags, kFlagNaN);
                 } else {
-                  const uint32_t pos = atomicAdd(&p.cand_cnt[qidx], 1u);
-                  if (pos < p.cand_cap)
-                    p.cand[(size_t)qidx * p.cand_stride + pos] = pack_key(score, (uint32_t)(n0 + c0 + j));
+                  if (cnt < p.cand_cap) mine[cnt] = pack_key(score, (uint32_t)(n0 + c0 + j));
+                  else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: this query falls back to the scan
+                  ++cnt;
                 }
               }
             }
+            hitcnt[qidx] = (unsigned short)min(cnt, 65535u);
           }
         }
       }

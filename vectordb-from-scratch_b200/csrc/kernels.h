@@ -35,10 +35,9 @@ struct MaskView {
 };
 
 // ---- K1: streaming scan + per-warp top-K ---------------------------------------------
-constexpr int kScanConsumerWarps = 8;
+constexpr int kScanConsumerWarps = 16;
 constexpr int kScanThreads = (kScanConsumerWarps + 1) * 32;
 constexpr int kScanMaxStages = 8;
-constexpr int kScanStageFloats = 8192;  // 32 KB per stage
 
 struct ScanParams {
   IndexView iv;
@@ -57,10 +56,11 @@ struct ScanParams {
   int rows_per_stage, seg_floats, nseg;
   int lanes_per_row;        // 8: 4 rows per warp at a time (dpad <= 256); 32: one row per warp (longer rows)
   int nstages;              // ring depth (<= kScanMaxStages)
+  int stage_floats;         // floats per ring stage (rows_per_stage * row stride in the stage)
 };
-// QT = queries sharing one pass over the database (1,2,4,8).
+// QT = queries sharing one pass over the database (1,2,4).
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st);
-size_t scan_smem_bytes(int QT, int dpad, int K, int nstages);
+size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats);
 
 // ---- ingest / query preparation ------------------------------------------------------
 struct IngestParams {
@@ -123,11 +123,15 @@ struct GemmParams {
   int seed_mode; int64_t seed_tiles, seed_stride;
   float* seeds;         // [q][seed_tiles][R]
   const float* thresh;  // [q]
+  // main mode: cand[q][cand_stride] is pre-filled with sentinels; CTA b appends to the slice
+  // [b*cand_cap, (b+1)*cand_cap) of each query; cand_cnt[q] is pre-set to cand_stride and only
+  // overwritten (0xffffffff) when a slice overflows
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
   uint32_t* flags;
   int debug;            // timing experiments only (see gemm_topk.cu)
 };
 constexpr int kSeedR = 8;
+constexpr int kGemmMaxQueries = 8192;   // per launch (u16 hit counter per query in shared memory)
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
                              cudaStream_t st);
 struct SeedFinalizeParams {

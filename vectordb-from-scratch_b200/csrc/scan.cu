@@ -2,21 +2,30 @@
 // fused distance epilogue, eligibility (tombstone + metadata-filter bitmask) test and per-warp
 // top-K lists.  Replaces the score-all + full-sort of the reference's FlatIndex::search
 // (src/flat_index.rs:53-63) and the per-pair metric loops (src/distance.rs:37-73) for small
-// query batches (q <= 8 queries share one pass over the database).
+// query batches (QT <= 4 queries share one pass over the database).
 //
-// Shape of the work: no reuse of the database bytes, so the kernel is HBM-bound.  One
-// persistent CTA per SM; a producer warp streams row blocks into a 4 x 32 KB shared-memory
-// ring with 1-D bulk async copies (TMA engine, SASS UBLKCP) completing on mbarriers; eight
-// consumer warps read the ring with conflict-free 128-bit loads (8 lanes per row), keep QT
-// accumulators per lane and insert into per-warp sorted lists only when a row beats the
-// list's current K-th key.  The scores computed here only rank candidates; the K survivors
-// per CTA are re-scored with the reference's exact arithmetic in select_rerank.cu.
+// Shape of the work: no reuse of the database bytes, so the kernel is HBM-bound and the design
+// is about keeping bytes in flight and the per-row dependency chain short:
+//   * one persistent CTA per SM; a producer warp streams row blocks into a shared-memory ring
+//     with 1-D bulk async copies (TMA engine, SASS UBLKCP) that complete on mbarriers.  A stage
+//     is ONE contiguous copy of whole rows (24-64 KB) whenever rows fit; a bandwidth probe
+//     (scripts/probes/bw_probe.cu) shows this path streams 7.3 TB/s on B200 with >= 16 KB copies;
+//   * sixteen consumer warps read the ring with conflict-free 128-bit loads: 8 lanes per row
+//     (4 rows per warp at a time) for rows <= 1 KB, one warp per row for longer rows;
+//   * tombstone / filter bits and the row norm for the NEXT stage are fetched while the current
+//     stage is processed, so no global-memory latency sits on a warp's per-row critical path;
+//   * a row touches the per-warp sorted list only when it beats the list's current K-th key.
+// The scores computed here only rank candidates; the K survivors per CTA are re-scored with the
+// reference's exact arithmetic in select_rerank.cu.
 #include "common.cuh"
 #include "kernels.h"
 
 namespace gfi {
 
 namespace {
+
+constexpr int NW = kScanConsumerWarps;
+constexpr int kMaxRounds = 4;  // row rounds per stage (rows_per_stage = rounds * NW * rows-per-warp)
 
 __device__ __forceinline__ void warp_list_insert(uint64_t* list, int K, uint64_t key, int lane) {
   // list ascending, key < list[K-1]; the last entry falls off.
@@ -43,11 +52,11 @@ __device__ __forceinline__ void warp_list_insert(uint64_t* list, int K, uint64_t
   __syncwarp();
 }
 
-// In-place ascending bitonic sort of arr[0..N) (N a power of two) by the 256 consumer threads.
+// In-place ascending bitonic sort of arr[0..N) (N a power of two) by the consumer threads.
 __device__ __forceinline__ void consumers_bitonic_sort(uint64_t* arr, int N, int tid) {
   for (int k = 2; k <= N; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < N / 2; t += kScanConsumerWarps * 32) {
+      for (int t = tid; t < N / 2; t += NW * 32) {
         const int i = ((t / j) * 2 * j) + (t % j);
         const int l = i + j;
         const bool up = ((i & k) == 0);
@@ -57,23 +66,34 @@ __device__ __forceinline__ void consumers_bitonic_sort(uint64_t* arr, int N, int
           arr[l] = a;
         }
       }
-      named_bar_sync(1, kScanConsumerWarps * 32);
+      named_bar_sync(1, NW * 32);
     }
   }
 }
 
-template <int METRIC, int QT, int LPR>
+// Row metadata fetched one block ahead as RAW words (nothing depends on the loads until the next
+// iteration, so their latency is hidden behind the current block's work).
+struct RowMeta {
+  uint32_t live[kMaxRounds];
+  uint64_t mask[kMaxRounds];
+  float norm[kMaxRounds];
+};
+
+template <int METRIC, int QT, int LPR, bool SEG>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
-  constexpr int G = 32 / LPR;  // rows processed concurrently by one warp (LPR lanes per row)
+  constexpr int G = 32 / LPR;              // rows processed concurrently by one warp (LPR lanes per row)
+  constexpr bool FAST = (QT == 1) && !SEG;  // single query, whole rows per stage: query lives in registers
+  constexpr int kQRegs = 8;                 // float4 per lane per row on the FAST path (dpad <= 256 * G)
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   const IndexView& iv = p.iv;
   const int dpad = iv.dpad;
   const int K = p.K;
-  float* stages = reinterpret_cast<float*>(smem_raw);
   const int NS = p.nstages;
-  float* qs = stages + (size_t)NS * kScanStageFloats;
-  uint64_t* lists = reinterpret_cast<uint64_t*>(qs + QT * dpad);  // [QT][8 warps][K]
-  uint64_t* full = lists + (size_t)QT * kScanConsumerWarps * K;
+  const int stage_floats = p.stage_floats;
+  float* stages = reinterpret_cast<float*>(smem_raw);
+  float* qs = stages + (size_t)NS * stage_floats;
+  uint64_t* lists = reinterpret_cast<uint64_t*>(qs + QT * dpad);  // [QT][NW][K]
+  uint64_t* full = lists + (size_t)QT * NW * K;
   uint64_t* empty = full + kScanMaxStages;
 
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
@@ -83,17 +103,19 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
   if (tid == 0) {
     for (int s = 0; s < NS; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kScanConsumerWarps);
+      mbar_init(&empty[s], NW);
     }
     fence_mbar_init();
   }
   __syncthreads();
 
-  const int64_t n = iv.n_slots;
-  const int R = p.rows_per_stage, nseg = p.nseg, segw = p.seg_floats;
-  const int64_t nblocks = (n + R - 1) / R;
-  const int rstride = (nseg == 1) ? dpad : segw;
-  uint32_t it = 0;  // ring iteration; producer and consumers walk the same sequence
+  const uint32_t n = (uint32_t)iv.n_slots;
+  const int R = p.rows_per_stage, nseg = SEG ? p.nseg : 1, segw = p.seg_floats;
+  const uint32_t nblocks = (n + R - 1) / R;
+  const int rstride = SEG ? segw : dpad;
+  const int rounds = R / (NW * G);
+  int stage = 0;       // ring position; producer and consumers walk the same sequence
+  uint32_t phase = 0;  // parity of the ring pass
 
   for (int q0 = 0; q0 < nq; q0 += QT) {
     const int nqp = min(QT, nq - q0);
@@ -106,104 +128,153 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
       }
       qs[i] = v;
     }
-    for (int i = tid; i < QT * kScanConsumerWarps * K; i += kScanThreads) lists[i] = kKeySentinel;
+    for (int i = tid; i < QT * NW * K; i += kScanThreads) lists[i] = kKeySentinel;
     __syncthreads();
 
-    if (warp == kScanConsumerWarps) {
+    if (warp == NW) {
       // ---------------- producer: bulk async copies into the ring ----------------
-      for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const int64_t row0 = blk * R;
-        const int rows = (int)min((int64_t)R, n - row0);
-        for (int seg = 0; seg < nseg; ++seg, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (it / NS) & 1u;
-          mbar_wait(&empty[s], ph ^ 1u);
-          float* dst = stages + (size_t)s * kScanStageFloats;
-          if (nseg == 1) {
+      for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const uint32_t row0 = blk * R;
+        const int rows = (int)min((uint32_t)R, n - row0);
+        for (int seg = 0; seg < nseg; ++seg) {
+          mbar_wait(&empty[stage], phase ^ 1u);
+          float* dst = stages + (size_t)stage * stage_floats;
+          if (!SEG) {
             if (lane == 0) {
               const uint32_t bytes = (uint32_t)rows * dpad * 4u;
-              mbar_arrive_expect_tx(&full[s], bytes);
-              bulk_g2s(dst, iv.x32 + row0 * dpad, bytes, &full[s]);
+              mbar_arrive_expect_tx(&full[stage], bytes);
+              bulk_g2s(dst, iv.x32 + (size_t)row0 * dpad, bytes, &full[stage]);
             }
           } else {
+            // rows longer than a segment: one copy per row and column segment (rows <= 32 here)
             const int segf = min(segw, dpad - seg * segw);
-            if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)rows * segf * 4u);
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)rows * segf * 4u);
             __syncwarp();
             if (lane < rows)
-              bulk_g2s(dst + lane * segw, iv.x32 + (row0 + lane) * dpad + (size_t)seg * segw, segf * 4u,
-                       &full[s]);
+              bulk_g2s(dst + lane * segw, iv.x32 + (size_t)(row0 + lane) * dpad + (size_t)seg * segw, segf * 4u,
+                       &full[stage]);
           }
           __syncwarp();
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
     } else {
       // ---------------- consumers ----------------
       const int g = lane / LPR, j = lane % LPR;
+      const int rsub = warp * G + g;  // this lane's row within a round
       uint64_t T[QT];
       uint64_t floor64[QT];
-      float qn[QT];
 #pragma unroll
       for (int qi = 0; qi < QT; ++qi) {
         T[qi] = kKeySentinel;
         floor64[qi] = 0;
-        qn[qi] = 1.f;
         if (qi < nqp) {
           const uint32_t qg = p.qlist ? p.qlist[q0 + qi] : (uint32_t)(q0 + qi);
           if (p.floor64) floor64[qi] = p.floor64[qg];
         }
       }
+      const bool has_mask = p.mask.bits != nullptr;
+      const bool mask_by_slot = has_mask && iv.ids_identity;
+      auto fetch_meta = [&](uint32_t blk, RowMeta& m) {
+        const uint32_t row0 = blk * R;
+#pragma unroll
+        for (int r = 0; r < kMaxRounds; ++r) {
+          m.live[r] = 0;
+          m.mask[r] = ~0ull;
+          m.norm[r] = 1.f;
+          const uint32_t slot = row0 + r * (NW * G) + rsub;
+          if (r < rounds && slot < n) {
+            m.live[r] = __ldg(iv.live + (slot >> 5));
+            if (mask_by_slot) m.mask[r] = ((int64_t)slot < p.mask.nbits) ? __ldg(p.mask.bits + (slot >> 6)) : 0ull;
+            if (METRIC == kMetricCos) m.norm[r] = __ldg(iv.norm + slot);
+          }
+        }
+      };
+      RowMeta meta_next;
+      if (blockIdx.x < nblocks) fetch_meta(blockIdx.x, meta_next);
+
+      // FAST path: this lane's slice of the (single) query stays in registers for the whole pass
+      float4 qreg[FAST ? kQRegs : 1];
+      if (FAST) {
+        const float4* q4 = reinterpret_cast<const float4*>(qs);
+#pragma unroll
+        for (int i = 0; i < kQRegs; ++i) {
+          const int t = j + i * LPR;
+          qreg[FAST ? i : 0] = (t < (dpad >> 2)) ? q4[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+
       float acc[QT];
-      for (int64_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
-        const int64_t row0 = blk * R;
-        const int rows = (int)min((int64_t)R, n - row0);
-        for (int seg = 0; seg < nseg; ++seg, ++it) {
-          const int s = it % NS;
-          const uint32_t ph = (it / NS) & 1u;
-          mbar_wait(&full[s], ph);
-          const float* sb = stages + (size_t)s * kScanStageFloats;
-          const int segf = (nseg == 1) ? dpad : min(segw, dpad - seg * segw);
+      for (uint32_t blk = blockIdx.x; blk < nblocks; blk += gridDim.x) {
+        const uint32_t row0 = blk * R;
+        const int rows = (int)min((uint32_t)R, n - row0);
+        const RowMeta meta = meta_next;
+        if (blk + gridDim.x < nblocks) fetch_meta(blk + gridDim.x, meta_next);
+
+        for (int seg = 0; seg < nseg; ++seg) {
+          mbar_wait(&full[stage], phase);
+          const float* sb = stages + (size_t)stage * stage_floats;
+          const int segf = SEG ? min(segw, dpad - seg * segw) : dpad;
           const int nf4 = segf >> 2;
-          const float4* qb = reinterpret_cast<const float4*>(qs + (size_t)seg * segw);
-          for (int i0 = warp * G; i0 < rows; i0 += kScanConsumerWarps * G) {
-            const int rl = i0 + g;
-            const int64_t slot = row0 + rl;
-            // eligibility + per-row scalars are fetched early so the loads overlap the FMA loop
-            bool elig = false;
-            float rnorm = 1.f;
-            if (seg == nseg - 1 && rl < rows) {
-              elig = (iv.live[slot >> 5] >> (slot & 31)) & 1u;
-              if (elig && p.mask.bits) {
-                const uint64_t id = iv.ids_identity ? (uint64_t)slot : iv.ids[slot];
-                elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
-              }
-              if (METRIC == kMetricCos) rnorm = iv.norm[slot];
-            }
-            if (nseg == 1 || seg == 0) {
 #pragma unroll
-              for (int qi = 0; qi < QT; ++qi) acc[qi] = 0.f;
-            }
+          for (int r = 0; r < kMaxRounds; ++r) {
+            if (r * (NW * G) + warp * G >= rows) break;  // warp-uniform
+            const int rl = r * (NW * G) + rsub;
+            const uint32_t slot = row0 + rl;
             const float4* xr = reinterpret_cast<const float4*>(sb + (size_t)rl * rstride);
-#pragma unroll 4
-            for (int t = j; t < nf4; t += LPR) {
-              const float4 x = xr[t];
+            if (FAST) {
+              float a0 = 0.f, a1 = 0.f;
 #pragma unroll
-              for (int qi = 0; qi < QT; ++qi) {
-                const float4 qv = qb[qi * (dpad >> 2) + t];
-                if (METRIC == kMetricL2) {
-                  const float a = qv.x - x.x, b = qv.y - x.y, c = qv.z - x.z, e = qv.w - x.w;
-                  acc[qi] = fmaf(a, a, acc[qi]);
-                  acc[qi] = fmaf(b, b, acc[qi]);
-                  acc[qi] = fmaf(c, c, acc[qi]);
-                  acc[qi] = fmaf(e, e, acc[qi]);
-                } else {
-                  acc[qi] = fmaf(qv.x, x.x, acc[qi]);
-                  acc[qi] = fmaf(qv.y, x.y, acc[qi]);
-                  acc[qi] = fmaf(qv.z, x.z, acc[qi]);
-                  acc[qi] = fmaf(qv.w, x.w, acc[qi]);
+              for (int i = 0; i < kQRegs; ++i) {
+                const int t = j + i * LPR;
+                if (t < nf4) {
+                  const float4 x = xr[t];
+                  const float4 qv = qreg[FAST ? i : 0];
+                  float& a = (i & 1) ? a1 : a0;
+                  if (METRIC == kMetricL2) {
+                    const float d0 = qv.x - x.x, d1 = qv.y - x.y, d2 = qv.z - x.z, d3 = qv.w - x.w;
+                    a = fmaf(d0, d0, a); a = fmaf(d1, d1, a); a = fmaf(d2, d2, a); a = fmaf(d3, d3, a);
+                  } else {
+                    a = fmaf(qv.x, x.x, a); a = fmaf(qv.y, x.y, a); a = fmaf(qv.z, x.z, a); a = fmaf(qv.w, x.w, a);
+                  }
+                }
+              }
+              acc[0] = a0 + a1;
+            } else {
+              if (!SEG || seg == 0) {
+#pragma unroll
+                for (int qi = 0; qi < QT; ++qi) acc[qi] = 0.f;
+              }
+              const float4* qb = reinterpret_cast<const float4*>(qs + (size_t)seg * segw);
+#pragma unroll 4
+              for (int t = j; t < nf4; t += LPR) {
+                const float4 x = xr[t];
+#pragma unroll
+                for (int qi = 0; qi < QT; ++qi) {
+                  const float4 qv = qb[qi * (dpad >> 2) + t];
+                  if (METRIC == kMetricL2) {
+                    const float d0 = qv.x - x.x, d1 = qv.y - x.y, d2 = qv.z - x.z, d3 = qv.w - x.w;
+                    acc[qi] = fmaf(d0, d0, acc[qi]);
+                    acc[qi] = fmaf(d1, d1, acc[qi]);
+                    acc[qi] = fmaf(d2, d2, acc[qi]);
+                    acc[qi] = fmaf(d3, d3, acc[qi]);
+                  } else {
+                    acc[qi] = fmaf(qv.x, x.x, acc[qi]);
+                    acc[qi] = fmaf(qv.y, x.y, acc[qi]);
+                    acc[qi] = fmaf(qv.z, x.z, acc[qi]);
+                    acc[qi] = fmaf(qv.w, x.w, acc[qi]);
+                  }
                 }
               }
             }
-            if (seg == nseg - 1) {
+            if (!SEG || seg == nseg - 1) {
+              // eligibility: tombstone bit, then the filter bit (by slot when ids are the identity)
+              bool elig = ((meta.live[r] >> (slot & 31)) & 1u) && ((meta.mask[r] >> (slot & 63)) & 1ull);
+              if (elig && has_mask && !mask_by_slot) {
+                const uint64_t id = iv.ids[slot];
+                elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
+              }
+              const float rnorm = meta.norm[r];
               if (METRIC == kMetricCos && elig && j == 0 && rnorm == 0.f) atomicOr(p.flags, kFlagZeroNorm);
               const float inv = (METRIC == kMetricCos) ? (1.0f / rnorm) : 1.f;
 #pragma unroll
@@ -216,7 +287,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                   const bool mine = elig && j == 0;
                   if (mine && score != score && !(METRIC == kMetricCos && rnorm == 0.f))
                     atomicOr(p.flags, kFlagNaN);
-                  const uint64_t key = pack_key(score, (uint32_t)slot);
+                  const uint64_t key = pack_key(score, slot);
                   const bool hit = mine && (score == score) && key < T[qi] && key > floor64[qi];
                   unsigned m = __ballot_sync(0xffffffffu, hit);
                   while (m) {
@@ -224,7 +295,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
                     m &= m - 1;
                     const uint64_t k64 = __shfl_sync(0xffffffffu, key, src);
                     if (k64 < T[qi]) {
-                      uint64_t* list = lists + ((size_t)qi * kScanConsumerWarps + warp) * K;
+                      uint64_t* list = lists + ((size_t)qi * NW + warp) * K;
                       warp_list_insert(list, K, k64, lane);
                       T[qi] = list[K - 1];
                     }
@@ -234,21 +305,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             }
           }
           __syncwarp();
-          if (lane == 0) mbar_arrive(&empty[s]);
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == NS) { stage = 0; phase ^= 1u; }
         }
       }
-      (void)qn;
     }
     __syncthreads();
 
-    // ---------------- CTA merge: 8 sorted lists -> top K per query, written to cand ----------------
-    if (warp < kScanConsumerWarps) {
+    // ---------------- CTA merge: NW sorted lists -> top K per query, written to cand ----------------
+    if (warp < NW) {
       for (int qi = 0; qi < nqp; ++qi) {
-        uint64_t* arr = lists + (size_t)qi * kScanConsumerWarps * K;
-        consumers_bitonic_sort(arr, kScanConsumerWarps * K, tid);
+        uint64_t* arr = lists + (size_t)qi * NW * K;
+        consumers_bitonic_sort(arr, NW * K, tid);
         const uint32_t qg = p.qlist ? p.qlist[q0 + qi] : (uint32_t)(q0 + qi);
         uint64_t* out = p.cand + (size_t)qg * p.cand_stride + (size_t)blockIdx.x * K;
-        for (int i = tid; i < K; i += kScanConsumerWarps * 32) out[i] = arr[i];
+        for (int i = tid; i < K; i += NW * 32) out[i] = arr[i];
         if (blockIdx.x == 0 && tid == 0) p.cand_cnt[qg] = gridDim.x * (uint32_t)K;
       }
     }
@@ -256,11 +327,11 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
   }
 }
 
-template <int METRIC, int LPR>
+template <int METRIC, int LPR, bool SEG>
 cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t smem, cudaStream_t st) {
 #define GFI_SCAN_CASE(Q)                                                                                  \
   case Q: {                                                                                               \
-    auto kern = scan_topk_kernel<METRIC, Q, LPR>;                                                              \
+    auto kern = scan_topk_kernel<METRIC, Q, LPR, SEG>;                                                    \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
     if (e != cudaSuccess) return e;                                                                       \
     kern<<<grid, kScanThreads, smem, st>>>(p);                                                            \
@@ -270,33 +341,34 @@ cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t sme
     GFI_SCAN_CASE(1)
     GFI_SCAN_CASE(2)
     GFI_SCAN_CASE(4)
-    GFI_SCAN_CASE(8)
   }
 #undef GFI_SCAN_CASE
   return cudaErrorInvalidValue;
 }
 
+template <int METRIC>
+cudaError_t launch_scan_shape(const ScanParams& p, int QT, int grid, size_t smem, cudaStream_t st) {
+  if (p.lanes_per_row == 8 && p.nseg == 1) return launch_scan_metric<METRIC, 8, false>(p, QT, grid, smem, st);
+  if (p.lanes_per_row == 32 && p.nseg == 1) return launch_scan_metric<METRIC, 32, false>(p, QT, grid, smem, st);
+  if (p.lanes_per_row == 32) return launch_scan_metric<METRIC, 32, true>(p, QT, grid, smem, st);
+  return cudaErrorInvalidValue;
+}
+
 }  // namespace
 
-size_t scan_smem_bytes(int QT, int dpad, int K, int nstages) {
-  return (size_t)nstages * kScanStageFloats * 4 + (size_t)QT * dpad * 4 +
-         (size_t)QT * kScanConsumerWarps * K * 8 + 2 * kScanMaxStages * 8 + 16;
+size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats) {
+  return (size_t)nstages * stage_floats * 4 + (size_t)QT * dpad * 4 + (size_t)QT * NW * K * 8 +
+         2 * kScanMaxStages * 8 + 16;
 }
 
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st) {
-  const size_t smem = scan_smem_bytes(QT, p.iv.dpad, p.K, p.nstages);
-  if (p.lanes_per_row == 8) {
-    switch (p.iv.metric) {
-      case kMetricL2: return launch_scan_metric<kMetricL2, 8>(p, QT, grid, smem, st);
-      case kMetricCos: return launch_scan_metric<kMetricCos, 8>(p, QT, grid, smem, st);
-      case kMetricDot: return launch_scan_metric<kMetricDot, 8>(p, QT, grid, smem, st);
-    }
-  } else if (p.lanes_per_row == 32) {
-    switch (p.iv.metric) {
-      case kMetricL2: return launch_scan_metric<kMetricL2, 32>(p, QT, grid, smem, st);
-      case kMetricCos: return launch_scan_metric<kMetricCos, 32>(p, QT, grid, smem, st);
-      case kMetricDot: return launch_scan_metric<kMetricDot, 32>(p, QT, grid, smem, st);
-    }
+  const size_t smem = scan_smem_bytes(QT, p.iv.dpad, p.K, p.nstages, p.stage_floats);
+  if (p.rows_per_stage > kMaxRounds * NW * (32 / p.lanes_per_row)) return cudaErrorInvalidValue;
+  if (p.iv.n_slots >= 0xFFFFFFF0ll) return cudaErrorInvalidValue;
+  switch (p.iv.metric) {
+    case kMetricL2: return launch_scan_shape<kMetricL2>(p, QT, grid, smem, st);
+    case kMetricCos: return launch_scan_shape<kMetricCos>(p, QT, grid, smem, st);
+    case kMetricDot: return launch_scan_shape<kMetricDot>(p, QT, grid, smem, st);
   }
   return cudaErrorInvalidValue;
 }
