@@ -515,7 +515,7 @@ struct SearchArgs {
 };
 
 // Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
-int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStream_t st) {
+int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStream_t st, bool first_chunk, bool last_chunk) {
   const int q = (int)a.q;
   const int grid_sm = h->opt_grid > 0 ? h->opt_grid : h->sm_count;
   IndexView iv = h->view();
@@ -534,7 +534,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
   CU_TRY(c->fb_list.ensure((size_t)q * 4));
   if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
-  CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+  if (first_chunk) CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
   Ctrl* ctrl = c->ctrl.as<Ctrl>();
 
   PrepQueriesParams pq{};
@@ -661,9 +661,9 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
                                : std::min(1024, pow2_at_least(std::max<int>(64, 4 * (int)a.kmax)));
   const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
   const int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
-  // candidate slots per (query, CTA): 4x the expected hits of a slice (+ slack), power of two
-  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(32, 4 * hits / std::max(main_grid, 1) + 16)));
-  const int64_t cand_stride = (int64_t)main_grid * cap;  // per query
+  // candidate slots per (query, CTA, column half): 4x the expected hits of a slice (+ slack), power of two
+  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * main_grid, 1) + 12)));
+  const int64_t cand_stride = (int64_t)main_grid * 2 * cap;  // per query
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
   // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`
@@ -677,7 +677,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   CU_TRY(c->cand_fb.ensure((size_t)q * scan_stride * 8));
   CU_TRY(c->cand_fb_cnt.ensure((size_t)q * 4));
   CU_TRY(c->thresh.ensure((size_t)q * 4));
-  CU_TRY(c->seeds.ensure((size_t)q * seed_tiles * kSeedR * 4));
+  CU_TRY(c->seeds.ensure((size_t)q * seed_tiles * 2 * kSeedR * 4));
   CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));  // sentinels
   CU_TRY(launch_fill_u32(c->cand_cnt.as<uint32_t>(), (uint32_t)cand_stride, q, st));
 
@@ -739,8 +739,27 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   s2.nq = 0;
   s2.certify = 0;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
+  if (!last_chunk) CU_TRY(cudaMemsetAsync(&ctrl->fb_count, 0, 4, st));  // the next chunk starts an empty fallback list
   h->n_launch += 7;
   h->n_tensor_q += q;
+  return GFI_OK;
+}
+
+// Enqueues one search batch; batches beyond the tensor kernel's per-launch query limit are cut into chunks.
+int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStream_t st) {
+  const int64_t lim = kGemmMaxQueries;
+  if (a.q <= lim) return enqueue_chunk(h, c, a, st, true, true);
+  for (int64_t q0 = 0; q0 < a.q; q0 += lim) {
+    SearchArgs s = a;
+    s.q = std::min(lim, a.q - q0);
+    s.d_queries = a.d_queries + q0 * h->dim;
+    s.d_ks = a.d_ks + q0;
+    s.d_out_ids = a.d_out_ids + q0 * a.kstride;
+    s.d_out_dist = a.d_out_dist + q0 * a.kstride;
+    s.d_out_counts = a.d_out_counts + q0;
+    int32_t rc = enqueue_chunk(h, c, s, st, q0 == 0, q0 + lim >= a.q);
+    if (rc != GFI_OK) return rc;
+  }
   return GFI_OK;
 }
 
@@ -1070,7 +1089,7 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   CU_TRY(cudaStreamSynchronize(st));
   prof_collect(h, c);
   const Ctrl* hc = c->h_ctrl.as<Ctrl>();
-  h->n_fallback_q += hc->fb_count;
+  h->n_fallback_q += hc->uncertified;
   if ((rc = flags_to_status(hc->flags)) != GFI_OK) return rc;
   const uint32_t* hcnt = c->h_counts.as<uint32_t>();
   for (int64_t i = 0; i < q; ++i) {
@@ -1138,7 +1157,7 @@ int32_t gfi_search_status(gfi_index* h) {
   c->pending_status = false;
   prof_collect(h, c);
   const Ctrl* hc = c->h_ctrl.as<Ctrl>();
-  h->n_fallback_q += hc->fb_count;
+  h->n_fallback_q += hc->uncertified;
   return flags_to_status(hc->flags);
 }
 

@@ -7,16 +7,20 @@
 // (src/storage.rs:302-310) over FlatIndex::search (src/flat_index.rs:52-65): each database
 // tile is read from HBM once and reused for every query of the batch.
 //
-// Structure (one persistent CTA per SM, 192 threads):
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
 //   warp 0      TMA producer: 2-D tiled bulk loads (SWIZZLE_128B) of a 128x64 query block and a
 //               256x64 row block per k-step into a 4-stage shared-memory ring (mbarrier full/empty)
 //   warp 1      MMA issuer: one lane issues 4 x tcgen05.mma (M=128,N=256,K=16) per k-step into one
 //               of two 256-column TMEM accumulators; tcgen05.commit releases ring slots and
 //               publishes finished accumulators
-//   warps 2-5   epilogue: thread == query.  tcgen05.ld 32 columns at a time, one FMA per value
-//               (score = acc * a[row] + b[row], which covers L2 / cosine / dot, per-row fp16 scale,
-//               tombstones and the filter mask via b = +inf), compare against the query's
-//               threshold, and append the rare survivors to the query's candidate list.
+//   warp 2      coefficient stager: per row of the tile the epilogue pair (a, b) -- metric, per-row
+//               fp16 scale, tombstone and filter bit (b = +inf) -- loaded one item ahead and
+//               published through an mbarrier, so the epilogue never waits on global memory
+//   warps 4-11  epilogue, thread == (query, half of the tile's columns): tcgen05.ld 32 columns at
+//               a time, one FMA per value (score = acc * a[row] + b[row]), a min tree and ONE
+//               compare per 32 values against the query's threshold; the rare survivors are
+//               appended with plain stores to a slice of the candidate buffer that is private to
+//               this (query, CTA, half) -- no atomics.
 // The thresholds come from a seed pass of the same kernel over an evenly strided sample of
 // tiles (seed_mode = 1).  Scores are approximate (fp16 inputs); select_rerank.cu re-scores the
 // best candidates with the reference's exact arithmetic and certifies the result.
@@ -33,17 +37,19 @@ constexpr int BM = 128, BN = 256, BK = 64;
 constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;  // 16 KB
 constexpr int kBBytes = BN * BK * 2;  // 32 KB
-constexpr int kGemmThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kGemmThreads = 384;
+constexpr int kEpiWarp0 = 4;          // first epilogue warp
+constexpr int kEpiThreads = 256;
 constexpr uint32_t kTmemCols = 512;
 
 constexpr size_t kOffA = 0;
 constexpr size_t kOffB = kOffA + (size_t)kStages * kABytes;
 constexpr size_t kOffCoef = kOffB + (size_t)kStages * kBBytes;
 constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
-constexpr size_t kOffCnt = kOffBar + 16 * 8 + 16;  // u8 hit counters, one per query of the batch
-constexpr size_t kSmemUsed = kOffCnt + 2 * kGemmMaxQueries;
+constexpr size_t kOffCnt = kOffBar + 16 * 8 + 16;  // u16 hit counters [2 halves][queries]
+constexpr size_t kSmemUsed = kOffCnt + 2 * 2 * kGemmMaxQueries;
 constexpr size_t kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
+static_assert(kSmemBytes <= 232448, "shared memory budget");
 
 // UMMA instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, N=256, M=128.
 constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -65,6 +71,21 @@ __device__ __forceinline__ float pow2_scale_inv(float maxabs) {
   return __uint_as_float((uint32_t)(127 - se) << 23);
 }
 
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
+// item -> (row tile, query tile).  The query tile is rotated by the row-tile index so that every
+// CTA meets every query tile: a query's candidates then spread evenly over all CTAs' slices.
+__device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, int64_t& nt_idx, int64_t& n_tile,
+                                           int& m_tile) {
+  nt_idx = w / p.num_m_tiles;
+  m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);
+  n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+}
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                  const GemmParams p) {
@@ -76,12 +97,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   float2* sCoef = reinterpret_cast<float2*>(smem + kOffCoef);
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffBar);
   uint64_t* empty = full + kStages;
-  uint64_t* tfull = empty + kStages;
-  uint64_t* tempty = tfull + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  // u16 hit counter per query, private to this CTA: no atomics on the hot path.  Items map to
-  // (row tile, query tile) with a rotation so that every CTA meets every query tile and a query's
-  // candidates spread evenly over all CTAs' slices.
+  uint64_t* tfull = empty + kStages;   // accumulator stage complete (MMA -> epilogue)
+  uint64_t* tempty = tfull + 2;        // accumulator + coefficient stage drained (epilogue -> MMA, stager)
+  uint64_t* cfull = tempty + 2;        // coefficient stage published (stager -> epilogue)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + 2);
   unsigned short* hitcnt = reinterpret_cast<unsigned short*>(smem + kOffCnt);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -97,10 +116,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], kEpiThreads);
+      mbar_init(&cfull[s], 1);
     }
     fence_mbar_init();
   }
-  for (int i = tid; i < p.num_m_tiles * BM; i += kGemmThreads) hitcnt[i] = 0;
+  for (int i = tid; i < 2 * kGemmMaxQueries; i += kGemmThreads) hitcnt[i] = 0;
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmx);
     tma_prefetch_desc(&tmq);
@@ -116,14 +136,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
-    uint32_t it = 0;
+    int s = 0;
+    uint32_t ph = 0, it = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
-      const int64_t nt_idx = w / p.num_m_tiles;
-      const int m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);  // rotated: see item_tiles note
-      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+      int64_t nt_idx, n_tile;
+      int m_tile;
+      item_tiles(p, w, nt_idx, n_tile, m_tile);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
         mbar_wait(&empty[s], ph ^ 1u);
         if (lane == 0) {
           // p.debug (timing experiments only, results invalid): bit0 / bit1 stop re-loading A / B once the
@@ -136,19 +155,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           if (ldB) tma_load_2d(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN), &full[s]);
         }
         __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    uint32_t it = 0, ai = 0;
+    int s = 0;
+    uint32_t ph = 0, ai = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1u;
+      for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         if (lane == 0) {
@@ -159,78 +178,98 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             umma_f16(d_tmem, make_sw128_desc(a0 + k * 32), make_sw128_desc(b0 + k * 32), kIdesc,
                      (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&empty[s]);                       // ring slot free once these MMAs retire
+          umma_commit(&empty[s]);                         // ring slot free once these MMAs retire
           if (kb == num_kb - 1) umma_commit(&tfull[as]);  // accumulator complete
         }
         __syncwarp();
+        if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else {
-    // ------------------------------ epilogue: thread == query ------------------------------
-    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
-    const int et = (warp - 2) * 32 + lane;    // 0..127 among epilogue threads
-    const int mrow = quarter * 32 + lane;     // row of the 128-query tile owned by this thread
+  } else if (warp == 2) {
+    // ------------------------------ coefficient stager ------------------------------
+    // lane owns rows lane, lane+32, ... of the tile.  Raw loads for the NEXT item are issued before
+    // the current item's values are consumed, so nothing here waits on memory in steady state.
+    constexpr int RPL = BN / 32;  // rows per lane
     const float inv_sq = pow2_scale_inv(*p.qmaxabs);
     const float kInf = __int_as_float(0x7f800000);
-
-    // per-row epilogue coefficients (a, b) of rows et and et+128 of an item's tile; ineligible rows
-    // (beyond the index, tombstoned, filtered out) get (0, +inf) so they can never pass a threshold
-    auto load_coef = [&](int64_t w, float2 (&c)[2]) {
-      const int64_t nt_idx = w / p.num_m_tiles;
-      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+    const bool has_mask = p.mask.bits != nullptr;
+    const bool by_slot = has_mask && iv.ids_identity;
+    struct Raw { float2 c[RPL]; uint32_t live[RPL]; uint64_t mask[RPL]; };
+    auto fetch = [&](int64_t w, Raw& r) {
+      int64_t nt_idx, n_tile;
+      int m_tile;
+      item_tiles(p, w, nt_idx, n_tile, m_tile);
 #pragma unroll
-      for (int rr = 0; rr < 2; ++rr) {
-        const int64_t slot = n_tile * BN + et + rr * kEpiThreads;
-        c[rr] = make_float2(0.f, kInf);
+      for (int i = 0; i < RPL; ++i) {
+        const int64_t slot = n_tile * BN + lane + 32 * i;
+        r.c[i] = make_float2(0.f, kInf);
+        r.live[i] = 0;
+        r.mask[i] = ~0ull;
         if (slot < iv.n_slots) {
-          bool elig = (iv.live[slot >> 5] >> (slot & 31)) & 1u;
-          if (elig && p.mask.bits) {
-            const uint64_t id = iv.ids_identity ? (uint64_t)slot : iv.ids[slot];
-            elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
-          }
-          if (elig) {
-            c[rr] = iv.coef[slot];
-            c[rr].x *= inv_sq;
-          }
+          r.c[i] = __ldg(iv.coef + slot);
+          r.live[i] = __ldg(iv.live + (slot >> 5));
+          if (by_slot) r.mask[i] = slot < p.mask.nbits ? __ldg(p.mask.bits + (slot >> 6)) : 0ull;
         }
       }
     };
-
-    float2 cnext[2];
-    if ((int64_t)blockIdx.x < n_items) load_coef(blockIdx.x, cnext);
+    Raw nxt;
+    if ((int64_t)blockIdx.x < n_items) fetch(blockIdx.x, nxt);
     uint32_t ai = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
-      const int64_t nt_idx = w / p.num_m_tiles;
-      const int m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);  // rotated: see item_tiles note
-      const int64_t n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+      int64_t nt_idx, n_tile;
+      int m_tile;
+      item_tiles(p, w, nt_idx, n_tile, m_tile);
+      const Raw cur = nxt;
+      if (w + gridDim.x < n_items) fetch(w + gridDim.x, nxt);
+      mbar_wait(&tempty[as], aph ^ 1u);  // the epilogue has drained the previous use of this stage
+      float2* cs = sCoef + as * BN;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int64_t slot = n_tile * BN + lane + 32 * i;
+        bool elig = ((cur.live[i] >> (slot & 31)) & 1u) && ((cur.mask[i] >> (slot & 63)) & 1ull);
+        if (elig && has_mask && !by_slot) {
+          const uint64_t id = iv.ids[slot];
+          elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
+        }
+        cs[lane + 32 * i] = elig ? make_float2(cur.c[i].x * inv_sq, cur.c[i].y) : make_float2(0.f, kInf);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cfull[as]);
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------ epilogue: thread == (query, column half) ------------------------------
+    const int quarter = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - kEpiWarp0) >> 2;     // which 128 columns of the 256-column tile
+    const int mrow = quarter * 32 + lane;         // row of the 128-query tile owned by this thread
+    const float kInf = __int_as_float(0x7f800000);
+    uint32_t ai = 0;
+    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
+      const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
+      int64_t nt_idx, n_tile;
+      int m_tile;
+      item_tiles(p, w, nt_idx, n_tile, m_tile);
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
-      float2* cs = sCoef + as * BN;
-      cs[et] = cnext[0];
-      cs[et + kEpiThreads] = cnext[1];
-      named_bar_sync(2, kEpiThreads);
-      // the next item's coefficient loads stay in flight while this item is processed
-      if (w + gridDim.x < n_items) load_coef(w + gridDim.x, cnext);
-
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
       if (p.seed_mode == 0 && qidx < p.q) thr = p.thresh[qidx];
       float sd[kSeedR];
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
 
+      mbar_wait(&cfull[as], aph);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
+      const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN); c0 += 32) {
+      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         // 32 (a,b) pairs as 16 broadcast 128-bit shared loads, issued while the TMEM load is in flight
         float4 cf[16];
-        const float4* c4 = reinterpret_cast<const float4*>(cs + c0);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cf[i] = c4[i];
+        for (int i = 0; i < 16; ++i) cf[i] = lds128(cs_addr + (c0 + 2 * i) * 8);
         tmem_ld_wait();
         float sc[32];
 #pragma unroll
@@ -238,6 +277,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           sc[2 * i] = fmaf(__uint_as_float(r[2 * i]), cf[i].x, cf[i].y);
           sc[2 * i + 1] = fmaf(__uint_as_float(r[2 * i + 1]), cf[i].z, cf[i].w);
         }
+        const int col0 = half * (BN / 2) + c0;
         if (p.seed_mode == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
@@ -255,45 +295,51 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           // debug dump of every approximate score (tests only; small inputs)
           if (qidx < p.q) {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + c0 + j)] = sc[j];
+            for (int j = 0; j < 32; ++j) p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + col0 + j)] = sc[j];
           }
         } else {
           // common case: no value of the block beats the threshold -> one min tree + one compare.
           // (fminf drops NaN operands; a NaN query makes every score NaN, which still reaches the slow path.)
-          float m[16];
+          float m8[4];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) m[i] = fminf(sc[2 * i], sc[2 * i + 1]);
-#pragma unroll
-          for (int w2 = 8; w2 > 0; w2 >>= 1) {
-#pragma unroll
-            for (int i = 0; i < w2; ++i) m[i] = fminf(m[i], m[i + w2]);
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float a = fminf(fminf(sc[8 * g8], sc[8 * g8 + 1]), fminf(sc[8 * g8 + 2], sc[8 * g8 + 3]));
+            const float b = fminf(fminf(sc[8 * g8 + 4], sc[8 * g8 + 5]), fminf(sc[8 * g8 + 6], sc[8 * g8 + 7]));
+            m8[g8] = fminf(a, b);
           }
-          if (!(m[0] >= thr) && qidx < p.q && !(p.debug & 8)) {
-            // rare: append to this (query, CTA)'s private slice of the candidate buffer -- plain
-            // stores, no atomics, nothing to wait for
-            uint32_t cnt = hitcnt[qidx];
-            uint64_t* mine = p.cand + (size_t)qidx * p.cand_stride + (size_t)blockIdx.x * p.cand_cap;
+          const float mall = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
+          if (!(mall >= thr) && qidx < p.q && !(p.debug & 8)) {
+            // rare: append to the slice of the candidate buffer private to this (query, CTA, half):
+            // plain stores, no atomics, nothing to wait for
+            unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
+            uint32_t cnt = *hc;
+            uint64_t* mine = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float score = sc[j];
-              if (!(score >= thr)) {
-                if (score != score) {
-                  atomicOr(p.flags, kFlagNaN);
-                } else {
-                  if (cnt < p.cand_cap) mine[cnt] = pack_key(score, (uint32_t)(n0 + c0 + j));
-                  else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: this query falls back to the scan
-                  ++cnt;
+            for (int g8 = 0; g8 < 4; ++g8) {
+              if (!(m8[g8] >= thr)) {
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float score = sc[8 * g8 + jj];
+                  if (!(score >= thr)) {
+                    if (score != score) {
+                      atomicOr(p.flags, kFlagNaN);
+                    } else {
+                      if (cnt < p.cand_cap) mine[cnt] = pack_key(score, (uint32_t)(n0 + col0 + 8 * g8 + jj));
+                      else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: the query falls back to the scan
+                      ++cnt;
+                    }
+                  }
                 }
               }
             }
-            hitcnt[qidx] = (unsigned short)min(cnt, 65535u);
+            *hc = (unsigned short)min(cnt, 65535u);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
       if (p.seed_mode == 1 && qidx < p.q) {
-        float* out = p.seeds + ((size_t)qidx * p.seed_tiles + nt_idx) * kSeedR;
+        float* out = p.seeds + (((size_t)qidx * p.seed_tiles + nt_idx) * 2 + half) * kSeedR;
 #pragma unroll
         for (int i = 0; i < kSeedR; ++i) out[i] = sd[i];
       }
@@ -313,7 +359,7 @@ __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
   const int lane = threadIdx.x & 31;
   const int qi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (qi >= p.q) return;
-  const int64_t total = p.seed_tiles * kSeedR;
+  const int64_t total = p.seed_tiles * 2 * kSeedR;
   const float* s = p.seeds + (size_t)qi * total;
   uint64_t prev = 0;
   uint64_t cur = ~0ull;
@@ -343,6 +389,7 @@ size_t gemm_smem_bytes() { return kSmemBytes; }
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
                              cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
+  if (p.num_m_tiles * BM > kGemmMaxQueries) return cudaErrorInvalidValue;
   cudaError_t e =
       cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   if (e != cudaSuccess) return e;

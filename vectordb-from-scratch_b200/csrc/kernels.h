@@ -121,17 +121,17 @@ struct GemmParams {
   int64_t num_n_tiles;
   // seed mode: per (sample tile, query) the R smallest scores; main mode: threshold filter
   int seed_mode; int64_t seed_tiles, seed_stride;
-  float* seeds;         // [q][seed_tiles][R]
+  float* seeds;         // [q][seed_tiles][2 column halves][R]
   const float* thresh;  // [q]
-  // main mode: cand[q][cand_stride] is pre-filled with sentinels; CTA b appends to the slice
-  // [b*cand_cap, (b+1)*cand_cap) of each query; cand_cnt[q] is pre-set to cand_stride and only
+  // main mode: cand[q][cand_stride] is pre-filled with sentinels; CTA b, column half h appends to the
+  // slice [(2b+h)*cand_cap, (2b+h+1)*cand_cap) of each query; cand_cnt[q] is pre-set to cand_stride and only
   // overwritten (0xffffffff) when a slice overflows
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
   uint32_t* flags;
   int debug;            // timing experiments only (see gemm_topk.cu)
 };
 constexpr int kSeedR = 8;
-constexpr int kGemmMaxQueries = 8192;   // per launch (u16 hit counter per query in shared memory)
+constexpr int kGemmMaxQueries = 4096;   // per launch (u16 hit counters [2 column halves][query] in shared memory)
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
                              cudaStream_t st);
 struct SeedFinalizeParams {
