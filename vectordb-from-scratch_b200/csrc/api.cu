@@ -650,6 +650,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     s.nq_dev = nullptr;
     s.nq = q;
     s.certify = 0;
+    s.list_len = K;
     CU_TRY(launch_select_rerank(s, std::min(q, grid_sm * 8), st));
     h->n_launch += 2;
     h->n_scan_q += q;
@@ -738,6 +739,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s2.nq_dev = &ctrl->fb_count;
   s2.nq = 0;
   s2.certify = 0;
+  s2.list_len = K;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
   if (!last_chunk) CU_TRY(cudaMemsetAsync(&ctrl->fb_count, 0, 4, st));  // the next chunk starts an empty fallback list
   h->n_launch += 7;

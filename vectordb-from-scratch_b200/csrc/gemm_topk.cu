@@ -355,31 +355,43 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
 }
 
 // One warp per query: the rank-th smallest of the query's seed scores becomes its threshold.
+// Each lane keeps the kSeedR smallest of its strided share in registers (single pass), then the warp
+// pops the global minimum `rank` times.
 __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
   const int lane = threadIdx.x & 31;
   const int qi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (qi >= p.q) return;
+  const float kInf = __int_as_float(0x7f800000);
   const int64_t total = p.seed_tiles * 2 * kSeedR;
   const float* s = p.seeds + (size_t)qi * total;
-  uint64_t prev = 0;
-  uint64_t cur = ~0ull;
-  for (int r = 0; r < p.rank; ++r) {
-    uint64_t best = ~0ull;
-    for (int64_t i = lane; i < total; i += 32) {
-      const float v = s[i];
-      if (v != v) continue;
-      const uint64_t key = ((uint64_t)f32_key(v) << 32) | (uint32_t)(i + 1);
-      if (key > prev && key < best) best = key;
+  float sd[kSeedR];
+#pragma unroll
+  for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
+  for (int64_t i = lane; i < total; i += 32) {
+    const float v = s[i];
+    if (v < sd[kSeedR - 1]) {  // false for NaN
+      sd[kSeedR - 1] = v;
+#pragma unroll
+      for (int j = kSeedR - 1; j > 0; --j) {
+        const float lo = fminf(sd[j - 1], sd[j]), hi = fmaxf(sd[j - 1], sd[j]);
+        sd[j - 1] = lo;
+        sd[j] = hi;
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const uint64_t other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other < best ? other : best;
-    }
-    cur = best;
-    if (best == ~0ull) break;
-    prev = best;
   }
-  if (lane == 0) p.thresh[qi] = (cur == ~0ull) ? __int_as_float(0x7f800000) : key_f32((uint32_t)(cur >> 32));
+  float cur = kInf;
+  for (int r = 0; r < p.rank; ++r) {
+    float m = sd[0];
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    cur = m;
+    const unsigned owners = __ballot_sync(0xffffffffu, sd[0] == m);
+    if (owners && lane == __ffs(owners) - 1) {  // pop this lane's head
+#pragma unroll
+      for (int j = 0; j < kSeedR - 1; ++j) sd[j] = sd[j + 1];
+      sd[kSeedR - 1] = kInf;
+    }
+  }
+  if (lane == 0) p.thresh[qi] = cur;
 }
 
 }  // namespace

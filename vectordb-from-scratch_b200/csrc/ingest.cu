@@ -76,26 +76,31 @@ __global__ void row_stats_kernel(const IngestParams p) {
   }
 }
 
-// One warp per query: pad/copy, batch max|q|, reference-exact sum of squares and norm.
+// One warp per query: pad/copy, batch max|q|, reference-exact sum of squares and norm.  The query is
+// staged in shared memory so the sequential exact chain runs on pipelined shared loads.
 __global__ void prep_queries_kernel(const PrepQueriesParams p) {
-  const int qi = blockIdx.x;
-  const int lane = threadIdx.x;
+  extern __shared__ float sq[];  // [warps per block][dpad] or unused when the query is too long
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
+  if (qi >= p.q) return;
   const float* src = p.q_in + (size_t)qi * p.d;
   float* dst = p.q32 + (size_t)qi * p.dpad;
+  float* mine = p.use_smem ? sq + (size_t)warp * p.dpad : nullptr;
   float m = 0.f;
   for (int c = lane; c < p.dpad; c += 32) {
     const float v = c < p.d ? src[c] : 0.f;
     dst[c] = v;
+    if (mine) mine[c] = v;
     m = fmaxf(m, fabsf(v));  // NaN is ignored by fmaxf; NaN queries surface as NaN distances later
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  __syncwarp();
   if (lane == 0) {
     if (p.qmaxabs) atomicMax(reinterpret_cast<unsigned int*>(p.qmaxabs), __float_as_uint(m));
+    const float* v = mine ? mine : src;
     float acc = -0.0f;
-    for (int i = 0; i < p.d; ++i) {
-      const float v = src[i];
-      acc = __fadd_rn(acc, __fmul_rn(v, v));
-    }
+#pragma unroll 8
+    for (int i = 0; i < p.d; ++i) acc = __fadd_rn(acc, __fmul_rn(v[i], v[i]));
     p.qsumsq[qi] = acc;
     p.qnorm[qi] = __fsqrt_rn(acc);
   }
@@ -189,7 +194,13 @@ cudaError_t launch_ingest(const IngestParams& p, cudaStream_t st) {
 
 cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st) {
   if (p.q <= 0) return cudaSuccess;
-  prep_queries_kernel<<<p.q, 32, 0, st>>>(p);
+  {
+    PrepQueriesParams pp = p;
+    const int wpb = 4;
+    const size_t smem = (size_t)wpb * p.dpad * 4;
+    pp.use_smem = smem <= 48 * 1024 ? 1 : 0;
+    prep_queries_kernel<<<(p.q + wpb - 1) / wpb, wpb * 32, pp.use_smem ? smem : 0, st>>>(pp);
+  }
   if (p.q16) {
     const int64_t total = (int64_t)p.qpad * p.dpad16;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);

@@ -79,6 +79,7 @@ struct PrepQueriesParams {
   float* qnorm; float* qsumsq;
   float* qmaxabs;      // [1] max |q| over the batch (for the common fp16 scale)
   int q, qpad, d, dpad, dpad16;
+  int use_smem;        // set by launch_prep_queries
 };
 cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st);
 
@@ -91,6 +92,7 @@ struct SelectParams {
   const uint32_t* nq_dev; int nq;
   const uint64_t* cand; const uint32_t* cand_cnt; int64_t cand_stride;
   int KP;                     // candidates reranked per query (power of two <= 1024)
+  int list_len;               // > 0: the input is ascending lists of this length (scan path); 0: unordered slices
   // certification (tensor path): every row that is not a candidate has approx score >= cutoff
   int certify;                // 0 = scan path (never falls back), 1 = tensor path
   const float* thresh;        // per-query score threshold used by the tensor kernel

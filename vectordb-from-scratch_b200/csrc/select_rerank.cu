@@ -74,12 +74,62 @@ __device__ __forceinline__ float exact_distance(const float* __restrict__ q, con
   return __fsub_rn(1.0f, sim);
 }
 
+constexpr int kSelCap = 2048;     // valid candidate keys kept in shared memory (else: passes over global memory)
+constexpr int kTileFloats = 4096;  // rerank tile: GC candidates x CW floats, GC * CW = 4096
+
+// Exact 64-bit radix select: returns the `need`-th smallest (1-based) of the valid keys in src[0..cnt).
+__device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t cnt, uint32_t need, uint64_t bound,
+                                                 uint32_t* hist, uint32_t* s_bucket, uint32_t* s_need, int tid) {
+  uint64_t prefix = 0, mask = 0;
+  for (int pass = 0; pass < 8; ++pass) {
+    const int shift = 56 - 8 * pass;
+    hist[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = tid; i < cnt; i += kSelThreads) {
+      const uint64_t key = src[i];
+      if (key <= bound && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
+    }
+    __syncthreads();
+    if (tid < 32) {
+      // each lane owns 8 consecutive buckets
+      uint32_t h[8], sum = 0;
+#pragma unroll
+      for (int b = 0; b < 8; ++b) { h[b] = hist[tid * 8 + b]; sum += h[b]; }
+      uint32_t incl = sum;
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (tid >= o) incl += v;
+      }
+      uint32_t before = incl - sum;
+      if (before < need && need <= incl) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) {
+          if (need <= before + h[b]) { *s_bucket = tid * 8 + b; *s_need = need - before; break; }
+          before += h[b];
+        }
+      }
+    }
+    __syncthreads();
+    prefix |= (uint64_t)(*s_bucket) << shift;
+    mask |= 0xffull << shift;
+    need = *s_need;
+    __syncthreads();
+  }
+  return prefix;
+}
+
 template <int METRIC>
 __global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const SelectParams p) {
+  // keys[] (compacted valid candidates) is dead once the selection is made; the rerank tiles reuse it
+  __shared__ __align__(16) unsigned char s_union[2 * (kTileFloats + 256) * 4];
   __shared__ uint64_t sel[kMaxKP];
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need;
-  const int tid = threadIdx.x;
+  __shared__ uint32_t bslot[256];
+  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need, s_bound_hi, s_bound_lo;
+  static_assert(sizeof(s_union) >= kSelCap * 8, "key buffer must fit the union");
+  uint64_t* keys = reinterpret_cast<uint64_t*>(s_union);
+  float* tiles = reinterpret_cast<float*>(s_union);
+  const int tid = threadIdx.x, lane = tid & 31;
   const IndexView& iv = p.iv;
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
 
@@ -92,90 +142,145 @@ __global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const Select
     const uint32_t k = p.ks[qg];
     const int KP = p.KP;
 
-    // ---- count valid keys ----
-    if (tid == 0) { s_count = 0; s_nvalid = 0; }
+    // ---- one pass over the candidate buffer: compact the useful keys into shared memory ----
+    // Scan-path input is `cnt / list_len` ascending lists: the smallest of the lists' last keys is an
+    // upper bound on the K-th best key overall, so only keys <= that bound can matter.
+    if (tid == 0) { s_count = 0; s_nvalid = 0; s_bound_hi = 0xffffffffu; s_bound_lo = 0xffffffffu; }
     __syncthreads();
-    uint32_t local = 0;
-    for (uint32_t i = tid; i < cnt; i += kSelThreads) local += (cand[i] != kKeySentinel);
-    for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
-    if ((tid & 31) == 0 && local) atomicAdd(&s_nvalid, local);
+    uint64_t bound = kKeySentinel - 1;
+    if (p.list_len > 0 && p.KP <= p.list_len) {
+      uint64_t mine = kKeySentinel;
+      for (uint32_t l = tid; l * (uint32_t)p.list_len < cnt; l += kSelThreads)
+        mine = min(mine, cand[(size_t)l * p.list_len + p.list_len - 1]);
+      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
+      if (lane == 0) atomicMin(&s_bound_hi, (uint32_t)(mine >> 32));
+      __syncthreads();
+      if (lane == 0 && (uint32_t)(mine >> 32) == s_bound_hi) atomicMin(&s_bound_lo, (uint32_t)mine);
+      __syncthreads();
+      bound = ((uint64_t)s_bound_hi << 32) | s_bound_lo;
+      if (bound == kKeySentinel) bound = kKeySentinel - 1;
+    }
+    for (uint32_t i0 = 0; i0 < cnt; i0 += kSelThreads * 4) {
+      uint64_t kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // loads first: four round trips overlap
+        const uint32_t i = i0 + u * kSelThreads + tid;
+        kk[u] = i < cnt ? cand[i] : kKeySentinel;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool valid = kk[u] <= bound;  // the sentinel is above every bound
+        const unsigned m = __ballot_sync(0xffffffffu, valid);
+        if (m) {
+          uint32_t base = 0;
+          if (lane == 0) base = atomicAdd(&s_nvalid, (uint32_t)__popc(m));
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+          if (valid && pos < (uint32_t)kSelCap) keys[pos] = kk[u];
+        }
+      }
+    }
     __syncthreads();
     const uint32_t nvalid = s_nvalid;
     const uint32_t kpeff = min((uint32_t)KP, nvalid);
+    const bool in_smem = nvalid <= (uint32_t)kSelCap;
+    const uint64_t* src = in_smem ? keys : cand;
+    const uint32_t src_n = in_smem ? nvalid : cnt;
 
-    // ---- exact radix select of the kpeff-th smallest key (only when nvalid > KP) ----
+    // ---- exact radix select of the KP-th smallest key (only when there are more than KP) ----
     uint64_t pivot = kKeySentinel - 1;  // everything valid is <= pivot
-    if (nvalid > (uint32_t)KP) {
-      uint64_t prefix = 0, mask = 0;
-      uint32_t need = KP;
-      for (int pass = 0; pass < 8; ++pass) {
-        const int shift = 56 - 8 * pass;
-        hist[tid] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < cnt; i += kSelThreads) {
-          const uint64_t key = cand[i];
-          if (key != kKeySentinel && (key & mask) == prefix) atomicAdd(&hist[(key >> shift) & 0xffu], 1u);
-        }
-        __syncthreads();
-        if (tid < 32) {
-          // each lane owns 8 consecutive buckets
-          uint32_t h[8], sum = 0;
-#pragma unroll
-          for (int b = 0; b < 8; ++b) { h[b] = hist[tid * 8 + b]; sum += h[b]; }
-          uint32_t incl = sum;
-          for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
-            if (tid >= o) incl += v;
-          }
-          uint32_t before = incl - sum;
-          if (before < need && need <= incl) {
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-              if (need <= before + h[b]) { s_bucket = tid * 8 + b; s_need = need - before; break; }
-              before += h[b];
-            }
-          }
-        }
-        __syncthreads();
-        prefix |= (uint64_t)s_bucket << shift;
-        mask |= 0xffull << shift;
-        need = s_need;
-        __syncthreads();
-      }
-      pivot = prefix;
-    }
-
-    // ---- gather the selected keys ----
+    if (nvalid > (uint32_t)KP) pivot = radix_select(src, src_n, (uint32_t)KP, bound, hist, &s_bucket, &s_need, tid);
     for (int i = tid; i < kMaxKP; i += kSelThreads) sel[i] = kKeySentinel;
     __syncthreads();
-    for (uint32_t i = tid; i < cnt; i += kSelThreads) {
-      const uint64_t key = cand[i];
-      if (key != kKeySentinel && key <= pivot) {
+    for (uint32_t i = tid; i < src_n; i += kSelThreads) {
+      const uint64_t key = src[i];
+      if (key <= bound && key <= pivot) {
         const uint32_t pos = atomicAdd(&s_count, 1u);
         if (pos < (uint32_t)kMaxKP) sel[pos] = key;
       }
     }
-    __syncthreads();
+    __syncthreads();  // keys[] is dead from here on
 
-    // ---- reference-exact rerank ----
+    // ---- reference-exact rerank: candidate rows staged through shared-memory tiles with coalesced
+    //      loads, one thread per candidate walks its row in order (sequential f32 chain) ----
     const float qn = p.qnorm[qg];
     const float* qv = p.q32 + (size_t)qg * iv.dpad;
     if (METRIC == kMetricCos && nvalid > 0 && qn == 0.f && tid == 0) atomicOr(p.flags, kFlagZeroNorm);
-    for (uint32_t t = tid; t < kpeff; t += kSelThreads) {
-      const uint32_t slot = (uint32_t)(sel[t] & 0xffffffffu);
-      const float xn = (METRIC == kMetricCos) ? iv.norm[slot] : 1.f;
-      float dist;
-      if (METRIC == kMetricCos && (xn == 0.f || qn == 0.f)) {
-        atomicOr(p.flags, kFlagZeroNorm);
-        dist = 0.f;
-      } else {
-        dist = exact_distance<METRIC>(qv, iv.x32 + (size_t)slot * iv.dpad, iv.d, qn, xn);
+    const int GC = kpeff <= 64 ? 64 : (kpeff <= 128 ? 128 : 256);
+    const int CW = kTileFloats / GC;        // floats per row chunk
+    const int cw4 = CW >> 2;
+    const int tstride = CW + 1;             // odd stride: conflict-free column walks
+    const int nchunk = (iv.d + CW - 1) / CW;
+    for (uint32_t b0 = 0; b0 < kpeff; b0 += GC) {
+      const int nb = (int)min((uint32_t)GC, kpeff - b0);
+      __syncthreads();
+      if (tid < GC) bslot[tid] = tid < nb ? (uint32_t)(sel[b0 + tid] & 0xffffffffu) : 0xffffffffu;
+      __syncthreads();
+      float acc = -0.0f;
+      float4 stage[4];
+      auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = tid + kSelThreads * i;
+          const int row = idx / cw4, c4 = idx - row * cw4;
+          const int col = c * CW + 4 * c4;
+          const uint32_t slot = bslot[row];
+          stage[i] = (slot != 0xffffffffu && col < iv.dpad)
+                         ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)slot * iv.dpad + col))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      auto store_chunk = [&](float* tile) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int idx = tid + kSelThreads * i;
+          const int row = idx / cw4, c4 = idx - row * cw4;
+          float* dst = tile + row * tstride + 4 * c4;
+          dst[0] = stage[i].x; dst[1] = stage[i].y; dst[2] = stage[i].z; dst[3] = stage[i].w;
+        }
+      };
+      load_chunk(0);
+      store_chunk(tiles);
+      __syncthreads();
+      for (int c = 0; c < nchunk; ++c) {
+        float* cur = tiles + (c & 1) * (kTileFloats + 256);
+        float* nxt = tiles + ((c + 1) & 1) * (kTileFloats + 256);
+        if (c + 1 < nchunk) load_chunk(c + 1);  // global loads in flight during the chain below
+        if (tid < nb) {
+          const float* row = cur + tid * tstride;
+          const int c0 = c * CW;
+          const int lim = min(CW, iv.d - c0);
+#pragma unroll 8
+          for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, __ldg(qv + c0 + i), row[i]);
+        }
+        if (c + 1 < nchunk) store_chunk(nxt);
+        __syncthreads();
+      }
+      if (tid < nb) {
+        const uint32_t slot = bslot[tid];
+        float dist;
+        if (METRIC == kMetricL2) {
+          dist = __fsqrt_rn(acc);
+        } else if (METRIC == kMetricDot) {
+          dist = -acc;
+        } else {
+          const float xn = iv.norm[slot];
+          if (xn == 0.f || qn == 0.f) {
+            atomicOr(p.flags, kFlagZeroNorm);
+            dist = 0.f;
+          } else {
+            float sim = __fdiv_rn(acc, __fmul_rn(qn, xn));
+            if (sim < -1.0f) sim = -1.0f;
+            else if (sim > 1.0f) sim = 1.0f;
+            dist = __fsub_rn(1.0f, sim);
+          }
+        }
         if (dist != dist) {
           atomicOr(p.flags, kFlagNaN);
           dist = 0.f;
         }
+        sel[b0 + tid] = pack_key(dist, slot);
       }
-      sel[t] = pack_key(dist, slot);
     }
     __syncthreads();
     int N = 32;
