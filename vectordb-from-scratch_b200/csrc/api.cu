@@ -98,7 +98,7 @@ struct Ctrl {
 struct SearchCtx {
   cudaStream_t stream = nullptr;
   DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
-      fb_list, out_ids, out_dist, out_counts;
+      fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info;
   PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl;
   bool pending_status = false;  // device search issued, status not yet collected
   // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
@@ -107,7 +107,7 @@ struct SearchCtx {
   size_t ev_used = 0;
   void release() {
     for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &cand_fb, &cand_fb_cnt,
-                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts})
+                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info})
       b->release();
     for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl}) b->release();
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -533,6 +533,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->qsumsq.ensure((size_t)q * 4));
   CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
   CU_TRY(c->fb_list.ensure((size_t)q * 4));
+  CU_TRY(c->sel_keys.ensure((size_t)q * 1024 * 8));
+  CU_TRY(c->sel_info.ensure((size_t)q * sizeof(SelInfo)));
   if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
   if (first_chunk) CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
   Ctrl* ctrl = c->ctrl.as<Ctrl>();
@@ -613,6 +615,9 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   };
   auto fill_select = [&](SelectParams& s, DevBuf& cand, DevBuf& cnt, int64_t stride, int KP) {
     s.iv = iv;
+    s.sel_keys = c->sel_keys.as<uint64_t>();
+    s.sel_info = c->sel_info.as<SelInfo>();
+    s.nq_max = q;
     s.q32 = c->q32.as<float>();
     s.qnorm = c->qnorm.as<float>();
     s.qsumsq = c->qsumsq.as<float>();
@@ -652,7 +657,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     s.certify = 0;
     s.list_len = K;
     CU_TRY(launch_select_rerank(s, std::min(q, grid_sm * 8), st));
-    h->n_launch += 2;
+    h->n_launch += 3;
     h->n_scan_q += q;
     return GFI_OK;
   }
@@ -742,7 +747,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s2.list_len = K;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
   if (!last_chunk) CU_TRY(cudaMemsetAsync(&ctrl->fb_count, 0, 4, st));  // the next chunk starts an empty fallback list
-  h->n_launch += 7;
+  h->n_launch += 9;
   h->n_tensor_q += q;
   return GFI_OK;
 }

@@ -84,12 +84,23 @@ struct PrepQueriesParams {
 cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st);
 
 // ---- K3: select + reference-exact rerank + certification -----------------------------
+struct SelInfo {  // per query, written by select_kernel, consumed by rerank_finalize_kernel
+  uint64_t pivot;   // KP-th best approximate key (cut-off of the reranked set)
+  uint32_t nvalid;  // useful candidate keys seen
+  uint32_t kpeff;   // candidates selected for rerank = min(KP, nvalid)
+  uint32_t overflow;
+  uint32_t done;    // warps of this query that finished their rerank share
+};
 struct SelectParams {
   IndexView iv;
   const float* q32; const float* qnorm; const float* qsumsq;
   const uint32_t* ks;         // per-query k
   const uint32_t* qlist;      // null = all
   const uint32_t* nq_dev; int nq;
+  int nq_max;                 // upper bound on *nq_dev (grid sizing of the predicated launches)
+  int few_candidates, warp_per_candidate;  // set by launch_select_rerank (latency modes for small batches)
+  uint64_t* sel_keys;         // [q][KP] scratch: selected approximate keys, then exact keys
+  SelInfo* sel_info;          // [q]
   const uint64_t* cand; const uint32_t* cand_cnt; int64_t cand_stride;
   int KP;                     // candidates reranked per query (power of two <= 1024)
   int list_len;               // > 0: the input is ascending lists of this length (scan path); 0: unordered slices

@@ -10,6 +10,8 @@
 // on the fp16 dot-product error it proves that no row outside the reranked set can belong to
 // the top-k; queries that cannot be certified are appended to a fallback list and re-run on
 // the exact scan kernel.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -118,20 +120,16 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
   return prefix;
 }
 
-template <int METRIC>
-__global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const SelectParams p) {
-  // keys[] (compacted valid candidates) is dead once the selection is made; the rerank tiles reuse it
-  __shared__ __align__(16) unsigned char s_union[2 * (kTileFloats + 256) * 4];
+// ---- K3a: per query, pick the KP best candidate keys (by approximate score) ----------------------
+__global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  __shared__ uint64_t keys[kSelCap];
   __shared__ uint64_t sel[kMaxKP];
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t bslot[256];
-  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need, s_bound_hi, s_bound_lo;
-  static_assert(sizeof(s_union) >= kSelCap * 8, "key buffer must fit the union");
-  uint64_t* keys = reinterpret_cast<uint64_t*>(s_union);
-  float* tiles = reinterpret_cast<float*>(s_union);
+  __shared__ uint64_t keys2[kSelCap];  // prefix keys of the sorted-list path (keys[] holds the heads meanwhile)
+  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need;
   const int tid = threadIdx.x, lane = tid & 31;
-  const IndexView& iv = p.iv;
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
+  auto sel_stage = [&](uint64_t*, uint32_t pos, uint64_t key) { keys2[pos] = key; };
 
   for (int qq = blockIdx.x; qq < nq; qq += gridDim.x) {
     const uint32_t qg = p.qlist ? p.qlist[qq] : (uint32_t)qq;
@@ -139,44 +137,79 @@ __global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const Select
     const uint32_t cnt_raw = p.cand_cnt[qg];
     const bool overflow = cnt_raw > (uint32_t)p.cand_stride;
     const uint32_t cnt = overflow ? (uint32_t)p.cand_stride : cnt_raw;
-    const uint32_t k = p.ks[qg];
     const int KP = p.KP;
 
-    // ---- one pass over the candidate buffer: compact the useful keys into shared memory ----
-    // Scan-path input is `cnt / list_len` ascending lists: the smallest of the lists' last keys is an
-    // upper bound on the K-th best key overall, so only keys <= that bound can matter.
-    if (tid == 0) { s_count = 0; s_nvalid = 0; s_bound_hi = 0xffffffffu; s_bound_lo = 0xffffffffu; }
+    // ---- compact the useful keys into shared memory ----
+    if (tid == 0) { s_count = 0; s_nvalid = 0; }
     __syncthreads();
     uint64_t bound = kKeySentinel - 1;
-    if (p.list_len > 0 && p.KP <= p.list_len) {
-      uint64_t mine = kKeySentinel;
-      for (uint32_t l = tid; l * (uint32_t)p.list_len < cnt; l += kSelThreads)
-        mine = min(mine, cand[(size_t)l * p.list_len + p.list_len - 1]);
-      for (int o = 16; o > 0; o >>= 1) mine = min(mine, __shfl_xor_sync(0xffffffffu, mine, o));
-      if (lane == 0) atomicMin(&s_bound_hi, (uint32_t)(mine >> 32));
-      __syncthreads();
-      if (lane == 0 && (uint32_t)(mine >> 32) == s_bound_hi) atomicMin(&s_bound_lo, (uint32_t)mine);
-      __syncthreads();
-      bound = ((uint64_t)s_bound_hi << 32) | s_bound_lo;
-      if (bound == kKeySentinel) bound = kKeySentinel - 1;
-    }
-    for (uint32_t i0 = 0; i0 < cnt; i0 += kSelThreads * 4) {
-      uint64_t kk[4];
+    const uint32_t L = p.list_len > 0 ? cnt / (uint32_t)p.list_len : 0;  // number of ascending lists
+    const uint32_t m_heads = L ? min((uint32_t)p.list_len, ((uint32_t)KP + L - 1) / L + 1) : 0;
+    if (L && L * m_heads <= (uint32_t)kSelCap) {
+      // Scan-path input: L ascending lists.  (a) The KP-th smallest of the lists' first m_heads keys
+      // bounds the KP-th smallest overall from above; (b) the keys <= that bound are a prefix of each
+      // list, so one thread per list walks its prefix (batches of 4 independent loads).
+      for (uint32_t l = tid; l < L; l += kSelThreads) {
+        for (uint32_t j0 = 0; j0 < m_heads; j0 += 4) {
+          uint64_t kk[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {  // loads first: four round trips overlap
-        const uint32_t i = i0 + u * kSelThreads + tid;
-        kk[u] = i < cnt ? cand[i] : kKeySentinel;
+          for (int u = 0; u < 4; ++u) kk[u] = (j0 + u < m_heads) ? cand[(size_t)l * p.list_len + j0 + u] : kKeySentinel;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            if (j0 + u < m_heads) keys[l * m_heads + j0 + u] = kk[u];
+        }
       }
+      __syncthreads();
+      const uint32_t nh = L * m_heads;
+      uint32_t nh_valid = 0;
+      for (uint32_t i = tid; i < nh; i += kSelThreads) nh_valid += keys[i] != kKeySentinel;
+      for (int o = 16; o > 0; o >>= 1) nh_valid += __shfl_xor_sync(0xffffffffu, nh_valid, o);
+      if (lane == 0 && nh_valid) atomicAdd(&s_count, nh_valid);
+      __syncthreads();
+      const uint32_t heads_valid = s_count;
+      __syncthreads();
+      if (tid == 0) s_count = 0;
+      if (heads_valid >= (uint32_t)KP)
+        bound = radix_select(keys, nh, (uint32_t)KP, kKeySentinel - 1, hist, &s_bucket, &s_need, tid);
+      __syncthreads();
+      for (uint32_t l = tid; l < L; l += kSelThreads) {
+        const uint64_t* lst = cand + (size_t)l * p.list_len;
+        for (uint32_t j0 = 0; j0 < (uint32_t)p.list_len; j0 += 4) {
+          uint64_t kk[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const bool valid = kk[u] <= bound;  // the sentinel is above every bound
-        const unsigned m = __ballot_sync(0xffffffffu, valid);
-        if (m) {
-          uint32_t base = 0;
-          if (lane == 0) base = atomicAdd(&s_nvalid, (uint32_t)__popc(m));
-          base = __shfl_sync(0xffffffffu, base, 0);
-          const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-          if (valid && pos < (uint32_t)kSelCap) keys[pos] = kk[u];
+          for (int u = 0; u < 4; ++u) kk[u] = (j0 + u < (uint32_t)p.list_len) ? lst[j0 + u] : kKeySentinel;
+          bool more = true;
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (more && kk[u] <= bound) {
+              const uint32_t pos = atomicAdd(&s_nvalid, 1u);
+              if (pos < (uint32_t)kSelCap) sel_stage(keys, pos, kk[u]);
+            } else {
+              more = false;
+            }
+          }
+          if (!more) break;
+        }
+      }
+    } else {
+      for (uint32_t i0 = 0; i0 < cnt; i0 += kSelThreads * 4) {
+        uint64_t kk[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {  // loads first: four round trips overlap
+          const uint32_t i = i0 + u * kSelThreads + tid;
+          kk[u] = i < cnt ? cand[i] : kKeySentinel;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const bool valid = kk[u] != kKeySentinel;
+          const unsigned m = __ballot_sync(0xffffffffu, valid);
+          if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_nvalid, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
+            if (valid && pos < (uint32_t)kSelCap) keys[pos] = kk[u];
+          }
         }
       }
     }
@@ -184,126 +217,218 @@ __global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const Select
     const uint32_t nvalid = s_nvalid;
     const uint32_t kpeff = min((uint32_t)KP, nvalid);
     const bool in_smem = nvalid <= (uint32_t)kSelCap;
-    const uint64_t* src = in_smem ? keys : cand;
+    const bool sorted_path = L && L * m_heads <= (uint32_t)kSelCap;
+    const uint64_t* src = in_smem ? (sorted_path ? keys2 : keys) : cand;
     const uint32_t src_n = in_smem ? nvalid : cnt;
 
     // ---- exact radix select of the KP-th smallest key (only when there are more than KP) ----
     uint64_t pivot = kKeySentinel - 1;  // everything valid is <= pivot
     if (nvalid > (uint32_t)KP) pivot = radix_select(src, src_n, (uint32_t)KP, bound, hist, &s_bucket, &s_need, tid);
-    for (int i = tid; i < kMaxKP; i += kSelThreads) sel[i] = kKeySentinel;
+    for (int i = tid; i < KP; i += kSelThreads) sel[i] = kKeySentinel;
     __syncthreads();
     for (uint32_t i = tid; i < src_n; i += kSelThreads) {
       const uint64_t key = src[i];
       if (key <= bound && key <= pivot) {
         const uint32_t pos = atomicAdd(&s_count, 1u);
-        if (pos < (uint32_t)kMaxKP) sel[pos] = key;
-      }
-    }
-    __syncthreads();  // keys[] is dead from here on
-
-    // ---- reference-exact rerank: candidate rows staged through shared-memory tiles with coalesced
-    //      loads, one thread per candidate walks its row in order (sequential f32 chain) ----
-    const float qn = p.qnorm[qg];
-    const float* qv = p.q32 + (size_t)qg * iv.dpad;
-    if (METRIC == kMetricCos && nvalid > 0 && qn == 0.f && tid == 0) atomicOr(p.flags, kFlagZeroNorm);
-    const int GC = kpeff <= 64 ? 64 : (kpeff <= 128 ? 128 : 256);
-    const int CW = kTileFloats / GC;        // floats per row chunk
-    const int cw4 = CW >> 2;
-    const int tstride = CW + 1;             // odd stride: conflict-free column walks
-    const int nchunk = (iv.d + CW - 1) / CW;
-    for (uint32_t b0 = 0; b0 < kpeff; b0 += GC) {
-      const int nb = (int)min((uint32_t)GC, kpeff - b0);
-      __syncthreads();
-      if (tid < GC) bslot[tid] = tid < nb ? (uint32_t)(sel[b0 + tid] & 0xffffffffu) : 0xffffffffu;
-      __syncthreads();
-      float acc = -0.0f;
-      float4 stage[4];
-      auto load_chunk = [&](int c) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = tid + kSelThreads * i;
-          const int row = idx / cw4, c4 = idx - row * cw4;
-          const int col = c * CW + 4 * c4;
-          const uint32_t slot = bslot[row];
-          stage[i] = (slot != 0xffffffffu && col < iv.dpad)
-                         ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)slot * iv.dpad + col))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      };
-      auto store_chunk = [&](float* tile) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int idx = tid + kSelThreads * i;
-          const int row = idx / cw4, c4 = idx - row * cw4;
-          float* dst = tile + row * tstride + 4 * c4;
-          dst[0] = stage[i].x; dst[1] = stage[i].y; dst[2] = stage[i].z; dst[3] = stage[i].w;
-        }
-      };
-      load_chunk(0);
-      store_chunk(tiles);
-      __syncthreads();
-      for (int c = 0; c < nchunk; ++c) {
-        float* cur = tiles + (c & 1) * (kTileFloats + 256);
-        float* nxt = tiles + ((c + 1) & 1) * (kTileFloats + 256);
-        if (c + 1 < nchunk) load_chunk(c + 1);  // global loads in flight during the chain below
-        if (tid < nb) {
-          const float* row = cur + tid * tstride;
-          const int c0 = c * CW;
-          const int lim = min(CW, iv.d - c0);
-#pragma unroll 8
-          for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, __ldg(qv + c0 + i), row[i]);
-        }
-        if (c + 1 < nchunk) store_chunk(nxt);
-        __syncthreads();
-      }
-      if (tid < nb) {
-        const uint32_t slot = bslot[tid];
-        float dist;
-        if (METRIC == kMetricL2) {
-          dist = __fsqrt_rn(acc);
-        } else if (METRIC == kMetricDot) {
-          dist = -acc;
-        } else {
-          const float xn = iv.norm[slot];
-          if (xn == 0.f || qn == 0.f) {
-            atomicOr(p.flags, kFlagZeroNorm);
-            dist = 0.f;
-          } else {
-            float sim = __fdiv_rn(acc, __fmul_rn(qn, xn));
-            if (sim < -1.0f) sim = -1.0f;
-            else if (sim > 1.0f) sim = 1.0f;
-            dist = __fsub_rn(1.0f, sim);
-          }
-        }
-        if (dist != dist) {
-          atomicOr(p.flags, kFlagNaN);
-          dist = 0.f;
-        }
-        sel[b0 + tid] = pack_key(dist, slot);
+        if (pos < (uint32_t)KP) sel[pos] = key;
       }
     }
     __syncthreads();
+    for (int i = tid; i < KP; i += kSelThreads) p.sel_keys[(size_t)qg * p.KP + i] = sel[i];
+    if (tid == 0) {
+      SelInfo info;
+      info.pivot = pivot;
+      info.nvalid = nvalid;
+      info.kpeff = kpeff;
+      info.overflow = overflow ? 1u : 0u;
+      info.done = 0;
+      p.sel_info[qg] = info;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- K3b: reference-exact rerank (one warp per 32 candidates) + finalize by the last warp ----------
+constexpr int kRrWarps = 4;                       // warps per block
+constexpr int kRrCW = 32;                         // floats per row chunk staged per step
+constexpr int kRrTile = 32 * (kRrCW + 1);         // one warp tile: 32 rows, odd stride
+static_assert(2 * kRrTile * 4 >= kMaxKP * 8, "the finalizing warp sorts in its tile buffers");
+
+__device__ __forceinline__ void warp_bitonic_sort(uint64_t* arr, int N, int lane) {
+  for (int k = 2; k <= N; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < N / 2; t += 32) {
+        const int i = ((t / j) * 2 * j) + (t % j);
+        const int l = i + j;
+        const bool up = ((i & k) == 0);
+        const uint64_t a = arr[i], b = arr[l];
+        if ((a > b) == up) {
+          arr[i] = b;
+          arr[l] = a;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <int METRIC>
+__global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const SelectParams p) {
+  __shared__ __align__(16) float s_tiles[kRrWarps][2 * kRrTile];
+  __shared__ float s_q[kRrWarps][2][32];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const IndexView& iv = p.iv;
+  const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
+  const int groups = p.warp_per_candidate ? p.KP : p.KP / 32;  // warps per query
+  const int64_t gw = (int64_t)blockIdx.x * kRrWarps + wib;
+  const int64_t total = (int64_t)nq * groups;
+  float* tile = s_tiles[wib];
+
+  for (int64_t wq = gw; wq < total; wq += (int64_t)gridDim.x * kRrWarps) {
+    const int qq = (int)(wq / groups), gi = (int)(wq - (int64_t)qq * groups);
+    const uint32_t qg = p.qlist ? p.qlist[qq] : (uint32_t)qq;
+    SelInfo* info = p.sel_info + qg;
+    const uint32_t kpeff = info->kpeff;
+    uint64_t* skeys = p.sel_keys + (size_t)qg * p.KP;
+    const float qn = p.qnorm[qg];
+    const float* qv = p.q32 + (size_t)qg * iv.dpad;
+    auto finish_distance = [&](float acc, uint32_t slot) -> float {
+      float dist;
+      if (METRIC == kMetricL2) {
+        dist = __fsqrt_rn(acc);
+      } else if (METRIC == kMetricDot) {
+        dist = -acc;
+      } else {
+        const float xn = iv.norm[slot];
+        if (xn == 0.f || qn == 0.f) {
+          atomicOr(p.flags, kFlagZeroNorm);
+          dist = 0.f;
+        } else {
+          float sim = __fdiv_rn(acc, __fmul_rn(qn, xn));
+          if (sim < -1.0f) sim = -1.0f;
+          else if (sim > 1.0f) sim = 1.0f;
+          dist = __fsub_rn(1.0f, sim);
+        }
+      }
+      if (dist != dist) {
+        atomicOr(p.flags, kFlagNaN);
+        dist = 0.f;
+      }
+      return dist;
+    };
+
+    if (p.warp_per_candidate) {
+      // latency mode (few candidates in total): the warp pulls one whole row and the query into shared
+      // memory with coalesced loads, then lane 0 walks them in order
+      if ((uint32_t)gi < kpeff) {
+        const uint32_t slot = (uint32_t)(skeys[gi] & 0xffffffffu);
+        float* xr = tile;
+        float* qr = tile + iv.dpad;
+        const float4* x4 = reinterpret_cast<const float4*>(iv.x32 + (size_t)slot * iv.dpad);
+        const float4* q4 = reinterpret_cast<const float4*>(qv);
+        for (int t = lane; t < (iv.dpad >> 2); t += 32) {
+          reinterpret_cast<float4*>(xr)[t] = __ldg(x4 + t);
+          reinterpret_cast<float4*>(qr)[t] = __ldg(q4 + t);
+        }
+        __syncwarp();
+        if (lane == 0) {
+          float acc = -0.0f;
+#pragma unroll 8
+          for (int i = 0; i < iv.d; ++i) acc = exact_step<METRIC>(acc, qr[i], xr[i]);
+          skeys[gi] = pack_key(finish_distance(acc, slot), slot);
+        }
+        __syncwarp();
+      }
+    } else {
+    const int ci = gi * 32 + lane;
+    const bool have = (uint32_t)ci < kpeff;
+    const uint32_t slot = have ? (uint32_t)(skeys[ci] & 0xffffffffu) : 0xffffffffu;
+
+    if ((uint32_t)(gi * 32) < kpeff) {
+      // rows staged through the warp's private tiles with coalesced loads (8 lanes per 128-byte row
+      // chunk); every lane then walks its own candidate's chunk in order: a sequential f32 chain
+      const int nchunk = (iv.d + kRrCW - 1) / kRrCW;
+      float4 stage[8];
+      float qstage;
+      float* qt = tile + 2 * kRrTile - 64;  // two 32-float query chunks live in the pad columns' tail
+      auto load_chunk = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
+          const uint32_t rs = __shfl_sync(0xffffffffu, slot, row);
+          const int col = c * kRrCW + 4 * c4;
+          stage[i] = (rs != 0xffffffffu && col < iv.dpad)
+                         ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)rs * iv.dpad + col))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        qstage = (c * kRrCW + lane < iv.dpad) ? __ldg(qv + c * kRrCW + lane) : 0.f;
+      };
+      auto store_chunk = [&](float* t, int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
+          float* dst = t + row * (kRrCW + 1) + 4 * c4;
+          dst[0] = stage[i].x; dst[1] = stage[i].y; dst[2] = stage[i].z; dst[3] = stage[i].w;
+        }
+        s_q[wib][buf][lane] = qstage;
+      };
+      (void)qt;
+      float acc = -0.0f;
+      load_chunk(0);
+      store_chunk(tile, 0);
+      __syncwarp();
+      for (int c = 0; c < nchunk; ++c) {
+        float* cur = tile + (c & 1) * kRrTile;
+        float* nxt = tile + ((c + 1) & 1) * kRrTile;
+        if (c + 1 < nchunk) load_chunk(c + 1);  // global loads in flight during the chain below
+        const float* row = cur + lane * (kRrCW + 1);
+        const float* qc = s_q[wib][c & 1];
+        const int c0 = c * kRrCW;
+        const int lim = min(kRrCW, iv.d - c0);
+        if (lim == kRrCW) {
+#pragma unroll
+          for (int i = 0; i < kRrCW; ++i) acc = exact_step<METRIC>(acc, qc[i], row[i]);
+        } else {
+          for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, qc[i], row[i]);
+        }
+        if (c + 1 < nchunk) store_chunk(nxt, (c + 1) & 1);
+        __syncwarp();
+      }
+      if (have) skeys[ci] = pack_key(finish_distance(acc, slot), slot);
+    }
+    }
+    // ---- the last warp of a query to get here sorts, emits and certifies ----
+    __threadfence();
+    __syncwarp();
+    uint32_t prev = 0;
+    if (lane == 0) prev = atomicAdd(&info->done, 1u);
+    prev = __shfl_sync(0xffffffffu, prev, 0);
+    if (prev != (uint32_t)groups - 1) continue;
+    __threadfence();
+    if (METRIC == kMetricCos && info->nvalid > 0 && qn == 0.f && lane == 0) atomicOr(p.flags, kFlagZeroNorm);
+    uint64_t* sk = reinterpret_cast<uint64_t*>(tile);
     int N = 32;
     while (N < (int)kpeff) N <<= 1;
-    block_bitonic_sort(sel, N, tid);
-
-    // ---- emit ----
+    for (int i = lane; i < N; i += 32) sk[i] = (uint32_t)i < kpeff ? __ldcg(skeys + i) : kKeySentinel;
+    __syncwarp();
+    warp_bitonic_sort(sk, N, lane);
+    const uint32_t k = p.ks[qg];
     const uint32_t kq = min(k, kpeff);
-    for (uint32_t t = tid; t < kq; t += kSelThreads) {
-      const uint64_t key = sel[t];
-      const uint32_t slot = (uint32_t)(key & 0xffffffffu);
-      p.out_ids[(size_t)qg * p.kstride + t] = iv.ids[slot];
+    for (uint32_t t = lane; t < kq; t += 32) {
+      const uint64_t key = sk[t];
+      const uint32_t sl = (uint32_t)(key & 0xffffffffu);
+      p.out_ids[(size_t)qg * p.kstride + t] = iv.ids[sl];
       p.out_dist[(size_t)qg * p.kstride + t] = key_f32((uint32_t)(key >> 32));
     }
-    if (tid == 0) p.out_counts[qg] = kq;
+    if (lane == 0) p.out_counts[qg] = kq;
 
     // ---- certification (tensor path) ----
-    if (p.certify && tid == 0 && k > 0) {
-      bool ok = !overflow && kpeff >= k;
+    if (p.certify && lane == 0 && k > 0) {
+      bool ok = !info->overflow && kpeff >= k;
       if (ok) {
-        const float tau = key_f32((uint32_t)(sel[k - 1] >> 32));  // exact k-th distance
+        const float tau = key_f32((uint32_t)(sk[k - 1] >> 32));  // exact k-th distance
         // every row that was not reranked has approximate score >= a_s
-        const float a_s = (nvalid > (uint32_t)KP) ? key_f32((uint32_t)(pivot >> 32)) : p.thresh[qg];
+        const float a_s = (info->nvalid > (uint32_t)p.KP) ? key_f32((uint32_t)(info->pivot >> 32)) : p.thresh[qg];
         const float dd = (float)iv.d;
         const float gamma = (dd + 8.f) * 5.9604645e-08f;  // (d+8) * 2^-24: sequential-sum rounding
         const float qmax = *p.qmaxabs;
@@ -331,7 +456,7 @@ __global__ void __launch_bounds__(kSelThreads) select_rerank_kernel(const Select
         if (p.uncertified) atomicAdd(p.uncertified, 1u);
       }
     }
-    __syncthreads();
+    __syncwarp();
   }
 }
 
@@ -382,10 +507,20 @@ __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const 
 
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
+  if (p.KP < 32 || p.KP > kMaxKP || (p.KP & (p.KP - 1))) return cudaErrorInvalidValue;
+  select_kernel<<<grid, kSelThreads, 0, st>>>(p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  SelectParams pp = p;
+  const int nq_max = p.nq_dev ? p.nq_max : p.nq;
+  pp.few_candidates = (int64_t)nq_max * p.KP <= 4096 ? 1 : 0;
+  pp.warp_per_candidate = ((int64_t)nq_max * p.KP <= 2048 && 2 * p.iv.dpad <= 2 * kRrTile) ? 1 : 0;
+  const int64_t warps = (int64_t)nq_max * (pp.warp_per_candidate ? p.KP : p.KP / 32);
+  const int blocks = (int)std::min<int64_t>((warps + kRrWarps - 1) / kRrWarps, 148 * 16);
   switch (p.iv.metric) {
-    case kMetricL2: select_rerank_kernel<kMetricL2><<<grid, kSelThreads, 0, st>>>(p); break;
-    case kMetricCos: select_rerank_kernel<kMetricCos><<<grid, kSelThreads, 0, st>>>(p); break;
-    case kMetricDot: select_rerank_kernel<kMetricDot><<<grid, kSelThreads, 0, st>>>(p); break;
+    case kMetricL2: rerank_finalize_kernel<kMetricL2><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
+    case kMetricCos: rerank_finalize_kernel<kMetricCos><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
+    case kMetricDot: rerank_finalize_kernel<kMetricDot><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
     default: return cudaErrorInvalidValue;
   }
   return cudaGetLastError();
