@@ -98,7 +98,7 @@ struct Ctrl {
 struct SearchCtx {
   cudaStream_t stream = nullptr;
   DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
-      fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info;
+      fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
   PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl;
   bool pending_status = false;  // device search issued, status not yet collected
   // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
@@ -107,7 +107,7 @@ struct SearchCtx {
   size_t ev_used = 0;
   void release() {
     for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &cand_fb, &cand_fb_cnt,
-                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info})
+                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
       b->release();
     for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl}) b->release();
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
@@ -501,6 +501,15 @@ void prof_collect(gfi_index* h, SearchCtx* c) {
   c->ev_used = 0;
 }
 
+bool is_pinned_host(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
 struct SearchArgs {
   const float* d_queries;  // device, [q][dim] unpadded
   int64_t q;
@@ -568,6 +577,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     segf = h->dpad;
     nseg = 1;
     R = 64 * std::max(1, std::min(4, kTargetStageBytes / (64 * h->dpad * 4)));
+  } else if (h->dpad <= 512) {
+    lpr = 16;  // two rows per warp at a time: halves the per-row reduction/bookkeeping cost of mid-size rows
+    segf = h->dpad;
+    nseg = 1;
+    R = 32 * std::max(1, std::min(4, kTargetStageBytes / (32 * h->dpad * 4)));
   } else {
     lpr = 32;
     segf = std::min(h->dpad, 1024);
@@ -575,6 +589,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     R = nseg == 1 ? 16 * std::max(1, std::min(4, kTargetStageBytes / (16 * h->dpad * 4))) : 16;
   }
   const int stage_floats = R * (nseg == 1 ? h->dpad : segf);
+  // filtered or heavily tombstoned scans gather only the eligible rows (one bulk copy per row)
+  const bool gather = a.d_mask != nullptr || h->n_live * 10 < h->n_slots * 9;
   // queries per pass: as many as shared memory allows next to a ring of at least 3 stages
   int QT = 4, nstages = 0;
   for (;; QT >>= 1) {
@@ -592,6 +608,12 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     if (h->opt_scan_stages > 0) nstages = std::max(2, std::min(nstages, h->opt_scan_stages));
   }
   const int64_t nblocks = (h->n_slots + R - 1) / R;
+  if (gather) {
+    CU_TRY(c->gather.ensure(((size_t)h->n_slots + 8) * 4));
+    CU_TRY(cudaMemsetAsync(c->gather.p, 0, 16, st));
+    CU_TRY(launch_compact_eligible(iv, mv, c->gather.as<uint32_t>() + 4, c->gather.as<uint32_t>(), st));
+    ++h->n_launch;
+  }
   const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
   const int64_t scan_stride = (int64_t)scan_grid * K;
 
@@ -606,6 +628,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     sp.cand_cnt = cnt.as<uint32_t>();
     sp.cand_stride = scan_stride;
     sp.flags = &ctrl->flags;
+    sp.gather_list = gather ? c->gather.as<uint32_t>() + 4 : nullptr;
+    sp.gather_count = gather ? c->gather.as<uint32_t>() : nullptr;
     sp.rows_per_stage = R;
     sp.seg_floats = segf;
     sp.nseg = nseg;
@@ -1080,9 +1104,14 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   CU_TRY(c->h_counts.ensure((size_t)q * 4));
   CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl)));
   if (mask) CU_TRY(c->mask.ensure(mask_words * 8));
-  memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
+  // queries already in pinned memory are copied straight from the caller's buffer
+  const void* q_src = queries;
+  if (!is_pinned_host(queries)) {
+    memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
+    q_src = c->h_q.p;
+  }
   memcpy(c->h_ks.p, ks, (size_t)q * 4);
-  CU_TRY(cudaMemcpyAsync(c->q_in.p, c->h_q.p, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, q_src, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
   if (mask) CU_TRY(cudaMemcpyAsync(c->mask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, st));
   SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax, mask ? c->mask.as<uint64_t>() : nullptr,

@@ -53,11 +53,16 @@ struct ScanParams {
   uint32_t* cand_cnt;       // [q]
   int64_t cand_stride;
   uint32_t* flags;
+  const uint32_t* gather_list;   // compacted eligible slots (filtered / tombstoned scans), or null
+  const uint32_t* gather_count;  // device-side length of gather_list
   int rows_per_stage, seg_floats, nseg;
   int lanes_per_row;        // 8: 4 rows per warp at a time (dpad <= 256); 32: one row per warp (longer rows)
   int nstages;              // ring depth (<= kScanMaxStages)
   int stage_floats;         // floats per ring stage (rows_per_stage * row stride in the stage)
 };
+// eligible (live and unmasked) slots -> list[0..*count)
+cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, uint32_t* list, uint32_t* count,
+                                    cudaStream_t st);
 // QT = queries sharing one pass over the database (1,2,4).
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st);
 size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats);

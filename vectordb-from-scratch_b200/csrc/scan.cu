@@ -17,6 +17,8 @@
 //   * a row touches the per-warp sorted list only when it beats the list's current K-th key.
 // The scores computed here only rank candidates; the K survivors per CTA are re-scored with the
 // reference's exact arithmetic in select_rerank.cu.
+#include <algorithm>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -74,6 +76,7 @@ __device__ __forceinline__ void consumers_bitonic_sort(uint64_t* arr, int N, int
 // Row metadata fetched one block ahead as RAW words (nothing depends on the loads until the next
 // iteration, so their latency is hidden behind the current block's work).
 struct RowMeta {
+  uint32_t slot[kMaxRounds];
   uint32_t live[kMaxRounds];
   uint64_t mask[kMaxRounds];
   float norm[kMaxRounds];
@@ -109,7 +112,10 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
   }
   __syncthreads();
 
-  const uint32_t n = (uint32_t)iv.n_slots;
+  // gather mode (filtered / tombstoned scans): rows are taken from a compacted list of eligible slots,
+  // one bulk copy per row, so ineligible rows cost no bandwidth at all
+  const uint32_t* glist = p.gather_list;
+  const uint32_t n = glist ? *p.gather_count : (uint32_t)iv.n_slots;
   const int R = p.rows_per_stage, nseg = SEG ? p.nseg : 1, segw = p.seg_floats;
   const uint32_t nblocks = (n + R - 1) / R;
   const int rstride = SEG ? segw : dpad;
@@ -139,7 +145,12 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
         for (int seg = 0; seg < nseg; ++seg) {
           mbar_wait(&empty[stage], phase ^ 1u);
           float* dst = stages + (size_t)stage * stage_floats;
-          if (!SEG) {
+          if (!SEG && glist) {
+            if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)rows * dpad * 4u);
+            __syncwarp();
+            for (int r = lane; r < rows; r += 32)
+              bulk_g2s(dst + (size_t)r * dpad, iv.x32 + (size_t)glist[row0 + r] * dpad, dpad * 4u, &full[stage]);
+          } else if (!SEG) {
             if (lane == 0) {
               const uint32_t bytes = (uint32_t)rows * dpad * 4u;
               mbar_arrive_expect_tx(&full[stage], bytes);
@@ -151,8 +162,9 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)rows * segf * 4u);
             __syncwarp();
             if (lane < rows)
-              bulk_g2s(dst + lane * segw, iv.x32 + (size_t)(row0 + lane) * dpad + (size_t)seg * segw, segf * 4u,
-                       &full[stage]);
+              bulk_g2s(dst + lane * segw,
+                       iv.x32 + (size_t)(glist ? glist[row0 + lane] : row0 + lane) * dpad + (size_t)seg * segw,
+                       segf * 4u, &full[stage]);
           }
           __syncwarp();
           if (++stage == NS) { stage = 0; phase ^= 1u; }
@@ -182,11 +194,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
           m.live[r] = 0;
           m.mask[r] = ~0ull;
           m.norm[r] = 1.f;
-          const uint32_t slot = row0 + r * (NW * G) + rsub;
-          if (r < rounds && slot < n) {
-            m.live[r] = __ldg(iv.live + (slot >> 5));
-            if (mask_by_slot) m.mask[r] = ((int64_t)slot < p.mask.nbits) ? __ldg(p.mask.bits + (slot >> 6)) : 0ull;
-            if (METRIC == kMetricCos) m.norm[r] = __ldg(iv.norm + slot);
+          const uint32_t pos = row0 + r * (NW * G) + rsub;
+          m.slot[r] = pos;
+          if (r < rounds && pos < n) {
+            if (glist) {
+              // every listed row is eligible; its slot comes from the list (one more dependent load for
+              // the cosine norm, still a whole block ahead of its use)
+              const uint32_t s = __ldg(glist + pos);
+              m.slot[r] = s;
+              m.live[r] = ~0u;
+              if (METRIC == kMetricCos) m.norm[r] = __ldg(iv.norm + s);
+            } else {
+              m.live[r] = __ldg(iv.live + (pos >> 5));
+              if (mask_by_slot) m.mask[r] = ((int64_t)pos < p.mask.nbits) ? __ldg(p.mask.bits + (pos >> 6)) : 0ull;
+              if (METRIC == kMetricCos) m.norm[r] = __ldg(iv.norm + pos);
+            }
           }
         }
       };
@@ -220,7 +242,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
           for (int r = 0; r < kMaxRounds; ++r) {
             if (r * (NW * G) + warp * G >= rows) break;  // warp-uniform
             const int rl = r * (NW * G) + rsub;
-            const uint32_t slot = row0 + rl;
+            const uint32_t slot = meta.slot[r];
             const float4* xr = reinterpret_cast<const float4*>(sb + (size_t)rl * rstride);
             if (FAST) {
               float a0 = 0.f, a1 = 0.f;
@@ -270,7 +292,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
             if (!SEG || seg == nseg - 1) {
               // eligibility: tombstone bit, then the filter bit (by slot when ids are the identity)
               bool elig = ((meta.live[r] >> (slot & 31)) & 1u) && ((meta.mask[r] >> (slot & 63)) & 1ull);
-              if (elig && has_mask && !mask_by_slot) {
+              if (elig && has_mask && !mask_by_slot && !glist) {
                 const uint64_t id = iv.ids[slot];
                 elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
               }
@@ -349,12 +371,46 @@ cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t sme
 template <int METRIC>
 cudaError_t launch_scan_shape(const ScanParams& p, int QT, int grid, size_t smem, cudaStream_t st) {
   if (p.lanes_per_row == 8 && p.nseg == 1) return launch_scan_metric<METRIC, 8, false>(p, QT, grid, smem, st);
+  if (p.lanes_per_row == 16 && p.nseg == 1) return launch_scan_metric<METRIC, 16, false>(p, QT, grid, smem, st);
   if (p.lanes_per_row == 32 && p.nseg == 1) return launch_scan_metric<METRIC, 32, false>(p, QT, grid, smem, st);
   if (p.lanes_per_row == 32) return launch_scan_metric<METRIC, 32, true>(p, QT, grid, smem, st);
   return cudaErrorInvalidValue;
 }
 
+// Compacts the eligible (live and unmasked) slots into a list (unordered: keys carry the slot, so the
+// processing order is irrelevant to the result).  One warp-aggregated atomic per 32 slots.
+__global__ void compact_eligible_kernel(const IndexView iv, const MaskView mask, uint32_t* list, uint32_t* count) {
+  const int lane = threadIdx.x & 31;
+  for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; s0 < iv.n_slots;
+       s0 += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = s0 + lane;
+    bool e = false;
+    if (s < iv.n_slots) {
+      e = (iv.live[s >> 5] >> (s & 31)) & 1u;
+      if (e && mask.bits) {
+        const uint64_t id = iv.ids_identity ? (uint64_t)s : iv.ids[s];
+        e = (id < (uint64_t)mask.nbits) && ((mask.bits[id >> 6] >> (id & 63)) & 1ull);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, e);
+    if (m) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (e) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s;
+    }
+  }
+}
+
 }  // namespace
+
+cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, uint32_t* list, uint32_t* count,
+                                    cudaStream_t st) {
+  if (iv.n_slots == 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((iv.n_slots + 255) / 256, 148 * 8);
+  compact_eligible_kernel<<<blocks, 256, 0, st>>>(iv, mask, list, count);
+  return cudaGetLastError();
+}
 
 size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats) {
   return (size_t)nstages * stage_floats * 4 + (size_t)QT * dpad * 4 + (size_t)QT * NW * K * 8 +

@@ -150,7 +150,8 @@ class GpuFlatIndex:
         cnt = np.zeros(q, dtype=np.uint32)
         mptr, mbits = None, 0
         if mask is not None:
-            words, mbits = pack_mask(mask)
+            # a bool array indexed by internal id, or a pre-packed (u64 words, nbits) pair
+            words, mbits = mask if isinstance(mask, tuple) else pack_mask(mask)
             mptr = words.ctypes.data
         self._chk(self._L.gfi_search(self._h, qs.ctypes.data if qs.size else None, q, d, ks.ctypes.data, mptr,
                                      mbits, out_ids.ctypes.data, out_dist.ctypes.data, cnt.ctypes.data, kmax))
