@@ -46,6 +46,19 @@ NAMES = {
 METRIC_ID = {"euclidean": 0, "cosine": 1, "dot": 2}
 
 
+def ncu_traffic(wl):
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, or None."""
+    import glob
+    for p in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+        try:
+            t = json.load(open(p)).get(wl)
+            if t:
+                return t["bytes_per_launch"]
+        except Exception:
+            pass
+    return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -283,17 +296,23 @@ def main():
         achieved = flops / (kern_ms * 1e-3) / 1e12
         long_step = ms > 2000.0
         peak = pk["bf16_tflops_sustained"] if long_step else pk["bf16_tflops"]
+        hbm_gbs = n * d * 2 / (kern_ms * 1e-3) / 1e9  # the fp16 shadow rows are read once per launch
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "gemm_topk_kernel (main pass)", "kernel_ms": kern_ms,
+                "traffic": ncu_traffic(wl), "kernel": "gemm_topk_kernel (main pass)", "kernel_ms": kern_ms,
                 "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16 " + ("sustained" if long_step else "burst"),
-                "hbm_gbs_scanned": n * d * 2 / (kern_ms * 1e-3) / 1e9}
+                "hbm_gbs_scanned": hbm_gbs}
+        if (n * d * 2 / 1e9) / pk["hbm_gbs"] > (flops / 1e12) / peak:
+            # low arithmetic intensity (few queries per row byte): the launch is bounded by HBM, not the tensor pipe
+            roof.update({"bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": hbm_gbs / pk["hbm_gbs"], "tensor_tflops": achieved,
+                         "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs"})
     else:
         kern_ms = (st1["scan_kernel_ns"] - st0["scan_kernel_ns"]) / max(sk_n, 1) / 1e6
         # algorithmic bytes per launch: every ELIGIBLE fp32 row once (+ the mask bits when filtering)
         nbytes = float(n_elig) * d * 4 + (n / 8 if wl in FILTER_PCT else 0)
         achieved = nbytes / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": None, "kernel": "scan_topk_kernel",
+                "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(wl), "kernel": "scan_topk_kernel",
                 "kernel_ms": kern_ms, "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs",
                 "full_scan_equiv_gbs": float(n) * d * 4 / (kern_ms * 1e-3) / 1e9, "eligible_rows": n_elig}
 
