@@ -77,6 +77,11 @@ int32_t gfi_add(gfi_index *h, const uint64_t *ids, const float *rows, int64_t n,
 int32_t gfi_add_generated(gfi_index *h, uint32_t seed, uint64_t first_row, int64_t n, int32_t kind,
                           uint64_t first_id);
 
+/* Bulk ingest of the reference's flat vector file (MmapVectorStorage, src/persistence/mmap.rs:13-15,
+ * 161-172: little-endian [dimension u32][count u32] then count x dimension f32).  Row i gets internal id
+ * first_id + i.  Reads in 32 MB chunks straight into the staged-add path (no per-row call). */
+int32_t gfi_add_from_file(gfi_index *h, const char *path, uint64_t first_id, int64_t *out_rows);
+
 /* Index::remove, src/index.rs:16 / src/flat_index.rs:43-46: idempotent (tombstone). */
 int32_t gfi_remove(gfi_index *h, uint64_t id);
 

@@ -381,3 +381,69 @@ def test_full_size_c2_cosine_batch_against_oracle_subset():
     exp = oracle.search_batch("cosine", rows, queries[:4], k, threads=4)
     for i, (eids, ed) in enumerate(exp):
         assert_topk_matches(ids[i], dist[i], eids, ed, ctx=f"C2 full q{i}")
+
+
+# ---------------------------------------------------------------- concurrency (B2: &self searches under RwLock::read)
+def test_concurrent_searches_from_many_threads():
+    """routes.rs:244,342: any tokio worker may call Index::search concurrently.  ctypes releases the GIL
+    during the foreign call, so these really overlap inside libgfi (search-context pool, one stream each)."""
+    import threading
+    n, d, k = 30000, 96, 10
+    rows = oracle.gen_rows(81, 0, n, d, 1)
+    idx = build("euclidean", rows)
+    batches = [oracle.gen_rows(900 + t, 0, 1 if t % 2 else 24, d, 1) for t in range(8)]
+    expected = [idx.search_arrays(b, k) for b in batches]  # sequential answers
+    results, errors = [None] * len(batches), []
+
+    def worker(t):
+        try:
+            for _ in range(20):
+                results[t] = idx.search_arrays(batches[t], k)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(batches))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    for (ei, ed, ec), (gi, gd, gc) in zip(expected, results):
+        assert np.array_equal(ei, gi) and np.array_equal(ed, gd) and np.array_equal(ec, gc)
+    exp0 = oracle.search_batch("euclidean", rows, batches[0], k, threads=4)
+    for i, (eids, ed) in enumerate(exp0):
+        assert_topk_matches(results[0][0][i], results[0][1][i], eids, ed, ctx=f"concurrent q{i}")
+
+
+def test_large_batch_is_chunked():
+    """q above the tensor kernel's per-launch query limit (4096) is cut into chunks transparently."""
+    n, d, q, k = 20000, 64, 4500, 5
+    rows = oracle.gen_rows(91, 0, n, d, 0)
+    queries = oracle.gen_rows(92, 0, q, d, 0)
+    idx = build("dot", rows)
+    ids, dist, cnt = idx.search_arrays(queries, k)
+    assert np.all(cnt == k)
+    pick = [0, 1, 4095, 4096, 4499]
+    exp = oracle.search_batch("dot", rows, queries[pick], k, threads=4)
+    for j, (eids, ed) in zip(pick, exp):
+        assert_topk_matches(ids[j], dist[j], eids, ed, ctx=f"chunked q{j}")
+    assert idx.stats()["tensor_queries"] == q
+
+
+def test_bulk_ingest_from_reference_flat_file(tmp_path):
+    """src/persistence/mmap.rs:13-15,161-172: [dim u32 LE][count u32 LE][f32 rows]."""
+    import struct
+    n, d = 5000, 48
+    rows = oracle.gen_rows(95, 0, n, d, 1)
+    path = tmp_path / "vectors.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("<II", d, n))
+        f.write(rows.tobytes())
+    idx = gfi.GpuFlatIndex(DM.Cosine)
+    assert idx.add_from_file(path, first_id=100) == n and idx.len() == n and idx.dim() == d
+    assert np.array_equal(idx.get_vector(100 + 4999), rows[4999])
+    q = oracle.gen_rows(96, 0, 3, d, 1)
+    check_batch(idx, "cosine", rows, q, 10, ids=np.arange(100, 100 + n, dtype=np.uint64), ctx="flat file")
+    other = gfi.GpuFlatIndex(DM.Cosine, dim=d + 1)
+    with pytest.raises(gfi.DimensionMismatch):
+        other.add_from_file(path)

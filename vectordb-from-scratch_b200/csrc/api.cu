@@ -903,10 +903,7 @@ int32_t gfi_reserve(gfi_index* h, int64_t n_rows) {
   return grow(h, n_rows);
 }
 
-int32_t gfi_add(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n, int64_t dim) {
-  if (!h) return fail(GFI_ERR_INDEX, "null handle");
-  if (n < 0 || (n > 0 && (!ids || (!rows && dim > 0)))) return fail(GFI_ERR_INDEX, "bad arguments");
-  std::unique_lock<std::shared_mutex> g(h->mu);
+static int32_t add_rows_locked(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n, int64_t dim) {
   if (h->dim == 0 && n > 0) {
     if (dim <= 0) return fail(GFI_ERR_INDEX, "zero-dimensional vectors are not supported");
     latch_dim(h, dim);
@@ -971,6 +968,47 @@ int32_t gfi_add(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n,
     } else if (h->st_n == h->st_cap) {
       if ((rc = flush_locked(h)) != GFI_OK) return rc;
     }
+  }
+  return GFI_OK;
+}
+
+int32_t gfi_add(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n, int64_t dim) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (n < 0 || (n > 0 && (!ids || (!rows && dim > 0)))) return fail(GFI_ERR_INDEX, "bad arguments");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  return add_rows_locked(h, ids, rows, n, dim);
+}
+
+int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int64_t* out_rows) {
+  if (!h || !path) return fail(GFI_ERR_INDEX, "null argument");
+  if (out_rows) *out_rows = 0;
+  FILE* f = fopen(path, "rb");
+  if (!f) return fail(GFI_ERR_INDEX, std::string("cannot open ") + path);
+  struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
+  unsigned char hdr[8];
+  if (fread(hdr, 1, 8, f) != 8) return fail(GFI_ERR_INDEX, "File too small for header");
+  const uint32_t dim = (uint32_t)hdr[0] | ((uint32_t)hdr[1] << 8) | ((uint32_t)hdr[2] << 16) | ((uint32_t)hdr[3] << 24);
+  const uint32_t count = (uint32_t)hdr[4] | ((uint32_t)hdr[5] << 8) | ((uint32_t)hdr[6] << 16) | ((uint32_t)hdr[7] << 24);
+  if (dim == 0) return fail(GFI_ERR_INDEX, "flat file has dimension 0");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  if (h->dim != 0 && (int64_t)dim != h->dim) {
+    tl_expected = h->dim;
+    tl_actual = dim;
+    return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
+  }
+  const int64_t chunk = std::max<int64_t>(1, (32ll << 20) / ((int64_t)dim * 4));
+  std::vector<float> buf((size_t)chunk * dim);
+  std::vector<uint64_t> ids((size_t)chunk);
+  int64_t done = 0;
+  while (done < (int64_t)count) {
+    const int64_t take = std::min<int64_t>(chunk, (int64_t)count - done);
+    if (fread(buf.data(), 4, (size_t)take * dim, f) != (size_t)take * dim)
+      return fail(GFI_ERR_INDEX, "flat file is shorter than its header says");
+    for (int64_t i = 0; i < take; ++i) ids[(size_t)i] = first_id + (uint64_t)(done + i);
+    int32_t rc = add_rows_locked(h, ids.data(), buf.data(), take, dim);
+    if (rc != GFI_OK) return rc;
+    done += take;
+    if (out_rows) *out_rows = done;
   }
   return GFI_OK;
 }

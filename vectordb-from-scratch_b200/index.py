@@ -89,6 +89,12 @@ class GpuFlatIndex:
     def add_generated(self, seed, first_row, n, kind, first_id):
         self._chk(self._L.gfi_add_generated(self._h, seed, first_row, n, kind, first_id))
 
+    def add_from_file(self, path, first_id=0):
+        """Bulk-load the reference's flat vector file (src/persistence/mmap.rs); returns the row count."""
+        n = ctypes.c_int64()
+        self._chk(self._L.gfi_add_from_file(self._h, str(path).encode(), int(first_id), ctypes.byref(n)))
+        return n.value
+
     def remove(self, id):
         """Index::remove (src/index.rs:16): idempotent."""
         self._chk(self._L.gfi_remove(self._h, int(id)))

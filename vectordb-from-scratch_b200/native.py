@@ -62,6 +62,7 @@ def lib():
         "gfi_destroy": (i32, [vp]),
         "gfi_add": (i32, [vp, vp, vp, i64, i64]),
         "gfi_add_generated": (i32, [vp, u32, u64, i64, i32, u64]),
+        "gfi_add_from_file": (i32, [vp, c.c_char_p, u64, c.POINTER(i64)]),
         "gfi_remove": (i32, [vp, u64]),
         "gfi_len": (i64, [vp]),
         "gfi_metric": (i32, [vp]),
