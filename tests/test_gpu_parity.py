@@ -447,3 +447,70 @@ def test_bulk_ingest_from_reference_flat_file(tmp_path):
     other = gfi.GpuFlatIndex(DM.Cosine, dim=d + 1)
     with pytest.raises(gfi.DimensionMismatch):
         other.add_from_file(path)
+
+
+# ---------------------------------------------------------------- more full-size checks (BASELINE.json configs)
+def test_full_size_c5_shard_l2_batch4096_against_oracle_subset():
+    """C5 shard: 12.5M x 128 Euclidean, batch 4096, k = 10 (one GPU's share of the 100M index).  The
+    whole batch runs on the tcgen05 path; 4 queries are checked bit for bit against the oracle at
+    full size, 16 against the independent exact-scan path, all for sortedness / idempotence."""
+    n, d, q, k = 12_500_000, 128, 4096, 10
+    idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
+    idx.reserve(n)
+    idx.add_generated(7, 0, n, 0, 0)
+    queries = oracle.gen_rows(8, 0, q, d, 0)
+    ids, dist, cnt = idx.search_arrays(queries, k)
+    assert np.all(cnt == k) and np.all(np.diff(dist, axis=1) >= 0) and np.all(dist >= 0)
+    st = idx.stats()
+    assert st["tensor_queries"] == q and st["fallback_queries"] <= 16, st
+    idx.set_option("tensor_min_q", 1 << 30)
+    ids_s, dist_s, _ = idx.search_arrays(queries[:16], k)
+    assert np.array_equal(ids_s, ids[:16]) and np.array_equal(dist_s, dist[:16])
+    rows = oracle.gen_rows(7, 0, n, d, 0)
+    exp = oracle.search_batch("euclidean", rows, queries[:4], k, threads=4)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(ids[i], dist[i], eids, ed, ctx=f"C5 full q{i}")
+
+
+def test_full_size_c3_c4_properties():
+    """C3 (10M x 768 dot, k=100) and C4 (10M x 384 Euclidean + filter, k=10) at full size through
+    size-independent properties: a stored row queried against itself comes back first (L2), the
+    merge of the answers over a mask and its complement equals the unfiltered answer, sortedness,
+    and agreement of the scan and tensor paths."""
+    from vectordb_from_scratch_b200 import synth
+    # ---- C4
+    n, d, k = 10_000_000, 384, 10
+    idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
+    idx.reserve(n)
+    idx.add_generated(6, 0, n, 0, 0)
+    probe = [0, 1234567, n - 1]
+    qs = np.concatenate([synth.gen_rows(6, r, 1, d, 0) for r in probe] + [synth.gen_rows(66, 0, 3, d, 0)])
+    ids, dist, cnt = idx.search_arrays(qs, k)
+    assert np.all(cnt == k) and np.all(np.diff(dist, axis=1) >= 0)
+    for j, r in enumerate(probe):
+        assert ids[j, 0] == r and dist[j, 0] == 0.0
+    rng = np.random.default_rng(4)
+    m = rng.random(n) < 0.5
+    a_ids, a_d, a_c = idx.search_arrays(qs, k, mask=m)
+    b_ids, b_d, b_c = idx.search_arrays(qs, k, mask=~m)
+    assert np.all(m[a_ids.astype(np.int64)]) and not np.any(m[b_ids.astype(np.int64)])
+    merged = numpy_merge(np.stack([a_ids, b_ids]), np.stack([a_d, b_d]), np.stack([a_c, b_c]), [k] * len(qs))
+    for i in range(len(qs)):
+        assert [p[1] for p in merged[i]] == [int(x) for x in ids[i]]
+        assert np.array_equal(np.array([p[0] for p in merged[i]], np.float32), dist[i])
+    sparse = rng.random(n) < 0.01
+    s_ids, s_d, s_c = idx.search_arrays(qs, k, mask=sparse)
+    assert np.all(s_c == k) and np.all(sparse[s_ids.astype(np.int64)]) and np.all(np.diff(s_d, axis=1) >= 0)
+    assert np.all(s_d[:, 0] >= dist[:, 0])
+    idx.close()
+    # ---- C3
+    n, d, k = 10_000_000, 768, 100
+    idx = gfi.GpuFlatIndex(DM.DotProduct, dim=d)
+    idx.reserve(n)
+    idx.add_generated(5, 0, n, 1, 0)
+    qs = synth.gen_rows(55, 0, 64, d, 1)
+    t_ids, t_d, t_c = idx.search_arrays(qs, k)            # batch 64: tcgen05 path (C3b)
+    assert idx.stats()["tensor_queries"] == 64 and np.all(t_c == k) and np.all(np.diff(t_d, axis=1) >= 0)
+    s_ids, s_d, s_c = idx.search_arrays(qs[:2], k)        # single queries: scan path (C3a)
+    assert idx.stats()["scan_queries"] == 2
+    assert np.array_equal(s_ids, t_ids[:2]) and np.array_equal(s_d, t_d[:2])
