@@ -119,6 +119,22 @@ int32_t gfi_search(gfi_index *h, const float *queries, int64_t q, int64_t dim, c
                    uint32_t *out_counts, int64_t kstride);
 
 /*
+ * Device-side metadata filters (the "next" row N2 of SURVEY.md section 8f).  The reference keeps
+ * Metadata{HashMap<String,String>} per internal id in VectorStore (src/storage.rs:19-42,90) and walks it on
+ * the host per candidate (storage.rs:272-285).  gfi_set_metadata mirrors VectorStore::insert_with_metadata's
+ * `self.metadata.insert(internal_id, metadata)` (storage.rs:169): the fields of `id` are REPLACED by the
+ * given key/value pairs and kept as dictionary-encoded columns in HBM.  gfi_search_filtered takes the
+ * reference's own JSON form of MetadataFilter (serde tag "op": eq / ne / exists / and / or,
+ * storage.rs:44-58), evaluates it on the GPU into an eligibility bitmask and runs FlatIndex::search over the
+ * matching rows (exact pre-filter; truth table of storage.rs:62-70).
+ */
+int32_t gfi_set_metadata(gfi_index *h, uint64_t id, int32_t n_fields, const char *const *keys,
+                         const char *const *values);
+int32_t gfi_search_filtered(gfi_index *h, const float *queries, int64_t q, int64_t dim, const uint32_t *ks,
+                            const char *filter_json, uint64_t *out_ids, float *out_dist, uint32_t *out_counts,
+                            int64_t kstride);
+
+/*
  * Same search with every buffer already in device memory (HBM) and asynchronous on
  * `stream` (a cudaStream_t passed as void*; NULL = the index's own stream): no host
  * synchronisation.  d_ks/d_mask/d_* are device pointers.  Call gfi_search_status to

@@ -93,7 +93,7 @@ def test_reference_store_kats():
         assert len(res) == 1 and res[0].id == "v1"
 
 
-@pytest.mark.parametrize("pushdown", [False, True])
+@pytest.mark.parametrize("pushdown", [False, True, "device"])
 def test_reference_filter_and_batch_kats(pushdown):
     def mk(case):
         st = gfi.VectorStore(DM.Euclidean)
@@ -514,3 +514,46 @@ def test_full_size_c3_c4_properties():
     s_ids, s_d, s_c = idx.search_arrays(qs[:2], k)        # single queries: scan path (C3a)
     assert idx.stats()["scan_queries"] == 2
     assert np.array_equal(s_ids, t_ids[:2]) and np.array_equal(s_d, t_d[:2])
+
+
+# ---------------------------------------------------------------- device-side MetadataFilter evaluation (N2)
+def test_device_side_filter_matches_host_truth_table():
+    """Filters in the reference's JSON form evaluated on the GPU (csrc/filter.cu) against the host truth
+    table (storage.rs:62-70) and the oracle run on the matching subset."""
+    n, d, k = 6000, 40, 10
+    rows = oracle.gen_rows(97, 0, n, d, 1)
+    store = gfi.VectorStore(DM.Euclidean)
+    colors = ["red", "green", "blue", "c\"q"]
+    for i in range(n):
+        md = gfi.Metadata()
+        if i % 7 != 0:
+            md.insert("color", colors[(i * 2654435761 >> 3) % 4])
+        if i % 3 == 0:
+            md.insert("size", "s%d" % (i % 2))
+        store.insert_with_metadata("v%d" % i, rows[i], md)
+    F = gfi.MetadataFilter
+    filters = [
+        F.eq("color", "red"), F.ne("color", "red"), F.exists("size"), F.eq("color", "nope"), F.eq("nofield", "x"),
+        F.ne("nofield", "x"), F.and_([]), F.or_([]), F.eq("color", "c\"q"),
+        F.and_([F.eq("color", "blue"), F.eq("size", "s0")]),
+        F.or_([F.eq("color", "green"), F.and_([F.exists("size"), F.ne("color", "red")])]),
+        F.and_([F.or_([F.eq("size", "s1"), F.eq("size", "s0")]), F.ne("size", "s1"), F.exists("color")]),
+    ]
+    queries = oracle.gen_rows(98, 0, 3, d, 1)
+    for flt in filters:
+        host_mask = store.filter_mask(flt)
+        ids, dist, cnt = store.index.search_filtered(queries, k, flt.to_json())
+        exp = oracle.search_batch("euclidean", rows, queries, k, eligible=host_mask, threads=4)
+        for i, (eids, ed) in enumerate(exp):
+            assert cnt[i] == len(eids), (flt.to_json(), cnt[i], len(eids))
+            assert_topk_matches(ids[i, :cnt[i]], dist[i, :cnt[i]], eids, ed, ctx=str(flt.to_json()))
+    # overwrite replaces metadata wholesale; delete removes the row from filtered results
+    md = gfi.Metadata()
+    md.insert("size", "huge")
+    store.insert_with_metadata("v5", rows[5], md)
+    store.delete("v10")
+    res = store.search_with_filter(rows[5], 3, F.eq("size", "huge"), pushdown="device")
+    assert [r.id for r in res] == ["v5"] and res[0].distance == 0.0
+    assert store.search_with_filter(rows[5], 3, F.and_([F.eq("size", "huge"), F.exists("color")]), pushdown="device") == []
+    with pytest.raises(gfi.IndexError_):
+        store.index.search_filtered(queries, k, '{"op": "xor", "filters": []}')

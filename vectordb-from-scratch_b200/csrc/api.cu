@@ -172,6 +172,15 @@ struct gfi_index {
   bool any_id = false;
   std::unordered_map<uint64_t, int64_t> odd_dim_rows;  // id -> dim of rows whose dim != index dim
 
+  // metadata (device-side filter evaluation): dictionary-encoded u32 column per field, code 0 = absent
+  std::map<std::string, int> meta_fields;
+  std::vector<std::map<std::string, uint32_t>> meta_values;
+  std::vector<std::vector<uint32_t>> meta_cols;  // host mirror, one entry per slot
+  std::vector<DevBuf> meta_dcols;
+  DevBuf meta_dptrs;
+  bool meta_dirty = false;
+  std::unordered_map<uint64_t, std::vector<std::pair<int, uint32_t>>> meta_pending;
+
   // staging (pinned)
   PinBuf st_rows, st_ids;
   int64_t st_n = 0, st_cap = 0;
@@ -369,6 +378,8 @@ int32_t read_counters(gfi_index* h) {
 
 // implemented in ingest.cu (kept here to avoid widening kernels.h): folds per-row flags into counters
 namespace gfi {
+bool compile_filter(const char* json, const std::map<std::string, int>& fields,
+                    const std::vector<std::map<std::string, uint32_t>>& values, FilterProgram* out, std::string* err);
 cudaError_t launch_fold_rowflags(const uint32_t* rowflags, const float* norm, int64_t first, int64_t n,
                                  uint32_t* counters, cudaStream_t st);
 }
@@ -521,6 +532,7 @@ struct SearchArgs {
   float* d_out_dist;
   uint32_t* d_out_counts;
   int64_t kstride;
+  bool mask_by_slot = false;  // the mask is indexed by slot (device-evaluated filter), not by internal id
 };
 
 // Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
@@ -528,6 +540,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const int q = (int)a.q;
   const int grid_sm = h->opt_grid > 0 ? h->opt_grid : h->sm_count;
   IndexView iv = h->view();
+  if (a.mask_by_slot) iv.ids_identity = 1;  // only mask indexing looks at this flag
   MaskView mv{a.d_mask, a.mask_bits};
 
   const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
@@ -878,6 +891,8 @@ int32_t gfi_destroy(gfi_index* h) {
   h->pool.clear();
   for (DevBuf* b : {&h->x32, &h->x16, &h->ids, &h->norm, &h->sumsq, &h->coef, &h->live, &h->rowflags, &h->counters})
     b->release();
+  for (auto& b : h->meta_dcols) b.release();
+  h->meta_dptrs.release();
   h->st_rows.release();
   h->st_ids.release();
   if (h->ingest_stream) cudaStreamDestroy(h->ingest_stream);
@@ -1088,6 +1103,40 @@ int32_t gfi_get_vector(gfi_index* h, uint64_t id, float* out, int64_t cap, int64
   return GFI_OK;
 }
 
+// applies pending metadata to the per-field columns and uploads dirty columns.  Unique lock held.
+static int32_t sync_metadata_locked(gfi_index* h) {
+  if (!h->meta_dirty) return GFI_OK;
+  int32_t rc;
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  const size_t nf = h->meta_values.size();
+  h->meta_cols.resize(nf);
+  h->meta_dcols.resize(nf);
+  for (auto& c : h->meta_cols) c.resize((size_t)h->n_slots, 0u);
+  for (auto it = h->meta_pending.begin(); it != h->meta_pending.end();) {
+    uint32_t slot;
+    if (lookup_slot(h, it->first, &slot)) {
+      for (auto& c : h->meta_cols) c[slot] = 0u;  // Metadata is replaced wholesale at insert (storage.rs:169)
+      for (auto& fv : it->second) h->meta_cols[(size_t)fv.first][slot] = fv.second;
+      it = h->meta_pending.erase(it);
+    } else {
+      ++it;  // row not stored (yet): keep for later
+    }
+  }
+  std::vector<const uint32_t*> ptrs(nf);
+  for (size_t f = 0; f < nf; ++f) {
+    CU_TRY(h->meta_dcols[f].ensure(std::max<size_t>(h->meta_cols[f].size(), 1) * 4));
+    if (!h->meta_cols[f].empty())
+      CU_TRY(cudaMemcpyAsync(h->meta_dcols[f].p, h->meta_cols[f].data(), h->meta_cols[f].size() * 4,
+                             cudaMemcpyHostToDevice, h->ingest_stream));
+    ptrs[f] = h->meta_dcols[f].as<uint32_t>();
+  }
+  CU_TRY(h->meta_dptrs.ensure(std::max<size_t>(nf, 1) * sizeof(void*)));
+  if (nf) CU_TRY(cudaMemcpyAsync(h->meta_dptrs.p, ptrs.data(), nf * sizeof(void*), cudaMemcpyHostToDevice, h->ingest_stream));
+  CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  h->meta_dirty = false;
+  return GFI_OK;
+}
+
 static int32_t ensure_flushed(gfi_index* h) {
   bool need;
   {
@@ -1102,19 +1151,32 @@ static int32_t ensure_flushed(gfi_index* h) {
   return GFI_OK;
 }
 
-int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                   const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
-                   uint32_t* out_counts, int64_t kstride) {
+static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                           const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
+                           float* out_dist, uint32_t* out_counts, int64_t kstride) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (q < 0 || (q > 0 && (!queries || !ks || !out_counts))) return fail(GFI_ERR_INDEX, "bad arguments");
   if (q == 0) return GFI_OK;
   int32_t rc = ensure_flushed(h);
   if (rc != GFI_OK) return rc;
+  if (filter_json && h->meta_dirty) {
+    std::unique_lock<std::shared_mutex> gu(h->mu);
+    if ((rc = sync_metadata_locked(h)) != GFI_OK) return rc;
+  }
   std::shared_lock<std::shared_mutex> g(h->mu);
   ++h->n_search;
   h->n_queries += q;
   bool empty;
   if ((rc = precheck(h, dim, &empty)) != GFI_OK) return rc;
+  FilterProgram prog{};
+  if (filter_json) {
+    std::string err;
+    if (!compile_filter(filter_json, h->meta_fields, h->meta_values, &prog, &err))
+      return fail(GFI_ERR_INDEX, "bad filter: " + err);
+    // a field created after the last metadata sync has no column yet: treat as absent
+    for (int i = 0; i < prog.n; ++i)
+      if (prog.ops[i].field >= (int)h->meta_dcols.size()) prog.ops[i].field = -1;
+  }
   uint32_t kmax = 0;
   for (int64_t i = 0; i < q; ++i) kmax = std::max(kmax, ks[i]);
   if (empty || kmax == 0) {
@@ -1129,7 +1191,8 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
   cudaStream_t st = c->stream;
   const uint32_t kout = std::min<uint32_t>(kmax, (uint32_t)std::min<int64_t>(kstride, 1 << 20));
-  const size_t mask_words = mask ? (size_t)((mask_bits + 63) / 64) : 0;
+  if (filter_json) { mask = nullptr; mask_bits = h->n_slots; }
+  const size_t mask_words = (mask || filter_json) ? (size_t)((mask_bits + 63) / 64) : 0;
   CU_TRY(c->q_in.ensure((size_t)q * dim * 4));
   CU_TRY(c->ks.ensure((size_t)q * 4));
   CU_TRY(c->out_ids.ensure((size_t)q * kout * 8));
@@ -1141,7 +1204,7 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   CU_TRY(c->h_dist.ensure((size_t)q * kout * 4));
   CU_TRY(c->h_counts.ensure((size_t)q * 4));
   CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl)));
-  if (mask) CU_TRY(c->mask.ensure(mask_words * 8));
+  if (mask || filter_json) CU_TRY(c->mask.ensure(mask_words * 8 + 8));
   // queries already in pinned memory are copied straight from the caller's buffer
   const void* q_src = queries;
   if (!is_pinned_host(queries)) {
@@ -1152,9 +1215,16 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   CU_TRY(cudaMemcpyAsync(c->q_in.p, q_src, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
   CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
   if (mask) CU_TRY(cudaMemcpyAsync(c->mask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, st));
-  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax, mask ? c->mask.as<uint64_t>() : nullptr,
-               mask_bits, c->out_ids.as<uint64_t>(), c->out_dist.as<float>(), c->out_counts.as<uint32_t>(),
-               (int64_t)kout};
+  if (filter_json) {
+    // the filter is evaluated on the device into a bitmask over slots: host metadata is never walked
+    CU_TRY(cudaMemsetAsync(c->mask.p, 0, mask_words * 8 + 8, st));
+    CU_TRY(launch_eval_filter(prog, h->meta_dptrs.as<const uint32_t*>(), h->n_slots, c->mask.as<uint64_t>(), st));
+    ++h->n_launch;
+  }
+  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax,
+               (mask || filter_json) ? c->mask.as<uint64_t>() : nullptr, mask_bits, c->out_ids.as<uint64_t>(),
+               c->out_dist.as<float>(), c->out_counts.as<uint32_t>(), (int64_t)kout};
+  a.mask_by_slot = filter_json != nullptr;
   if ((rc = enqueue_search(h, c, a, st)) != GFI_OK) { cudaStreamSynchronize(st); return rc; }
   CU_TRY(cudaMemcpyAsync(c->h_ids.p, c->out_ids.p, (size_t)q * kout * 8, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)q * kout * 4, cudaMemcpyDeviceToHost, st));
@@ -1171,6 +1241,51 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
     memcpy(out_ids + i * kstride, c->h_ids.as<uint64_t>() + (size_t)i * kout, (size_t)hcnt[i] * 8);
     memcpy(out_dist + i * kstride, c->h_dist.as<float>() + (size_t)i * kout, (size_t)hcnt[i] * 4);
   }
+  return GFI_OK;
+}
+
+int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                   const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
+                   uint32_t* out_counts, int64_t kstride) {
+  return search_impl(h, queries, q, dim, ks, mask, mask_bits, nullptr, out_ids, out_dist, out_counts, kstride);
+}
+
+int32_t gfi_search_filtered(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                            const char* filter_json, uint64_t* out_ids, float* out_dist, uint32_t* out_counts,
+                            int64_t kstride) {
+  if (!filter_json) return fail(GFI_ERR_INDEX, "null filter");
+  return search_impl(h, queries, q, dim, ks, nullptr, 0, filter_json, out_ids, out_dist, out_counts, kstride);
+}
+
+int32_t gfi_set_metadata(gfi_index* h, uint64_t id, int32_t n_fields, const char* const* keys,
+                         const char* const* values) {
+  if (!h || n_fields < 0 || (n_fields > 0 && (!keys || !values))) return fail(GFI_ERR_INDEX, "bad arguments");
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  std::vector<std::pair<int, uint32_t>> enc;
+  enc.reserve((size_t)n_fields);
+  for (int i = 0; i < n_fields; ++i) {
+    auto it = h->meta_fields.find(keys[i]);
+    int f;
+    if (it == h->meta_fields.end()) {
+      f = (int)h->meta_values.size();
+      h->meta_fields[keys[i]] = f;
+      h->meta_values.emplace_back();
+    } else {
+      f = it->second;
+    }
+    auto& dict = h->meta_values[(size_t)f];
+    auto vt = dict.find(values[i]);
+    uint32_t code;
+    if (vt == dict.end()) {
+      code = (uint32_t)dict.size() + 1u;
+      dict[values[i]] = code;
+    } else {
+      code = vt->second;
+    }
+    enc.emplace_back(f, code);
+  }
+  h->meta_pending[id] = std::move(enc);
+  h->meta_dirty = true;
   return GFI_OK;
 }
 
@@ -1404,6 +1519,13 @@ int32_t compact_locked(gfi_index* h) {
   h->cap = ncap;
   h->n_slots = n_out;
   h->n_live = n_out;
+  for (auto& col : h->meta_cols) {
+    std::vector<uint32_t> nc((size_t)n_out, 0u);
+    for (int64_t j = 0; j < n_out; ++j)
+      if ((size_t)perm[(size_t)j] < col.size()) nc[(size_t)j] = col[perm[(size_t)j]];
+    col.swap(nc);
+  }
+  if (!h->meta_cols.empty()) h->meta_dirty = true;
   h->h_live.swap(nh_live);
   h->runs.swap(nruns);
   h->ids_identity = identity;

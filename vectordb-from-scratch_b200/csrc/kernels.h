@@ -158,6 +158,14 @@ struct SeedFinalizeParams {
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st);
 size_t gemm_smem_bytes();
 
+// ---- device-side MetadataFilter evaluation (filter.cu) ---------------------------------
+constexpr int kFilterEq = 0, kFilterNe = 1, kFilterExists = 2, kFilterAnd = 3, kFilterOr = 4;
+constexpr int kFilterMaxOps = 64, kFilterMaxDepth = 24;
+struct FilterOp { int kind; int field; uint32_t code; };  // And/Or: code = number of children
+struct FilterProgram { int n; FilterOp ops[kFilterMaxOps]; };  // postfix
+cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const* d_cols, int64_t n_slots,
+                               uint64_t* mask_words, cudaStream_t st);
+
 // misc
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st);
 cudaError_t launch_gather_rows(const IndexView& src, const uint32_t* perm, int64_t n_out, float* x32,

@@ -163,6 +163,32 @@ class GpuFlatIndex:
                                      mbits, out_ids.ctypes.data, out_dist.ctypes.data, cnt.ctypes.data, kmax))
         return out_ids, out_dist, cnt
 
+    def set_metadata(self, id, fields):
+        """Replace the metadata of `id` (dict str -> str): VectorStore::insert_with_metadata's
+        `self.metadata.insert(internal_id, metadata)` (src/storage.rs:169), kept as columns in HBM."""
+        items = list(fields.items())
+        n = len(items)
+        keys = (ctypes.c_char_p * max(n, 1))(*[k.encode() for k, _ in items])
+        vals = (ctypes.c_char_p * max(n, 1))(*[v.encode() for _, v in items])
+        self._chk(self._L.gfi_set_metadata(self._h, int(id), n, keys, vals))
+
+    def search_filtered(self, queries, ks, filter_json):
+        """FlatIndex::search over the rows matching a MetadataFilter (the reference's JSON form,
+        src/storage.rs:44-58), with the filter evaluated on the GPU.  Array form like search_arrays."""
+        import json as _json
+        if not isinstance(filter_json, str):
+            filter_json = _json.dumps(filter_json)
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        q, d = qs.shape
+        ks = np.ascontiguousarray(np.broadcast_to(np.asarray(ks, dtype=np.uint32), (q,)))
+        kmax = max(int(ks.max()) if q else 0, 1)
+        out_ids = np.zeros((q, kmax), dtype=np.uint64)
+        out_dist = np.zeros((q, kmax), dtype=np.float32)
+        cnt = np.zeros(q, dtype=np.uint32)
+        self._chk(self._L.gfi_search_filtered(self._h, qs.ctypes.data, q, d, ks.ctypes.data, filter_json.encode(),
+                                              out_ids.ctypes.data, out_dist.ctypes.data, cnt.ctypes.data, kmax))
+        return out_ids, out_dist, cnt
+
     def search_masked(self, query, k, eligible):
         """FlatIndex::search over the rows whose internal id is eligible (filter push-down)."""
         return self.search_batch([(query, k)], mask=eligible)[0]

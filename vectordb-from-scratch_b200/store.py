@@ -58,6 +58,14 @@ class MetadataFilter:
             return MetadataFilter(op, filters=[MetadataFilter.from_json(f) for f in obj["filters"]])
         return MetadataFilter(op, obj.get("field"), obj.get("value"))
 
+    def to_json(self):
+        if self.op in ("and", "or"):
+            return {"op": self.op, "filters": [f.to_json() for f in self.filters]}
+        out = {"op": self.op, "field": self.field}
+        if self.op != "exists":
+            out["value"] = self.value
+        return out
+
     def matches(self, md: Metadata) -> bool:
         if self.op == "eq":
             return md.get(self.field) == self.value and md.get(self.field) is not None
@@ -91,6 +99,7 @@ class VectorStore:
         self.next_id = 0
         self.dimension: Optional[int] = None
         self._host_rows: Dict[int, np.ndarray] = {}  # host mirror (what a Rust wrapper lends as &Vector)
+        self.device_metadata = True  # also keep metadata as dictionary-encoded columns on the GPU
 
     with_index = classmethod(lambda cls, index: cls(index=index))
 
@@ -113,6 +122,8 @@ class VectorStore:
         internal = self.next_id
         self.next_id += 1
         self.index.add(internal, v)
+        if self.device_metadata:
+            self.index.set_metadata(internal, metadata.fields)
         self.id_to_internal[id] = internal
         self.internal_to_id[internal] = id
         self.metadata[internal] = metadata
@@ -177,6 +188,9 @@ class VectorStore:
         if self.is_empty():
             return []
         q = self._check_dim(query)
+        if pushdown == "device":  # filter evaluated on the GPU from the device-side metadata columns
+            ids, dist, cnt = self.index.search_filtered(q[None, :], [k], flt.to_json())
+            return self._to_results([(int(ids[0, j]), float(dist[0, j])) for j in range(cnt[0])])
         if pushdown:
             return self._to_results(self.index.search_masked(q, k, self.filter_mask(flt)))
         fetch_k = min(max(k * 3, k), self.len())
@@ -216,5 +230,9 @@ class VectorStore:
         if self.is_empty():
             return [[] for _ in queries]
         qs = [(self._check_dim(q), k) for q, k in queries]
+        if pushdown == "device":
+            ids, dist, cnt = self.index.search_filtered(np.stack([q for q, _ in qs]), [k for _, k in qs], flt.to_json())
+            return [self._to_results([(int(ids[i, j]), float(dist[i, j])) for j in range(cnt[i])])
+                    for i in range(len(qs))]
         mask = self.filter_mask(flt)
         return [self._to_results(r) for r in self.index.search_batch(qs, mask=mask)]
