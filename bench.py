@@ -83,7 +83,7 @@ class ClockSampler(threading.Thread):
                 self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.05)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
@@ -126,7 +126,7 @@ def cpu_reference_run(wl, steps, warmup, sample_q=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gfi", choices=["gfi", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
@@ -246,6 +246,9 @@ def main():
     idx.search_status()
     ms = max_over_ranks(e0.elapsed_time(e1))
     st1 = idx.stats()
+    if rank == 0:  # the clock sampler (an nvidia-smi poll) covers the device-timed region only: left running it
+        sampler.stop_flag.set()  # perturbs the host-synchronous e2e calls below
+        sampler.join(timeout=3)
     ms_per_step = ms / args.steps
     # Weak scaling: every rank scores the q queries against its own 1-shard database, so the units all ranks
     # process per step are world * q (query, shard) searches; at N=1 this is plain queries/s.  The rate at which
@@ -261,11 +264,14 @@ def main():
         for _ in range(2):
             idx.search_arrays(queries_h, ks_h, mask=mask_h)
         barrier()
+        st_e0 = idx.stats()
         t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 10))
         for _ in range(e2e_steps):
             ids_h, dist_h, cnt_h = idx.search_arrays(queries_h, ks_h, mask=mask_h)
         t_e2e = (time.perf_counter() - t0) / e2e_steps
+        st_e1 = idx.stats()
+        e2e_kernel_ms = sum(st_e1[k2] - st_e0[k2] for k2 in ("tensor_kernel_ns", "scan_kernel_ns")) / e2e_steps / 1e6
     else:
         # sharded end to end: H2D of the replicated queries, local search, all-gather, merge, D2H on rank 0
         qpin = torch.from_numpy(queries_h).pin_memory()
@@ -281,10 +287,9 @@ def main():
         barrier()
         t_e2e = max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     idx.search_status()
-    if rank == 0:
-        sampler.stop_flag.set()
-        sampler.join(timeout=3)
     e2e_qps = world * q / t_e2e
+    if world > 1:
+        e2e_kernel_ms = None
 
     # ---- roofline of the dominant kernel (CUDA events around each launch, collected by libgfi) ----
     pk, pk_kind = peaks()
@@ -336,7 +341,8 @@ def main():
                    "index_rows_total": n * world, "l2_policy": "inputs larger than L2 (database >> 126 MB)",
                    "parallelism": f"row-sharded x{world}" if world > 1 else "single GPU"},
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(q * d * 4 + q * 4 + (mask_bits + 7) // 8),
-                "d2h_bytes_per_step": int(q * k * 12 + q * 4 + 16), "ms_per_step": t_e2e * 1e3},
+                "d2h_bytes_per_step": int(q * k * 12 + q * 4 + 16), "ms_per_step": t_e2e * 1e3,
+                "dominant_kernel_ms": e2e_kernel_ms},
         "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
         "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "scanned_gbs_fp32_equiv": n * world * d * 4 / (ms_per_step * 1e-3) / 1e9,

@@ -99,7 +99,9 @@ struct SearchCtx {
   cudaStream_t stream = nullptr;
   DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
       fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
-  PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl;
+  PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl, h_out;
+  DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
+  void* ctrl_dev = nullptr;  // control block of the search being enqueued (inside out_blk or `ctrl`)
   bool pending_status = false;  // device search issued, status not yet collected
   // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
   struct EvPair { cudaEvent_t a, b; int kind; };
@@ -109,7 +111,8 @@ struct SearchCtx {
     for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &cand_fb, &cand_fb_cnt,
                       &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
       b->release();
-    for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl}) b->release();
+    for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl, &h_out}) b->release();
+    out_blk.release();
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     evs.clear();
     ev_used = 0;
@@ -553,13 +556,16 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->q32.ensure((size_t)q * h->dpad * 4));
   CU_TRY(c->qnorm.ensure((size_t)q * 4));
   CU_TRY(c->qsumsq.ensure((size_t)q * 4));
-  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  if (!c->ctrl_dev) {
+    CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+    c->ctrl_dev = c->ctrl.p;
+  }
   CU_TRY(c->fb_list.ensure((size_t)q * 4));
   CU_TRY(c->sel_keys.ensure((size_t)q * 1024 * 8));
   CU_TRY(c->sel_info.ensure((size_t)q * sizeof(SelInfo)));
   if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
-  if (first_chunk) CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
-  Ctrl* ctrl = c->ctrl.as<Ctrl>();
+  if (first_chunk) CU_TRY(cudaMemsetAsync(c->ctrl_dev, 0, sizeof(Ctrl), st));
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(c->ctrl_dev);
 
   PrepQueriesParams pq{};
   pq.q_in = a.d_queries;
@@ -1195,15 +1201,16 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   const size_t mask_words = (mask || filter_json) ? (size_t)((mask_bits + 63) / 64) : 0;
   CU_TRY(c->q_in.ensure((size_t)q * dim * 4));
   CU_TRY(c->ks.ensure((size_t)q * 4));
-  CU_TRY(c->out_ids.ensure((size_t)q * kout * 8));
-  CU_TRY(c->out_dist.ensure((size_t)q * kout * 4));
-  CU_TRY(c->out_counts.ensure((size_t)q * 4));
+  // one device block [Ctrl | counts | dist | ids] so a single D2H copy returns everything
+  const size_t off_cnt = 64, off_dist = off_cnt + (((size_t)q * 4 + 63) & ~(size_t)63);
+  const size_t off_ids = off_dist + (((size_t)q * kout * 4 + 63) & ~(size_t)63);
+  const size_t blk_bytes = off_ids + (size_t)q * kout * 8;
+  CU_TRY(c->out_blk.ensure(blk_bytes));
+  CU_TRY(c->h_out.ensure(blk_bytes));
   CU_TRY(c->h_q.ensure((size_t)q * dim * 4));
   CU_TRY(c->h_ks.ensure((size_t)q * 4));
-  CU_TRY(c->h_ids.ensure((size_t)q * kout * 8));
-  CU_TRY(c->h_dist.ensure((size_t)q * kout * 4));
-  CU_TRY(c->h_counts.ensure((size_t)q * 4));
-  CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl)));
+  char* blk = c->out_blk.as<char>();
+  c->ctrl_dev = blk;
   if (mask || filter_json) CU_TRY(c->mask.ensure(mask_words * 8 + 8));
   // queries already in pinned memory are copied straight from the caller's buffer
   const void* q_src = queries;
@@ -1222,24 +1229,27 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     ++h->n_launch;
   }
   SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax,
-               (mask || filter_json) ? c->mask.as<uint64_t>() : nullptr, mask_bits, c->out_ids.as<uint64_t>(),
-               c->out_dist.as<float>(), c->out_counts.as<uint32_t>(), (int64_t)kout};
+               (mask || filter_json) ? c->mask.as<uint64_t>() : nullptr, mask_bits,
+               reinterpret_cast<uint64_t*>(blk + off_ids), reinterpret_cast<float*>(blk + off_dist),
+               reinterpret_cast<uint32_t*>(blk + off_cnt), (int64_t)kout};
   a.mask_by_slot = filter_json != nullptr;
-  if ((rc = enqueue_search(h, c, a, st)) != GFI_OK) { cudaStreamSynchronize(st); return rc; }
-  CU_TRY(cudaMemcpyAsync(c->h_ids.p, c->out_ids.p, (size_t)q * kout * 8, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)q * kout * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(c->h_counts.p, c->out_counts.p, (size_t)q * 4, cudaMemcpyDeviceToHost, st));
-  CU_TRY(cudaMemcpyAsync(c->h_ctrl.p, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
+  rc = enqueue_search(h, c, a, st);
+  c->ctrl_dev = nullptr;
+  if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
+  CU_TRY(cudaMemcpyAsync(c->h_out.p, blk, blk_bytes, cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
   prof_collect(h, c);
-  const Ctrl* hc = c->h_ctrl.as<Ctrl>();
+  const char* hb = c->h_out.as<char>();
+  const Ctrl* hc = reinterpret_cast<const Ctrl*>(hb);
   h->n_fallback_q += hc->uncertified;
   if ((rc = flags_to_status(hc->flags)) != GFI_OK) return rc;
-  const uint32_t* hcnt = c->h_counts.as<uint32_t>();
+  const uint32_t* hcnt = reinterpret_cast<const uint32_t*>(hb + off_cnt);
+  const float* hdist = reinterpret_cast<const float*>(hb + off_dist);
+  const uint64_t* hids = reinterpret_cast<const uint64_t*>(hb + off_ids);
   for (int64_t i = 0; i < q; ++i) {
     out_counts[i] = hcnt[i];
-    memcpy(out_ids + i * kstride, c->h_ids.as<uint64_t>() + (size_t)i * kout, (size_t)hcnt[i] * 8);
-    memcpy(out_dist + i * kstride, c->h_dist.as<float>() + (size_t)i * kout, (size_t)hcnt[i] * 4);
+    memcpy(out_ids + i * kstride, hids + (size_t)i * kout, (size_t)hcnt[i] * 8);
+    memcpy(out_dist + i * kstride, hdist + (size_t)i * kout, (size_t)hcnt[i] * 4);
   }
   return GFI_OK;
 }
@@ -1320,7 +1330,10 @@ int32_t gfi_search_device(gfi_index* h, const float* d_queries, int64_t q, const
     return GFI_OK;
   }
   SearchArgs a{d_queries, q, d_ks, kmax, d_mask, mask_bits, d_out_ids, d_out_dist, d_out_counts, kstride};
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  c->ctrl_dev = c->ctrl.p;
   rc = enqueue_search(h, c, a, st);
+  c->ctrl_dev = nullptr;
   c->pending_status = true;
   // remember which stream to synchronise when the status is collected
   c->h_ctrl.ensure(sizeof(Ctrl) + sizeof(cudaStream_t));

@@ -402,9 +402,15 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
                              cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
   if (p.num_m_tiles * BM > kGemmMaxQueries) return cudaErrorInvalidValue;
-  cudaError_t e =
-      cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-  if (e != cudaSuccess) return e;
+  static bool attr_set[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (!attr_set[dev & 15]) {  // once per device: the driver call is not free
+    cudaError_t e =
+        cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[dev & 15] = true;
+  }
   const CUtensorMap* tx = reinterpret_cast<const CUtensorMap*>(tmap_x_host);
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
   gemm_topk_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);

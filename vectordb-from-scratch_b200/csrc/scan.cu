@@ -354,8 +354,14 @@ cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t sme
 #define GFI_SCAN_CASE(Q)                                                                                  \
   case Q: {                                                                                               \
     auto kern = scan_topk_kernel<METRIC, Q, LPR, SEG>;                                                    \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    if (e != cudaSuccess) return e;                                                                       \
+    static bool attr_set[16] = {};                                                                        \
+    int dev = 0;                                                                                          \
+    cudaGetDevice(&dev);                                                                                  \
+    if (!attr_set[dev & 15]) { /* once per kernel and device: the driver call is not free */              \
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);    \
+      if (e != cudaSuccess) return e;                                                                     \
+      attr_set[dev & 15] = true;                                                                          \
+    }                                                                                                     \
     kern<<<grid, kScanThreads, smem, st>>>(p);                                                            \
     return cudaGetLastError();                                                                            \
   }

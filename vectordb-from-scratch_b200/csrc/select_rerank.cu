@@ -122,10 +122,11 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
 
 // ---- K3a: per query, pick the KP best candidate keys (by approximate score) ----------------------
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
-  __shared__ uint64_t keys[kSelCap];
-  __shared__ uint64_t sel[kMaxKP];
+  extern __shared__ __align__(16) uint64_t s_dyn[];  // sel[KP] | keys[kSelCap] | (sorted-list path only) keys2[kSelCap]
+  uint64_t* sel = s_dyn;
+  uint64_t* keys = s_dyn + p.KP;
+  uint64_t* keys2 = keys + kSelCap;  // prefix keys of the sorted-list path (keys[] holds the heads meanwhile)
   __shared__ uint32_t hist[256];
-  __shared__ uint64_t keys2[kSelCap];  // prefix keys of the sorted-list path (keys[] holds the heads meanwhile)
   __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need;
   const int tid = threadIdx.x, lane = tid & 31;
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
@@ -508,7 +509,8 @@ __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const 
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
   if (p.KP < 32 || p.KP > kMaxKP || (p.KP & (p.KP - 1))) return cudaErrorInvalidValue;
-  select_kernel<<<grid, kSelThreads, 0, st>>>(p);
+  const size_t sel_smem = ((size_t)p.KP + (size_t)kSelCap * (p.list_len > 0 ? 2 : 1)) * 8;
+  select_kernel<<<grid, kSelThreads, sel_smem, st>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   SelectParams pp = p;
