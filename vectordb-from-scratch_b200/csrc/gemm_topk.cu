@@ -160,6 +160,13 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
+    // Convergent code: all lanes run the loop with identical (uniform) operands and one elected lane issues
+    // inside the asm, so the descriptors live in uniform registers and a k-step is a few dozen instructions.
+    // Descriptor low words: (addr >> 4) | LBO<<16; a stage is 16 KB (A) / 32 KB (B) further, a K step 32 bytes.
+    const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
+    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull);
     int s = 0;
     uint32_t ph = 0, ai = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
@@ -170,21 +177,18 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a0 = smem_u32(sA + (size_t)s * kABytes);
-          const uint32_t b0 = smem_u32(sB + (size_t)s * kBBytes);
-#pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            umma_f16(d_tmem, make_sw128_desc(a0 + k * 32), make_sw128_desc(b0 + k * 32), kIdesc,
-                     (kb | k) != 0 ? 1u : 0u);
-          }
-          umma_commit(&empty[s]);                         // ring slot free once these MMAs retire
-          if (kb == num_kb - 1) umma_commit(&tfull[as]);  // accumulator complete
-        }
-        __syncwarp();
+        const uint32_t a_lo = a_lo_base + (uint32_t)s * (kABytes >> 4);
+        const uint32_t b_lo = b_lo_base + (uint32_t)s * (kBBytes >> 4);
+        umma_f16_elect(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
+        umma_f16_elect(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
+        umma_f16_elect(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
+        umma_f16_elect(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+        umma_commit_elect(empty0 + s * 8);                           // ring slot free once these MMAs retire
+        if (kb == num_kb - 1) umma_commit_elect(tfull0 + as * 8);    // accumulator complete
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
+    (void)full0;
   } else if (warp == 2) {
     // ------------------------------ coefficient stager ------------------------------
     // lane owns rows lane, lane+32, ... of the tile.  Raw loads for the NEXT item are issued before
