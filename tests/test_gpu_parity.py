@@ -134,6 +134,9 @@ SCAN_CASES = [  # n, d, kind, q, k
     (900, 17, 0, 9, 33),       # odd d, q > 8 (two passes), k -> K=64
     (1200, 1000, 1, 1, 10),    # d > 256 and not a multiple of 256
     (257, 64, 1, 2, 300),      # k > n
+    (600, 1500, 1, 2, 10),     # rows longer than 4 KB: column-segmented ring stages
+    (500, 2100, 0, 5, 7),      # three column segments, q > 4 (two passes)
+    (3000, 64, 0, 1, 1000),    # k = 1000: the largest list length (K = 1024)
 ]
 
 
@@ -557,3 +560,12 @@ def test_device_side_filter_matches_host_truth_table():
     assert store.search_with_filter(rows[5], 3, F.and_([F.eq("size", "huge"), F.exists("color")]), pushdown="device") == []
     with pytest.raises(gfi.IndexError_):
         store.index.search_filtered(queries, k, '{"op": "xor", "filters": []}')
+
+
+def test_k_above_list_capacity_is_a_loud_error():
+    rows = oracle.gen_rows(99, 0, 2000, 16, 0)
+    idx = build("euclidean", rows)
+    with pytest.raises(gfi.IndexError_) as e:
+        idx.search(rows[0], 1500)
+    assert "k too large" in str(e.value)
+    assert len(idx.search(rows[0], 1016)) == 1016
