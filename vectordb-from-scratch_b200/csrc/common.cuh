@@ -32,14 +32,6 @@ __device__ __forceinline__ uint64_t pack_key(float d, uint32_t slot) {
 }
 constexpr uint64_t kKeySentinel = 0xFFFFFFFFFFFFFFFFull;
 
-// ---- reference-exact arithmetic (src/distance.rs:37-73, src/vector.rs:35-37) ----------
-// Sequential f32 sums, separately rounded multiply and add (no FMA contraction), neutral
-// element -0.0.  The __f*_rn intrinsics are never contracted by nvcc.
-__device__ __forceinline__ float exact_sumsq(const float* __restrict__ v, int d) {
-  float acc = -0.0f;
-  for (int i = 0; i < d; ++i) acc = __fadd_rn(acc, __fmul_rn(v[i], v[i]));
-  return acc;
-}
 
 // ---- synthetic generator (identical to oracle/flat_oracle.c) ------------------------
 __host__ __device__ __forceinline__ uint32_t mix32(uint32_t x) {
@@ -71,9 +63,6 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 }
 __device__ __forceinline__ void fence_mbar_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -121,15 +110,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(tmap) : "memory");
 }
 
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred = 0;
-  asm volatile(
-      "{\n\t.reg .pred P;\n\t"
-      "elect.sync _|P, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, P;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
 
 // tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
@@ -148,16 +128,6 @@ __device__ __forceinline__ void tc_fence_before() {
 }
 __device__ __forceinline__ void tc_fence_after() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-}
-// D[tmem] (+)= A[smem desc] * B[smem desc]^T, kind::f16 (fp16/bf16 in, fp32 accumulate). One thread issues.
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
 }
 // Warp-uniform variants: every lane executes the call with identical operands and ONE elected lane
 // issues.  Keeping the call site convergent lets the compiler keep descriptors in uniform registers
@@ -180,12 +150,6 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar_saddr) {
       "elect.sync _|q, 0xffffffff;\n\t"
       "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar_saddr)
       : "memory");
-}
-// Arrive on an mbarrier when all previously issued tcgen05.mma of this thread retire.
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                   smem_u32(bar))
-               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread = TMEM lane).

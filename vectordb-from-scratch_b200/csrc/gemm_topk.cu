@@ -400,8 +400,6 @@ __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
 
 }  // namespace
 
-size_t gemm_smem_bytes() { return kSmemBytes; }
-
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
                              cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;

@@ -11,7 +11,6 @@ constexpr int kMetricL2 = 0, kMetricCos = 1, kMetricDot = 2;
 // ---- error word shared by all kernels of one search call ---------------------------
 constexpr uint32_t kFlagNaN = 1u;        // a distance is NaN (reference: panic at flat_index.rs:62)
 constexpr uint32_t kFlagZeroNorm = 2u;   // cosine with a zero-norm eligible row / query (distance.rs:51-55)
-constexpr uint32_t kFlagOverflow = 4u;   // a candidate buffer overflowed (tensor path -> scan fallback)
 constexpr uint32_t kFlagInternal = 8u;   // watchdog / internal inconsistency
 
 // Read-only device view of the index, passed by value to kernels.
@@ -156,7 +155,6 @@ struct SeedFinalizeParams {
   const float* seeds; int q; int64_t seed_tiles; int rank; float* thresh;
 };
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st);
-size_t gemm_smem_bytes();
 
 // ---- device-side MetadataFilter evaluation (filter.cu) ---------------------------------
 constexpr int kFilterEq = 0, kFilterNe = 1, kFilterExists = 2, kFilterAnd = 3, kFilterOr = 4;

@@ -22,25 +22,8 @@ namespace {
 constexpr int kSelThreads = 256;
 constexpr int kMaxKP = 1024;
 
-__device__ __forceinline__ void block_bitonic_sort(uint64_t* arr, int N, int tid) {
-  for (int k = 2; k <= N; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < N / 2; t += kSelThreads) {
-        const int i = ((t / j) * 2 * j) + (t % j);
-        const int l = i + j;
-        const bool up = ((i & k) == 0);
-        const uint64_t a = arr[i], b = arr[l];
-        if ((a > b) == up) {
-          arr[i] = b;
-          arr[l] = a;
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
-// Reference-exact distance of query q (d floats) to row x; *score_out = pre-sqrt / raw value.
+// One step of the reference's sequential sums (src/distance.rs:37-44,67-73): separately rounded
+// subtract / multiply / add, never contracted to FMA.
 template <int METRIC>
 __device__ __forceinline__ float exact_step(float acc, float a, float b) {
   if (METRIC == kMetricL2) {
@@ -48,32 +31,6 @@ __device__ __forceinline__ float exact_step(float acc, float a, float b) {
     return __fadd_rn(acc, __fmul_rn(t, t));
   }
   return __fadd_rn(acc, __fmul_rn(a, b));
-}
-
-template <int METRIC>
-__device__ __forceinline__ float exact_distance(const float* __restrict__ q, const float* __restrict__ x,
-                                                int d, float qnorm, float xnorm) {
-  // Exactly d terms, in order (the zero padding beyond d is never touched).
-  float acc = -0.0f;
-  const float4* q4 = reinterpret_cast<const float4*>(q);
-  const float4* x4 = reinterpret_cast<const float4*>(x);
-  const int nv = d >> 2;
-#pragma unroll 4
-  for (int i = 0; i < nv; ++i) {
-    const float4 a = __ldg(q4 + i);
-    const float4 b = __ldg(x4 + i);
-    acc = exact_step<METRIC>(acc, a.x, b.x);
-    acc = exact_step<METRIC>(acc, a.y, b.y);
-    acc = exact_step<METRIC>(acc, a.z, b.z);
-    acc = exact_step<METRIC>(acc, a.w, b.w);
-  }
-  for (int i = nv * 4; i < d; ++i) acc = exact_step<METRIC>(acc, __ldg(q + i), __ldg(x + i));
-  if (METRIC == kMetricL2) return __fsqrt_rn(acc);
-  if (METRIC == kMetricDot) return -acc;
-  float sim = __fdiv_rn(acc, __fmul_rn(qnorm, xnorm));
-  if (sim < -1.0f) sim = -1.0f;
-  else if (sim > 1.0f) sim = 1.0f;
-  return __fsub_rn(1.0f, sim);
 }
 
 constexpr int kSelCap = 2048;     // valid candidate keys kept in shared memory (else: passes over global memory)
