@@ -711,7 +711,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
   const int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
   // candidate slots per (query, CTA, column half): 4x the expected hits of a slice (+ slack), power of two
-  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * main_grid, 1) + 12)));
+  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * main_grid, 1) + 8)));
   const int64_t cand_stride = (int64_t)main_grid * 2 * cap;  // per query
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));

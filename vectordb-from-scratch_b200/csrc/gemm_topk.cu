@@ -79,13 +79,18 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 
 // item -> (row tile, query tile).  The query tile is rotated by the row-tile index so that every
 // CTA meets every query tile: a query's candidates then spread evenly over all CTAs' slices.
+template <int MODE>
 __device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, int64_t& nt_idx, int64_t& n_tile,
                                            int& m_tile) {
   nt_idx = w / p.num_m_tiles;
   m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);
-  n_tile = p.seed_mode == 1 ? nt_idx * p.seed_stride : nt_idx;
+  n_tile = MODE == 1 ? nt_idx * p.seed_stride : nt_idx;
 }
 
+// MODE 0: main pass (threshold filter), 1: seed pass (per-thread smallest scores), 2: debug dump of all scores.
+// One instance per mode keeps the hot instance's code small: the epilogue is sensitive to instruction-cache
+// misses (a 4x larger unrolled epilogue ran 3x slower).
+template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                  const GemmParams p) {
@@ -106,7 +111,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const IndexView& iv = p.iv;
   const int num_kb = (iv.dpad16 + BK - 1) / BK;
-  const int64_t n_items = (p.seed_mode == 1 ? p.seed_tiles : p.num_n_tiles) * p.num_m_tiles;
+  const int64_t n_items = (MODE == 1 ? p.seed_tiles : p.num_n_tiles) * p.num_m_tiles;
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -141,7 +146,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         if (lane == 0) {
@@ -202,7 +207,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     auto fetch = [&](int64_t w, Raw& r) {
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
         const int64_t slot = n_tile * BN + lane + 32 * i;
@@ -223,7 +228,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
       const Raw cur = nxt;
       if (w + gridDim.x < n_items) fetch(w + gridDim.x, nxt);
       mbar_wait(&tempty[as], aph ^ 1u);  // the epilogue has drained the previous use of this stage
@@ -252,11 +257,11 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
-      if (p.seed_mode == 0 && qidx < p.q) thr = p.thresh[qidx];
+      if (MODE == 0 && qidx < p.q) thr = p.thresh[qidx];
       float sd[kSeedR];
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
@@ -282,7 +287,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           sc[2 * i + 1] = fmaf(__uint_as_float(r[2 * i + 1]), cf[i].z, cf[i].w);
         }
         const int col0 = half * (BN / 2) + c0;
-        if (p.seed_mode == 1) {
+        if (MODE == 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             if (sc[j] < sd[kSeedR - 1]) {
@@ -295,7 +300,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
               }
             }
           }
-        } else if (p.seed_mode == 2) {
+        } else if (MODE == 2) {
           // debug dump of every approximate score (tests only; small inputs)
           if (qidx < p.q) {
 #pragma unroll
@@ -312,37 +317,52 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
             m8[g8] = fminf(a, b);
           }
           const float mall = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
-          if (!(mall >= thr) && qidx < p.q && !(p.debug & 8)) {
-            // rare: append to the slice of the candidate buffer private to this (query, CTA, half):
-            // plain stores, no atomics, nothing to wait for
-            unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
-            uint32_t cnt = *hc;
-            uint64_t* mine = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
-#pragma unroll
+          // Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in this block, the
+          // warp re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane
+          // appends its own survivors to the candidate slice private to this (query, CTA, half) -- plain
+          // stores, no atomics.
+          if (__any_sync(0xffffffffu, !(mall >= thr) && qidx < p.q) && !(p.debug & 8)) {
+#pragma unroll 1
             for (int g8 = 0; g8 < 4; ++g8) {
-              if (!(m8[g8] >= thr)) {
+              const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
+              const bool mine = !(mg >= thr) && qidx < p.q;
+              if (!__any_sync(0xffffffffu, mine)) continue;
+              uint32_t v[8];
+              tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
+              const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+              const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+              tmem_ld_wait();
+              if (mine) {
+                float s8[8];
+                s8[0] = fmaf(__uint_as_float(v[0]), k0.x, k0.y); s8[1] = fmaf(__uint_as_float(v[1]), k0.z, k0.w);
+                s8[2] = fmaf(__uint_as_float(v[2]), k1.x, k1.y); s8[3] = fmaf(__uint_as_float(v[3]), k1.z, k1.w);
+                s8[4] = fmaf(__uint_as_float(v[4]), k2.x, k2.y); s8[5] = fmaf(__uint_as_float(v[5]), k2.z, k2.w);
+                s8[6] = fmaf(__uint_as_float(v[6]), k3.x, k3.y); s8[7] = fmaf(__uint_as_float(v[7]), k3.z, k3.w);
+                unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
+                uint32_t cnt = *hc;
+                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
-                  const float score = sc[8 * g8 + jj];
+                  const float score = s8[jj];
                   if (!(score >= thr)) {
                     if (score != score) {
                       atomicOr(p.flags, kFlagNaN);
                     } else {
-                      if (cnt < p.cand_cap) mine[cnt] = pack_key(score, (uint32_t)(n0 + col0 + 8 * g8 + jj));
+                      if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(n0 + col0 + 8 * g8 + jj));
                       else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: the query falls back to the scan
                       ++cnt;
                     }
                   }
                 }
+                *hc = (unsigned short)min(cnt, 65535u);
               }
             }
-            *hc = (unsigned short)min(cnt, 65535u);
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[as]);
-      if (p.seed_mode == 1 && qidx < p.q) {
+      if (MODE == 1 && qidx < p.q) {
         float* out = p.seeds + (((size_t)qidx * p.seed_tiles + nt_idx) * 2 + half) * kSeedR;
 #pragma unroll
         for (int i = 0; i < kSeedR; ++i) out[i] = sd[i];
@@ -408,14 +428,17 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 15]) {  // once per device: the driver call is not free
-    cudaError_t e =
-        cudaFuncSetAttribute(gemm_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev & 15] = true;
   }
   const CUtensorMap* tx = reinterpret_cast<const CUtensorMap*>(tmap_x_host);
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
-  gemm_topk_kernel<<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
+  if (p.seed_mode == 0) gemm_topk_kernel<0><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
+  else if (p.seed_mode == 1) gemm_topk_kernel<1><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
+  else gemm_topk_kernel<2><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
   return cudaGetLastError();
 }
 

@@ -332,14 +332,8 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
       };
       (void)qt;
       float acc = -0.0f;
-      load_chunk(0);
-      store_chunk(tile, 0);
-      __syncwarp();
-      for (int c = 0; c < nchunk; ++c) {
-        float* cur = tile + (c & 1) * kRrTile;
-        float* nxt = tile + ((c + 1) & 1) * kRrTile;
-        if (c + 1 < nchunk) load_chunk(c + 1);  // global loads in flight during the chain below
-        const float* row = cur + lane * (kRrCW + 1);
+      auto chain = [&](int c) {
+        const float* row = tile + (c & 1) * kRrTile + lane * (kRrCW + 1);
         const float* qc = s_q[wib][c & 1];
         const int c0 = c * kRrCW;
         const int lim = min(kRrCW, iv.d - c0);
@@ -349,7 +343,47 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
         } else {
           for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, qc[i], row[i]);
         }
-        if (c + 1 < nchunk) store_chunk(nxt, (c + 1) & 1);
+      };
+      // software pipeline, two chunks of global loads in flight: while chunk c is walked from shared
+      // memory, chunk c+1 sits in registers (stored right after) and chunk c+2 is being fetched
+      float4 stage2[8];
+      float qstage2 = 0.f;
+      auto load_chunk2 = [&](int c) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
+          const uint32_t rs = __shfl_sync(0xffffffffu, slot, row);
+          const int col = c * kRrCW + 4 * c4;
+          stage2[i] = (rs != 0xffffffffu && col < iv.dpad)
+                          ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)rs * iv.dpad + col))
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        qstage2 = (c * kRrCW + lane < iv.dpad) ? __ldg(qv + c * kRrCW + lane) : 0.f;
+      };
+      auto store_chunk2 = [&](float* t, int buf) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
+          float* dst = t + row * (kRrCW + 1) + 4 * c4;
+          dst[0] = stage2[i].x; dst[1] = stage2[i].y; dst[2] = stage2[i].z; dst[3] = stage2[i].w;
+        }
+        s_q[wib][buf][lane] = qstage2;
+      };
+      load_chunk(0);
+      store_chunk(tile, 0);
+      if (nchunk > 1) load_chunk(1);
+      __syncwarp();
+      for (int c = 0; c < nchunk; c += 2) {
+        // even step: registers `stage` hold chunk c+1
+        if (c + 2 < nchunk) load_chunk2(c + 2);
+        chain(c);
+        if (c + 1 < nchunk) store_chunk(tile + kRrTile, 1);
+        __syncwarp();
+        if (c + 1 >= nchunk) break;
+        // odd step: registers `stage2` hold chunk c+2
+        if (c + 3 < nchunk) load_chunk(c + 3);
+        chain(c + 1);
+        if (c + 2 < nchunk) store_chunk2(tile, 0);
         __syncwarp();
       }
       if (have) skeys[ci] = pack_key(finish_distance(acc, slot), slot);
