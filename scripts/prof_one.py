@@ -49,7 +49,7 @@ def timed(steps):
 
 if a.debug_sweep:
     idx.search_arrays(queries, ks)
-    for dbg in (0, 1, 2, 3, 4, 7):
+    for dbg in (0, 3, 4, 7, 23):
         idx.set_option("gemm_debug", dbg)
         try:
             r = timed(a.steps)

@@ -291,6 +291,31 @@ def test_tensor_path_matches_oracle(case):
     assert st["fallback_queries"] <= q // 4, st   # certification normally succeeds
 
 
+def test_tensor_path_cosine_coefficient_epilogue_and_tombstones():
+    """Cosine normally takes the raw-accumulator epilogue; the per-row-coefficient epilogue must give the same
+    answer, and the raw epilogue must drop tombstoned rows (it meets them as ordinary accumulators)."""
+    n, d, q, k = 24000, 256, 48, 10
+    rows = oracle.gen_rows(51, 0, n, d, 1)
+    queries = oracle.gen_rows(52, 0, q, d, 1)
+    idx = build("cosine", rows)
+    check_batch(idx, "cosine", rows, queries, k, ctx="raw epilogue")
+    idx.set_option("raw_epilogue", 0)
+    check_batch(idx, "cosine", rows, queries, k, ctx="coefficient epilogue")
+    idx.set_option("raw_epilogue", 1)
+    # remove the current winners of every query: they must vanish from the next answer
+    ids0, _, _ = idx.search_arrays(queries, k)
+    live = np.ones(n, dtype=bool)
+    for r in np.unique(ids0[:, :3]):
+        idx.remove(int(r))
+        live[int(r)] = False
+    got_ids, got_d, cnt = idx.search_arrays(queries, k)
+    ids = np.arange(n, dtype=np.uint64)
+    exp = oracle.search_batch("cosine", rows[live], queries, k, ids=ids[live], threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"raw tombstones q{i}")
+    assert idx.stats()["tensor_queries"] == 4 * q
+
+
 def test_tensor_path_with_mask_and_tombstones():
     n, d, q, k = 20000, 256, 48, 10
     rows = oracle.gen_rows(31, 0, n, d, 1)

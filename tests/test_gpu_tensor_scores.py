@@ -22,6 +22,17 @@ def fp16_scaled(a, per_row):
     return v.astype(np.float16).astype(np.float64), s.astype(np.float64)
 
 
+def fp16_normalised(a):
+    """ingest.cu for cosine: rows times fl(2^14 / norm), norm = the reference's sequential f32 sum of squares."""
+    a = np.asarray(a, dtype=np.float32)
+    sumsq = np.cumsum(a * a, axis=1, dtype=np.float32)[:, -1]
+    nrm = np.sqrt(sumsq, dtype=np.float32)
+    t = (np.float32(16384.0) / nrm).astype(np.float32)
+    v = (a * t[:, None]).astype(np.float32)
+    v = np.where(np.abs(v) < 2.0 ** -14, np.float32(0.0), v)
+    return v.astype(np.float16).astype(np.float64), np.full((a.shape[0], 1), 16384.0)
+
+
 @pytest.mark.parametrize("metric,n,d,q,kind", [
     ("dot", 512, 64, 128, 1),        # one k-block, exact tiles
     ("dot", 700, 128, 5, 1),         # partial row tile, partial query tile
@@ -34,22 +45,29 @@ def test_tensor_scores_match_fp16_model(metric, n, d, q, kind):
     idx = gfi.GpuFlatIndex({"dot": DM.DotProduct, "euclidean": DM.Euclidean, "cosine": DM.Cosine}[metric])
     idx.add_batch(np.arange(n, dtype=np.uint64), rows)
     got = idx.debug_tensor_scores(queries).astype(np.float64)
-    x16, sx = fp16_scaled(rows, per_row=True)
     q16, sq = fp16_scaled(queries, per_row=False)
-    dot = (q16 @ x16.T) / (sq * sx.T)  # [q, n]
     r64 = rows.astype(np.float64)
+    if metric == "cosine":
+        # cosine rows are stored normalised: fp16(x * (2^14 / ||x||)), norm in the reference's f32 arithmetic
+        x16, sx = fp16_normalised(rows)
+    else:
+        x16, sx = fp16_scaled(rows, per_row=True)
+    dot = (q16 @ x16.T) / (sq * sx.T)  # [q, n]; for cosine this is already q.x / ||x||
     if metric == "dot":
         model = -dot
     elif metric == "cosine":
-        model = -dot / np.sqrt((r64 ** 2).sum(axis=1))[None, :]
+        model = -dot
     else:
         model = (r64 ** 2).sum(axis=1)[None, :] - 2.0 * dot
     scale = np.abs(model).max()
     err = np.abs(got - model).max()
     assert err <= 2e-5 * scale, f"tcgen05 scores differ from the fp16 model: max err {err} (scale {scale})"
-    # the certification bound: |approx dot - exact dot| <= eps_rel * ||q|| * ||x||
+    # the certification bound: |approx dot - exact dot| <= eps_rel * ||q|| * ||x||  (cosine: both sides / ||x||)
     exact = queries.astype(np.float64) @ r64.T
     qn = np.linalg.norm(queries.astype(np.float64), axis=1)[:, None]
     xn = np.linalg.norm(r64, axis=1)[None, :]
     eps_rel = 2.0 ** -10 + 2.0 ** -20 + 2 * np.sqrt(d) * 2.0 ** -26 + (d + 8) * 2.0 ** -23
-    assert np.all(np.abs(dot - exact) <= eps_rel * qn * xn)
+    if metric == "cosine":
+        assert np.all(np.abs(dot - exact / xn) <= eps_rel * qn)
+    else:
+        assert np.all(np.abs(dot - exact) <= eps_rel * qn * xn)

@@ -9,6 +9,7 @@
 // (stream + workspace) from a pool so concurrent `&self` callers never share state.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <chrono>
 
 #include <algorithm>
 #include <atomic>
@@ -197,6 +198,7 @@ struct gfi_index {
   int opt_grid = 0;        // 0 = sm_count
   int opt_tensor_min_rows = 8192;
   int opt_seed_rank = 8;
+  int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
   int opt_profile = 0;
   int opt_gemm_debug = 0;
   int opt_scan_stages = 0;
@@ -759,7 +761,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   SeedFinalizeParams sf{c->seeds.as<float>(), q, seed_tiles, rank, c->thresh.as<float>()};
   CU_TRY(launch_seed_finalize(sf, st));
   // main pass
-  gp.seed_mode = 0;
+  // cosine without a caller mask: raw-accumulator epilogue (rows are stored pre-normalised, one coefficient)
+  gp.seed_mode = (h->metric == kMetricCos && mv.bits == nullptr && h->opt_raw_epilogue) ? 3 : 0;
   prof_begin(h, c, 1, st);
   CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, main_grid, st));
   prof_end(h, c, st);
@@ -1192,6 +1195,9 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   if ((int64_t)kmax > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
   if (!out_ids || !out_dist) return fail(GFI_ERR_INDEX, "null output buffers");
   if ((rc = set_device(h)) != GFI_OK) return rc;
+  static const bool host_trace = getenv("GFI_HOST_TRACE") != nullptr;  // investigation aid: phase times on stderr
+  auto now_us = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  const double t_begin = host_trace ? now_us() : 0.0;
   SearchCtx* c = acquire_ctx(h);
   if (!c) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
   struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
@@ -1237,7 +1243,9 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   c->ctrl_dev = nullptr;
   if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
   CU_TRY(cudaMemcpyAsync(c->h_out.p, blk, blk_bytes, cudaMemcpyDeviceToHost, st));
+  const double t_enq = host_trace ? now_us() : 0.0;
   CU_TRY(cudaStreamSynchronize(st));
+  const double t_sync = host_trace ? now_us() : 0.0;
   prof_collect(h, c);
   const char* hb = c->h_out.as<char>();
   const Ctrl* hc = reinterpret_cast<const Ctrl*>(hb);
@@ -1251,6 +1259,9 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     memcpy(out_ids + i * kstride, hids + (size_t)i * kout, (size_t)hcnt[i] * 8);
     memcpy(out_dist + i * kstride, hdist + (size_t)i * kout, (size_t)hcnt[i] * 4);
   }
+  if (host_trace)
+    fprintf(stderr, "[gfi trace] q=%lld enqueue %.1f us, wait %.1f us, unpack %.1f us\n", (long long)q, t_enq - t_begin,
+            t_sync - t_enq, now_us() - t_sync);
   return GFI_OK;
 }
 
@@ -1455,6 +1466,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "scan_qt") h->opt_scan_qt = (int)value;
   else if (n == "grid") h->opt_grid = (int)value;
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
+  else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
   else if (n == "scan_stages") h->opt_scan_stages = (int)value;

@@ -40,6 +40,7 @@ constexpr int kBBytes = BN * BK * 2;  // 32 KB
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;          // first epilogue warp
 constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = kEpiThreads / 32;
 constexpr uint32_t kTmemCols = 512;
 
 constexpr size_t kOffA = 0;
@@ -87,7 +88,8 @@ __device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, int64
   n_tile = MODE == 1 ? nt_idx * p.seed_stride : nt_idx;
 }
 
-// MODE 0: main pass (threshold filter), 1: seed pass (per-thread smallest scores), 2: debug dump of all scores.
+// MODE 0: main pass (threshold filter, per-row coefficients), 1: seed pass (per-thread smallest scores),
+// 2: debug dump of all scores, 3: main pass with the raw epilogue (cosine, no mask).
 // One instance per mode keeps the hot instance's code small: the epilogue is sensitive to instruction-cache
 // misses (a 4x larger unrolled epilogue ran 3x slower).
 template <int MODE>
@@ -120,7 +122,7 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], kEpiThreads);
+      mbar_init(&tempty[s], kEpiWarps);
       mbar_init(&cfull[s], 1);
     }
     fence_mbar_init();
@@ -184,17 +186,19 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         tc_fence_after();
         const uint32_t a_lo = a_lo_base + (uint32_t)s * (kABytes >> 4);
         const uint32_t b_lo = b_lo_base + (uint32_t)s * (kBBytes >> 4);
-        umma_f16_elect(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
-        umma_f16_elect(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
-        umma_f16_elect(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
-        umma_f16_elect(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+        if (!(p.debug & 16)) {  // bit4 (timing experiments): barrier handshakes only, no MMA
+          umma_f16_elect(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
+          umma_f16_elect(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
+          umma_f16_elect(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
+          umma_f16_elect(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+        }
         umma_commit_elect(empty0 + s * 8);                           // ring slot free once these MMAs retire
         if (kb == num_kb - 1) umma_commit_elect(tfull0 + as * 8);    // accumulator complete
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
     (void)full0;
-  } else if (warp == 2) {
+  } else if (warp == 2 && MODE != 3) {
     // ------------------------------ coefficient stager ------------------------------
     // lane owns rows lane, lane+32, ... of the tile.  Raw loads for the NEXT item are issued before
     // the current item's values are consumed, so nothing here waits on memory in steady state.
@@ -252,6 +256,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     const int half = (warp - kEpiWarp0) >> 2;     // which 128 columns of the 256-column tile
     const int mrow = quarter * 32 + lane;         // row of the 128-query tile owned by this thread
     const float kInf = __int_as_float(0x7f800000);
+    // raw mode: score = acc * c_q, c_q = -(1 / query scale) * 2^-14 (row scale), exact powers of two
+    const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
     uint32_t ai = 0;
     for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
@@ -261,18 +267,84 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
-      if (MODE == 0 && qidx < p.q) thr = p.thresh[qidx];
+      if ((MODE == 0 || MODE == 3) && qidx < p.q) thr = p.thresh[qidx];
       float sd[kSeedR];
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
 
-      mbar_wait(&cfull[as], aph);
+      // one lane polls, the warp follows: 32x fewer try_wait probes competing with the MMA / TMA warps' own
+      // barrier traffic (acquire by lane 0 + __syncwarp orders the other lanes' reads)
+      if (MODE != 3) mbar_wait(&cfull[as], aph);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
+      if (MODE == 3) {
+        // Raw epilogue (cosine rows are stored pre-normalised, so score = acc * c_q with one per-batch constant):
+        // the filter compares accumulators with thr / c_q directly -- no per-row coefficients, 3-input max trees.
+        // Two 32-column loads are kept in flight; tombstoned / out-of-range rows are weeded out in the rare path.
+        const float thr_raw = __fdiv_rn(thr, c_q);  // exact: c_q is a (negative) power of two
+        auto process = [&](const uint32_t (&r)[32], const int c0) {
+          float m8[4];
+#pragma unroll
+          for (int g8 = 0; g8 < 4; ++g8) {
+            const float a = fmax3(__uint_as_float(r[8 * g8]), __uint_as_float(r[8 * g8 + 1]), __uint_as_float(r[8 * g8 + 2]));
+            const float b = fmax3(__uint_as_float(r[8 * g8 + 3]), __uint_as_float(r[8 * g8 + 4]), __uint_as_float(r[8 * g8 + 5]));
+            m8[g8] = fmax3(a, b, fmaxf(__uint_as_float(r[8 * g8 + 6]), __uint_as_float(r[8 * g8 + 7])));
+          }
+          const float mall = fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3]));
+          if (__any_sync(0xffffffffu, !(mall <= thr_raw) && qidx < p.q) && !(p.debug & 8)) {
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN / 2); c0 += 32) {
+            for (int g8 = 0; g8 < 4; ++g8) {
+              const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
+              const bool mine = !(mg <= thr_raw) && qidx < p.q;
+              if (!__any_sync(0xffffffffu, mine)) continue;
+              uint32_t v[8];
+              tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
+              const int64_t slot0 = n0 + half * (BN / 2) + c0 + 8 * g8;  // multiple of 8: one word of live bits
+              uint32_t lv = 0;
+              if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
+              tmem_ld_wait();
+              if (mine) {
+                unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
+                uint32_t cnt = *hc;
+                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                  const float acc = __uint_as_float(v[jj]);
+                  if (!(acc <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots) {
+                    if (acc != acc) {
+                      atomicOr(p.flags, kFlagNaN);
+                    } else {
+                      if (cnt < p.cand_cap) slice[cnt] = pack_key(acc * c_q, (uint32_t)(slot0 + jj));
+                      else p.cand_cnt[qidx] = 0xffffffffu;
+                      ++cnt;
+                    }
+                  }
+                }
+                *hc = (unsigned short)min(cnt, 65535u);
+              }
+            }
+          }
+        };
+        if (!(p.debug & 4)) {
+          uint32_t ra[32], rb[32];
+          tmem_ld_32x32b_x32(taddr, ra);
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(taddr + 32, rb);
+          process(ra, 0);
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(taddr + 64, ra);
+          process(rb, 32);
+          tmem_ld_wait();
+          tmem_ld_32x32b_x32(taddr + 96, rb);
+          process(ra, 64);
+          tmem_ld_wait();
+          process(rb, 96);
+        }
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < ((MODE == 3 || (p.debug & 4)) ? 0 : BN / 2); c0 += 32) {
         uint32_t r[32];
         tmem_ld_32x32b_x32(taddr + c0, r);
         // 32 (a,b) pairs as 16 broadcast 128-bit shared loads, issued while the TMEM load is in flight
@@ -361,7 +433,8 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[as]);  // one arrival per warp
       if (MODE == 1 && qidx < p.q) {
         float* out = p.seeds + (((size_t)qidx * p.seed_tiles + nt_idx) * 2 + half) * kSeedR;
 #pragma unroll
@@ -431,6 +504,7 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
     cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev & 15] = true;
   }
@@ -438,6 +512,7 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
   if (p.seed_mode == 0) gemm_topk_kernel<0><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
   else if (p.seed_mode == 1) gemm_topk_kernel<1><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
+  else if (p.seed_mode == 3) gemm_topk_kernel<3><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
   else gemm_topk_kernel<2><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
   return cudaGetLastError();
 }

@@ -52,7 +52,15 @@ __global__ void row_stats_kernel(const IngestParams p) {
   if (nrm == 0.f) fl |= kRowZeroNorm;
   if (!finite) fl |= kRowNonFinite | kRowUnsafe16;
   float s_row = 1.f;
-  if (finite && maxabs > 0.f) {
+  if (p.metric == kMetricCos) {
+    // cosine: the fp16 copy holds the NORMALISED row times 2^14, so every row has the same coefficient
+    // (-2^-14) and the tensor pass can filter on raw accumulators (gemm_topk.cu, raw epilogue).
+    s_row = 0.f;
+    if (finite && nrm > 0.f) {
+      s_row = __fdiv_rn(16384.f, nrm);
+      if (!(s_row <= 3.4028234664e38f) || !(nrm <= 3.4028234664e38f)) { s_row = 0.f; fl |= kRowUnsafe16; }
+    }
+  } else if (finite && maxabs > 0.f) {
     const int se = 14 - f32_exponent(maxabs);
     if (se > 100) fl |= kRowUnsafe16;  // too small for a representable power-of-two scale
     s_row = __uint_as_float((uint32_t)(min(max(se, -100), 100) + 127) << 23);
@@ -61,16 +69,16 @@ __global__ void row_stats_kernel(const IngestParams p) {
   if (p.x16) {
     __half* h = p.x16 + slot * p.dpad16;
     for (int i = 0; i < p.dpad16; ++i) {
-      float v = i < p.d ? x[i] * s_row : 0.f;
+      float v = i < p.d ? __fmul_rn(x[i], s_row) : 0.f;
       if (fabsf(v) < 6.103515625e-05f) v = 0.f;  // below 2^-14: flush (no fp16 subnormals on the MMA path)
       h[i] = __float2half_rn(v);
     }
   }
   if (p.coef) {
     float2 c;
-    const float inv_s = 1.0f / s_row;  // exact: power of two
+    const float inv_s = 1.0f / s_row;  // exact: power of two (unused for cosine)
     if (p.metric == kMetricL2) c = make_float2(-2.f * inv_s, acc);
-    else if (p.metric == kMetricCos) c = make_float2(nrm > 0.f ? -inv_s / nrm : 0.f, 0.f);
+    else if (p.metric == kMetricCos) c = make_float2(-6.103515625e-05f, 0.f);  // -2^-14, same for every row
     else c = make_float2(-inv_s, 0.f);
     p.coef[slot] = c;
   }
