@@ -17,10 +17,12 @@ ap.add_argument("--rows", type=int, default=0)
 ap.add_argument("--q", type=int, default=0)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--debug-sweep", action="store_true")
+ap.add_argument("--metric", default="")
 ap.add_argument("--opt", action="append", default=[], help="name=value passed to gfi_set_option")
 a = ap.parse_args()
 metric, n, d, kind, seed, q, k = WORKLOADS[a.workload]
 n = a.rows or n
+metric = a.metric or metric
 q = a.q or q
 idx = gfi.GpuFlatIndex(METRIC_ID[metric], dim=d)
 idx.reserve(n)
@@ -49,7 +51,7 @@ def timed(steps):
 
 if a.debug_sweep:
     idx.search_arrays(queries, ks)
-    for dbg in (0, 3, 4, 7, 23):
+    for dbg in (32, 32 + 4, 32 + 7, 32 + 23):  # bit5: print cycles / clock of CTA 0
         idx.set_option("gemm_debug", dbg)
         try:
             r = timed(a.steps)

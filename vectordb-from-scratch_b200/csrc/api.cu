@@ -198,6 +198,8 @@ struct gfi_index {
   int opt_grid = 0;        // 0 = sm_count
   int opt_tensor_min_rows = 8192;
   int opt_seed_rank = 8;
+  int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
+                             // gain -- the pass is power-limited either way -- so off by default
   int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
   int opt_profile = 0;
   int opt_gemm_debug = 0;
@@ -711,10 +713,15 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const int KP = h->opt_kp > 0 ? std::min(1024, pow2_at_least(h->opt_kp))
                                : std::min(1024, pow2_at_least(std::max<int>(64, 4 * (int)a.kmax)));
   const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
-  const int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
-  // candidate slots per (query, CTA, column half): 4x the expected hits of a slice (+ slack), power of two
-  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * main_grid, 1) + 8)));
-  const int64_t cand_stride = (int64_t)main_grid * 2 * cap;  // per query
+  int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
+  // CTA pairs (tcgen05 cta_group::2) when the batch has an even number of 128-query tiles: each SM then takes in
+  // a third less data per k-step through its L2 port, which is what bounds the single-CTA kernel
+  const bool pair = h->opt_pair && ((qpad / 128) % 2 == 0) && main_grid >= 2;
+  if (pair) main_grid &= ~1;
+  const int units = pair ? main_grid / 2 : main_grid;  // candidate slices are per (query, unit, column half)
+  // candidate slots per slice: 4x the expected hits of a slice (+ slack), power of two
+  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * units, 1) + 8)));
+  const int64_t cand_stride = (int64_t)units * 2 * cap;  // per query
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
   // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`
@@ -732,7 +739,9 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));  // sentinels
   CU_TRY(launch_fill_u32(c->cand_cnt.as<uint32_t>(), (uint32_t)cand_stride, q, st));
 
-  CUtensorMap tmx, tmq;
+  CUtensorMap tmx, tmq, tmx_half;
+  if (pair && !make_tmap_2d(&tmx_half, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 128))
+    return fail(GFI_ERR_INDEX, "cuTensorMapEncodeTiled failed");
   if (!make_tmap_2d(&tmx, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 256) ||
       !make_tmap_2d(&tmq, c->q16.p, (uint64_t)h->dpad16, (uint64_t)qpad, (uint64_t)h->dpad16 * 2, 64, 128))
     return fail(GFI_ERR_INDEX, "cuTensorMapEncodeTiled failed");
@@ -763,8 +772,9 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   // main pass
   // cosine without a caller mask: raw-accumulator epilogue (rows are stored pre-normalised, one coefficient)
   gp.seed_mode = (h->metric == kMetricCos && mv.bits == nullptr && h->opt_raw_epilogue) ? 3 : 0;
+  gp.pair = pair ? 1 : 0;
   prof_begin(h, c, 1, st);
-  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, main_grid, st));
+  CU_TRY(launch_gemm_topk(gp, pair ? &tmx_half : &tmx, &tmq, main_grid, st));
   prof_end(h, c, st);
   // select + exact rerank + certification
   SelectParams s{};
@@ -1467,6 +1477,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "grid") h->opt_grid = (int)value;
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;
+  else if (n == "pair") h->opt_pair = (int)value;
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
   else if (n == "scan_stages") h->opt_scan_stages = (int)value;

@@ -25,6 +25,7 @@
 // tiles (seed_mode = 1).  Scores are approximate (fp16 inputs); select_rerank.cu re-scores the
 // best candidates with the reference's exact arithmetic and certifies the result.
 #include <cuda.h>
+#include <cstdio>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -34,27 +35,34 @@ namespace gfi {
 namespace {
 
 constexpr int BM = 128, BN = 256, BK = 64;
-constexpr int kStages = 4;
 constexpr int kABytes = BM * BK * 2;  // 16 KB
-constexpr int kBBytes = BN * BK * 2;  // 32 KB
 constexpr int kGemmThreads = 384;
 constexpr int kEpiWarp0 = 4;          // first epilogue warp
 constexpr int kEpiThreads = 256;
 constexpr int kEpiWarps = kEpiThreads / 32;
 constexpr uint32_t kTmemCols = 512;
 
-constexpr size_t kOffA = 0;
-constexpr size_t kOffB = kOffA + (size_t)kStages * kABytes;
-constexpr size_t kOffCoef = kOffB + (size_t)kStages * kBBytes;
-constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
-constexpr size_t kOffCnt = kOffBar + 16 * 8 + 16;  // u16 hit counters [2 halves][queries]
-constexpr size_t kSmemUsed = kOffCnt + 2 * 2 * kGemmMaxQueries;
-constexpr size_t kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
-static_assert(kSmemBytes <= 232448, "shared memory budget");
-
-// UMMA instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, N=256, M=128.
-constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                            ((uint32_t)(BM >> 4) << 24);
+// CG = CTAs per MMA group.  CG == 1: one SM computes a 128 (queries) x 256 (rows) tile from a 16 KB query block
+// and a 32 KB row block per k-step.  CG == 2: a CTA pair (two SMs of one TPC) issues tcgen05.mma.cta_group::2,
+// M = 256: each CTA holds its own 128 queries and HALF of the row block (16 KB), the tensor cores fetch the other
+// half from the peer's shared memory.  Per SM that cuts the bytes taken in through the L2->SM port from 48 to
+// 32 KB per k-step -- the port (64 B/clk) is what bounds the CG == 1 kernel -- and leaves room for 6 ring stages.
+template <int CG> struct Geo {
+  static constexpr int kStages = CG == 2 ? 6 : 4;
+  static constexpr int kBRows = BN / CG;               // rows of the row block held by one CTA
+  static constexpr int kBBytes = kBRows * BK * 2;      // 32 KB / 16 KB
+  static constexpr size_t kOffA = 0;
+  static constexpr size_t kOffB = kOffA + (size_t)kStages * kABytes;
+  static constexpr size_t kOffCoef = kOffB + (size_t)kStages * kBBytes;
+  static constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
+  static constexpr size_t kOffCnt = kOffBar + 24 * 8 + 16;  // u16 hit counters [2 halves][queries]
+  static constexpr size_t kSmemUsed = kOffCnt + 2 * 2 * kGemmMaxQueries;
+  static constexpr size_t kSmemBytes = kSmemUsed + 1024;  // slack for manual 1024-byte alignment
+  static_assert(kSmemBytes <= 232448, "shared memory budget");
+  // UMMA instruction descriptor, kind::f16: D=f32, A=B=f16, both K-major, N=256, M=128*CG.
+  static constexpr uint32_t kIdesc = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                     ((uint32_t)((BM * CG) >> 4) << 24);
+};
 
 // UMMA shared-memory descriptor for a K-major SWIZZLE_128B tile (rows of 128 bytes, 8-row groups
 // 1024 bytes apart): start>>4 | LBO(16B, unused)<<16 | SBO(1024B)<<32 | version 1<<46 | SW128 (2)<<61.
@@ -80,40 +88,52 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 
 // item -> (row tile, query tile).  The query tile is rotated by the row-tile index so that every
 // CTA meets every query tile: a query's candidates then spread evenly over all CTAs' slices.
-template <int MODE>
-__device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, int64_t& nt_idx, int64_t& n_tile,
-                                           int& m_tile) {
-  nt_idx = w / p.num_m_tiles;
-  m_tile = (int)((w - nt_idx * p.num_m_tiles + nt_idx) % p.num_m_tiles);
-  n_tile = MODE == 1 ? nt_idx * p.seed_stride : nt_idx;
+template <int MODE, int CG>
+__device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, uint32_t rank, int64_t& nt_idx,
+                                           int64_t& n_tile, int& m_tile) {
+  // 32-bit arithmetic: items < 2^31 (launch_gemm_topk checks), and every role pays this once per item
+  const uint32_t mg = (uint32_t)p.num_m_tiles / CG;  // query-tile groups: a CTA pair takes two adjacent tiles
+  const uint32_t wi = (uint32_t)w;
+  const uint32_t nt = wi / mg;
+  const uint32_t r = wi - nt * mg + nt % mg;
+  nt_idx = nt;
+  m_tile = (int)((r >= mg ? r - mg : r) * CG + rank);
+  n_tile = MODE == 1 ? (int64_t)nt * p.seed_stride : (int64_t)nt;
 }
 
 // MODE 0: main pass (threshold filter, per-row coefficients), 1: seed pass (per-thread smallest scores),
 // 2: debug dump of all scores, 3: main pass with the raw epilogue (cosine, no mask).
 // One instance per mode keeps the hot instance's code small: the epilogue is sensitive to instruction-cache
 // misses (a 4x larger unrolled epilogue ran 3x slower).
-template <int MODE>
-__global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
-                 const GemmParams p) {
+template <int MODE, int CG>
+__device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUtensorMap& tmq, const GemmParams& p) {
+  using G = Geo<CG>;
+  constexpr int kStages = G::kStages;
+  constexpr int kBBytes = G::kBBytes;
+  constexpr uint32_t kIdesc = G::kIdesc;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                                          ~(uintptr_t)1023);
-  unsigned char* sA = smem + kOffA;
-  unsigned char* sB = smem + kOffB;
-  float2* sCoef = reinterpret_cast<float2*>(smem + kOffCoef);
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kOffBar);
+  unsigned char* sA = smem + G::kOffA;
+  unsigned char* sB = smem + G::kOffB;
+  float2* sCoef = reinterpret_cast<float2*>(smem + G::kOffCoef);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + G::kOffBar);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;   // accumulator stage complete (MMA -> epilogue)
   uint64_t* tempty = tfull + 2;        // accumulator + coefficient stage drained (epilogue -> MMA, stager)
   uint64_t* cfull = tempty + 2;        // coefficient stage published (stager -> epilogue)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cfull + 2);
-  unsigned short* hitcnt = reinterpret_cast<unsigned short*>(smem + kOffCnt);
+  uint64_t* cempty = cfull + 2;        // coefficient stage drained (epilogue -> stager, CTA-local)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
+  unsigned short* hitcnt = reinterpret_cast<unsigned short*>(smem + G::kOffCnt);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const IndexView& iv = p.iv;
   const int num_kb = (iv.dpad16 + BK - 1) / BK;
-  const int64_t n_items = (MODE == 1 ? p.seed_tiles : p.num_n_tiles) * p.num_m_tiles;
+  // work units: CTAs (CG == 1) or CTA pairs (CG == 2); both CTAs of a pair walk the same item sequence
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const int64_t unit = CG == 2 ? (int64_t)(blockIdx.x >> 1) : (int64_t)blockIdx.x;
+  const int64_t nunits = (int64_t)gridDim.x / CG;
+  const int64_t n_items = (MODE == 1 ? p.seed_tiles : p.num_n_tiles) * (p.num_m_tiles / CG);
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -122,8 +142,9 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
-      mbar_init(&tempty[s], kEpiWarps);
-      mbar_init(&cfull[s], 1);
+      mbar_init(&tempty[s], kEpiWarps * CG);  // pair: both CTAs' epilogue warps arrive on the leader's barrier
+      mbar_init(&cfull[s], 2);
+      mbar_init(&cempty[s], kEpiWarps);
     }
     fence_mbar_init();
   }
@@ -133,22 +154,35 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     tma_prefetch_desc(&tmq);
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if ((p.debug & 32) && tid == 0 && blockIdx.x == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
+    // pair: each CTA loads its own query block and its half of the row block; all bytes of a stage (both CTAs')
+    // are counted on the LEADER's full barrier, which is the one the MMA issuer waits on.
     int s = 0;
     uint32_t ph = 0, it = 0;
-    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x) {
+    const uint32_t full_lead0 = CG == 2 ? mapa_u32(smem_u32(full), 0) : 0u;
+    for (int64_t w = unit; w < n_items; w += nunits) {
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE, CG>(p, w, rank, nt_idx, n_tile, m_tile);
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         if (lane == 0) {
@@ -156,27 +190,38 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           // ring has been filled once, to separate the load path from the MMA and epilogue cost.
           const bool ldA = !((p.debug & 1) && it >= (uint32_t)kStages);
           const bool ldB = !((p.debug & 2) && it >= (uint32_t)kStages);
-          if (ldA || ldB) mbar_arrive_expect_tx(&full[s], (ldA ? kABytes : 0) + (ldB ? kBBytes : 0));
-          else mbar_arrive(&full[s]);
-          if (ldA) tma_load_2d(sA + (size_t)s * kABytes, &tmq, kb * BK, m_tile * BM, &full[s]);
-          if (ldB) tma_load_2d(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN), &full[s]);
+          const uint32_t bytes = (ldA ? kABytes : 0) + (ldB ? kBBytes : 0);
+          if (CG == 2) {
+            if (rank == 0) {
+              if (bytes) mbar_arrive_expect_tx(&full[s], bytes * 2);
+              else mbar_arrive(&full[s]);
+            }
+            const uint32_t bar = full_lead0 + (uint32_t)s * 8u;
+            if (ldA) tma_load_2d_pair(sA + (size_t)s * kABytes, &tmq, kb * BK, m_tile * BM, bar);
+            if (ldB) tma_load_2d_pair(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN) + (int)rank * G::kBRows, bar);
+          } else {
+            if (bytes) mbar_arrive_expect_tx(&full[s], bytes);
+            else mbar_arrive(&full[s]);
+            if (ldA) tma_load_2d(sA + (size_t)s * kABytes, &tmq, kb * BK, m_tile * BM, &full[s]);
+            if (ldB) tma_load_2d(sB + (size_t)s * kBBytes, &tmx, kb * BK, (int)(n_tile * BN), &full[s]);
+          }
         }
         __syncwarp();
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------ MMA issuer ------------------------------
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------ MMA issuer (pair: leader CTA only) ------------------------------
     // Convergent code: all lanes run the loop with identical (uniform) operands and one elected lane issues
     // inside the asm, so the descriptors live in uniform registers and a k-step is a few dozen instructions.
-    // Descriptor low words: (addr >> 4) | LBO<<16; a stage is 16 KB (A) / 32 KB (B) further, a K step 32 bytes.
+    // Descriptor low words: (addr >> 4) | LBO<<16; a stage is 16 KB (A) / 32|16 KB (B) further, a K step 32 bytes.
     const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t b_lo_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
     const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
-    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), tfull0 = smem_u32(tfull);
+    const uint32_t empty0 = smem_u32(empty), tfull0 = smem_u32(tfull);
     int s = 0;
     uint32_t ph = 0, ai = 0;
-    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
+    for (int64_t w = unit; w < n_items; w += nunits, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       mbar_wait(&tempty[as], aph ^ 1u);
       tc_fence_after();
@@ -187,22 +232,35 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
         const uint32_t a_lo = a_lo_base + (uint32_t)s * (kABytes >> 4);
         const uint32_t b_lo = b_lo_base + (uint32_t)s * (kBBytes >> 4);
         if (!(p.debug & 16)) {  // bit4 (timing experiments): barrier handshakes only, no MMA
-          umma_f16_elect(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
-          umma_f16_elect(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
-          umma_f16_elect(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
-          umma_f16_elect(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+          if (CG == 2) {
+            umma_f16_elect_pair(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
+            umma_f16_elect_pair(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
+            umma_f16_elect_pair(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
+            umma_f16_elect_pair(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+          } else {
+            umma_f16_elect(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
+            umma_f16_elect(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
+            umma_f16_elect(d_tmem, a_lo + 4, b_lo + 4, desc_hi, kIdesc, 1u);
+            umma_f16_elect(d_tmem, a_lo + 6, b_lo + 6, desc_hi, kIdesc, 1u);
+          }
         }
-        umma_commit_elect(empty0 + s * 8);                           // ring slot free once these MMAs retire
-        if (kb == num_kb - 1) umma_commit_elect(tfull0 + as * 8);    // accumulator complete
+        // ring slot free / accumulator complete once these MMAs retire (pair: signalled in both CTAs)
+        if (CG == 2) {
+          umma_commit_elect_pair(empty0 + s * 8, 3);
+          if (kb == num_kb - 1) umma_commit_elect_pair(tfull0 + as * 8, 3);
+        } else {
+          umma_commit_elect(empty0 + s * 8);
+          if (kb == num_kb - 1) umma_commit_elect(tfull0 + as * 8);
+        }
         if (++s == kStages) { s = 0; ph ^= 1u; }
       }
     }
-    (void)full0;
-  } else if (warp == 2 && MODE != 3) {
+  } else if ((warp == 2 || warp == 3) && MODE != 3) {
     // ------------------------------ coefficient stager ------------------------------
     // lane owns rows lane, lane+32, ... of the tile.  Raw loads for the NEXT item are issued before
     // the current item's values are consumed, so nothing here waits on memory in steady state.
-    constexpr int RPL = BN / 32;  // rows per lane
+    constexpr int RPL = BN / 64;  // rows per lane: warps 2 and 3 stage 128 rows each
+    const int r0 = (warp - 2) * (BN / 2);
     const float inv_sq = pow2_scale_inv(*p.qmaxabs);
     const float kInf = __int_as_float(0x7f800000);
     const bool has_mask = p.mask.bits != nullptr;
@@ -211,10 +269,10 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     auto fetch = [&](int64_t w, Raw& r) {
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE, CG>(p, w, rank, nt_idx, n_tile, m_tile);
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
-        const int64_t slot = n_tile * BN + lane + 32 * i;
+        const int64_t slot = n_tile * BN + r0 + lane + 32 * i;
         r.c[i] = make_float2(0.f, kInf);
         r.live[i] = 0;
         r.mask[i] = ~0ull;
@@ -226,26 +284,26 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       }
     };
     Raw nxt;
-    if ((int64_t)blockIdx.x < n_items) fetch(blockIdx.x, nxt);
+    if (unit < n_items) fetch(unit, nxt);
     uint32_t ai = 0;
-    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
+    for (int64_t w = unit; w < n_items; w += nunits, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE, CG>(p, w, rank, nt_idx, n_tile, m_tile);
       const Raw cur = nxt;
-      if (w + gridDim.x < n_items) fetch(w + gridDim.x, nxt);
-      mbar_wait(&tempty[as], aph ^ 1u);  // the epilogue has drained the previous use of this stage
+      if (w + nunits < n_items) fetch(w + nunits, nxt);
+      mbar_wait(&cempty[as], aph ^ 1u);  // the epilogue has drained the previous use of this stage
       float2* cs = sCoef + as * BN;
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
-        const int64_t slot = n_tile * BN + lane + 32 * i;
+        const int64_t slot = n_tile * BN + r0 + lane + 32 * i;
         bool elig = ((cur.live[i] >> (slot & 31)) & 1u) && ((cur.mask[i] >> (slot & 63)) & 1ull);
         if (elig && has_mask && !by_slot) {
           const uint64_t id = iv.ids[slot];
           elig = (id < (uint64_t)p.mask.nbits) && ((p.mask.bits[id >> 6] >> (id & 63)) & 1ull);
         }
-        cs[lane + 32 * i] = elig ? make_float2(cur.c[i].x * inv_sq, cur.c[i].y) : make_float2(0.f, kInf);
+        cs[r0 + lane + 32 * i] = elig ? make_float2(cur.c[i].x * inv_sq, cur.c[i].y) : make_float2(0.f, kInf);
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&cfull[as]);
@@ -257,13 +315,14 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
     const int mrow = quarter * 32 + lane;         // row of the 128-query tile owned by this thread
     const float kInf = __int_as_float(0x7f800000);
     // raw mode: score = acc * c_q, c_q = -(1 / query scale) * 2^-14 (row scale), exact powers of two
+    const uint32_t tempty_lead0 = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0u;
     const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
     uint32_t ai = 0;
-    for (int64_t w = blockIdx.x; w < n_items; w += gridDim.x, ++ai) {
+    for (int64_t w = unit; w < n_items; w += nunits, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
       int64_t nt_idx, n_tile;
       int m_tile;
-      item_tiles<MODE>(p, w, nt_idx, n_tile, m_tile);
+      item_tiles<MODE, CG>(p, w, rank, nt_idx, n_tile, m_tile);
       const int64_t n0 = n_tile * BN;
       const int qidx = m_tile * BM + mrow;
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
@@ -279,45 +338,87 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
-      if (MODE == 3) {
-        // Raw epilogue (cosine rows are stored pre-normalised, so score = acc * c_q with one per-batch constant):
-        // the filter compares accumulators with thr / c_q directly -- no per-row coefficients, 3-input max trees.
-        // Two 32-column loads are kept in flight; tombstoned / out-of-range rows are weeded out in the rare path.
-        const float thr_raw = __fdiv_rn(thr, c_q);  // exact: c_q is a (negative) power of two
+      if (MODE == 0 || MODE == 3) {
+        // Main-pass filter, 32 columns at a time with two TMEM loads in flight.
+        //  MODE 0: score = acc * a[row] + b[row] (coefficients as broadcast 128-bit shared loads), 3-input MIN
+        //          trees, ONE compare per 32 values against the query's threshold.
+        //  MODE 3 (cosine, rows stored pre-normalised: score = acc * c_q with one per-batch constant): compare raw
+        //          accumulators with thr / c_q -- no coefficients, 3-input MAX trees; tombstoned / out-of-range
+        //          rows are weeded out in the rare path.
+        // Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in a block, the warp
+        // re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane appends
+        // its own survivors to the candidate slice private to this (query, unit, half): plain stores, no atomics.
+        const float thr_raw = MODE == 3 ? __fdiv_rn(thr, c_q) : 0.f;  // exact: c_q is a (negative) power of two
         auto process = [&](const uint32_t (&r)[32], const int c0) {
           float m8[4];
 #pragma unroll
           for (int g8 = 0; g8 < 4; ++g8) {
-            const float a = fmax3(__uint_as_float(r[8 * g8]), __uint_as_float(r[8 * g8 + 1]), __uint_as_float(r[8 * g8 + 2]));
-            const float b = fmax3(__uint_as_float(r[8 * g8 + 3]), __uint_as_float(r[8 * g8 + 4]), __uint_as_float(r[8 * g8 + 5]));
-            m8[g8] = fmax3(a, b, fmaxf(__uint_as_float(r[8 * g8 + 6]), __uint_as_float(r[8 * g8 + 7])));
+            float v0 = __uint_as_float(r[8 * g8]), v1 = __uint_as_float(r[8 * g8 + 1]);
+            float v2 = __uint_as_float(r[8 * g8 + 2]), v3 = __uint_as_float(r[8 * g8 + 3]);
+            float v4 = __uint_as_float(r[8 * g8 + 4]), v5 = __uint_as_float(r[8 * g8 + 5]);
+            float v6 = __uint_as_float(r[8 * g8 + 6]), v7 = __uint_as_float(r[8 * g8 + 7]);
+            if (MODE == 3) {
+              m8[g8] = fmax3(fmax3(v0, v1, v2), fmax3(v3, v4, v5), fmaxf(v6, v7));
+            } else {
+              const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+              const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+              v0 = fmaf(v0, k0.x, k0.y); v1 = fmaf(v1, k0.z, k0.w);
+              v2 = fmaf(v2, k1.x, k1.y); v3 = fmaf(v3, k1.z, k1.w);
+              v4 = fmaf(v4, k2.x, k2.y); v5 = fmaf(v5, k2.z, k2.w);
+              v6 = fmaf(v6, k3.x, k3.y); v7 = fmaf(v7, k3.z, k3.w);
+              // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the rare path)
+              m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
+            }
           }
-          const float mall = fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3]));
-          if (__any_sync(0xffffffffu, !(mall <= thr_raw) && qidx < p.q) && !(p.debug & 8)) {
+          const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
+          const bool hit_any = MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
+          if (__any_sync(0xffffffffu, hit_any && qidx < p.q) && !(p.debug & 8)) {
 #pragma unroll 1
             for (int g8 = 0; g8 < 4; ++g8) {
               const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
-              const bool mine = !(mg <= thr_raw) && qidx < p.q;
+              const bool mine = (MODE == 3 ? !(mg <= thr_raw) : !(mg >= thr)) && qidx < p.q;
               if (!__any_sync(0xffffffffu, mine)) continue;
               uint32_t v[8];
               tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
               const int64_t slot0 = n0 + half * (BN / 2) + c0 + 8 * g8;  // multiple of 8: one word of live bits
-              uint32_t lv = 0;
-              if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
+              uint32_t lv = 0xffu;
+              float4 k0, k1, k2, k3;
+              if (MODE == 3) {
+                lv = 0;
+                if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
+              } else {
+                k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+                k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+              }
               tmem_ld_wait();
               if (mine) {
+                float s8[8];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) s8[jj] = __uint_as_float(v[jj]);
+                if (MODE == 3) {
+#pragma unroll
+                  for (int jj = 0; jj < 8; ++jj) {
+                    const bool ok = !(s8[jj] <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots;
+                    s8[jj] = ok ? s8[jj] * c_q : __int_as_float(0x7f800000);  // +inf never beats the threshold
+                  }
+                } else {
+                  s8[0] = fmaf(s8[0], k0.x, k0.y); s8[1] = fmaf(s8[1], k0.z, k0.w);
+                  s8[2] = fmaf(s8[2], k1.x, k1.y); s8[3] = fmaf(s8[3], k1.z, k1.w);
+                  s8[4] = fmaf(s8[4], k2.x, k2.y); s8[5] = fmaf(s8[5], k2.z, k2.w);
+                  s8[6] = fmaf(s8[6], k3.x, k3.y); s8[7] = fmaf(s8[7], k3.z, k3.w);
+                }
                 unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
                 uint32_t cnt = *hc;
-                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
+                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap;
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
-                  const float acc = __uint_as_float(v[jj]);
-                  if (!(acc <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots) {
-                    if (acc != acc) {
+                  const float score = s8[jj];
+                  if (!(score >= thr)) {
+                    if (score != score) {
                       atomicOr(p.flags, kFlagNaN);
                     } else {
-                      if (cnt < p.cand_cap) slice[cnt] = pack_key(acc * c_q, (uint32_t)(slot0 + jj));
-                      else p.cand_cnt[qidx] = 0xffffffffu;
+                      if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(slot0 + jj));
+                      else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: the query falls back to the scan
                       ++cnt;
                     }
                   }
@@ -342,99 +443,50 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
           tmem_ld_wait();
           process(rb, 96);
         }
-      }
+      } else {
+        // seed pass / debug dump: one 32-column block at a time
 #pragma unroll 1
-      for (int c0 = 0; c0 < ((MODE == 3 || (p.debug & 4)) ? 0 : BN / 2); c0 += 32) {
-        uint32_t r[32];
-        tmem_ld_32x32b_x32(taddr + c0, r);
-        // 32 (a,b) pairs as 16 broadcast 128-bit shared loads, issued while the TMEM load is in flight
-        float4 cf[16];
+        for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN / 2); c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_32x32b_x32(taddr + c0, r);
+          float4 cf[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) cf[i] = lds128(cs_addr + (c0 + 2 * i) * 8);
-        tmem_ld_wait();
-        float sc[32];
+          for (int i = 0; i < 16; ++i) cf[i] = lds128(cs_addr + (c0 + 2 * i) * 8);
+          tmem_ld_wait();
+          float sc[32];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          sc[2 * i] = fmaf(__uint_as_float(r[2 * i]), cf[i].x, cf[i].y);
-          sc[2 * i + 1] = fmaf(__uint_as_float(r[2 * i + 1]), cf[i].z, cf[i].w);
-        }
-        const int col0 = half * (BN / 2) + c0;
-        if (MODE == 1) {
+          for (int i = 0; i < 16; ++i) {
+            sc[2 * i] = fmaf(__uint_as_float(r[2 * i]), cf[i].x, cf[i].y);
+            sc[2 * i + 1] = fmaf(__uint_as_float(r[2 * i + 1]), cf[i].z, cf[i].w);
+          }
+          const int col0 = half * (BN / 2) + c0;
+          if (MODE == 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            if (sc[j] < sd[kSeedR - 1]) {
-              sd[kSeedR - 1] = sc[j];
+            for (int j = 0; j < 32; ++j) {
+              if (sc[j] < sd[kSeedR - 1]) {
+                sd[kSeedR - 1] = sc[j];
 #pragma unroll
-              for (int i = kSeedR - 1; i > 0; --i) {
-                const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
-                sd[i - 1] = lo;
-                sd[i] = hi;
+                for (int i = kSeedR - 1; i > 0; --i) {
+                  const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
+                  sd[i - 1] = lo;
+                  sd[i] = hi;
+                }
               }
             }
-          }
-        } else if (MODE == 2) {
-          // debug dump of every approximate score (tests only; small inputs)
-          if (qidx < p.q) {
+          } else if (qidx < p.q) {
+            // debug dump of every approximate score (tests only; small inputs)
 #pragma unroll
             for (int j = 0; j < 32; ++j) p.seeds[(size_t)qidx * p.seed_stride + (size_t)(n0 + col0 + j)] = sc[j];
-          }
-        } else {
-          // common case: no value of the block beats the threshold -> one min tree + one compare.
-          // (fminf drops NaN operands; a NaN query makes every score NaN, which still reaches the slow path.)
-          float m8[4];
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            const float a = fminf(fminf(sc[8 * g8], sc[8 * g8 + 1]), fminf(sc[8 * g8 + 2], sc[8 * g8 + 3]));
-            const float b = fminf(fminf(sc[8 * g8 + 4], sc[8 * g8 + 5]), fminf(sc[8 * g8 + 6], sc[8 * g8 + 7]));
-            m8[g8] = fminf(a, b);
-          }
-          const float mall = fminf(fminf(m8[0], m8[1]), fminf(m8[2], m8[3]));
-          // Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in this block, the
-          // warp re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane
-          // appends its own survivors to the candidate slice private to this (query, CTA, half) -- plain
-          // stores, no atomics.
-          if (__any_sync(0xffffffffu, !(mall >= thr) && qidx < p.q) && !(p.debug & 8)) {
-#pragma unroll 1
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
-              const bool mine = !(mg >= thr) && qidx < p.q;
-              if (!__any_sync(0xffffffffu, mine)) continue;
-              uint32_t v[8];
-              tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
-              const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
-              const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
-              tmem_ld_wait();
-              if (mine) {
-                float s8[8];
-                s8[0] = fmaf(__uint_as_float(v[0]), k0.x, k0.y); s8[1] = fmaf(__uint_as_float(v[1]), k0.z, k0.w);
-                s8[2] = fmaf(__uint_as_float(v[2]), k1.x, k1.y); s8[3] = fmaf(__uint_as_float(v[3]), k1.z, k1.w);
-                s8[4] = fmaf(__uint_as_float(v[4]), k2.x, k2.y); s8[5] = fmaf(__uint_as_float(v[5]), k2.z, k2.w);
-                s8[6] = fmaf(__uint_as_float(v[6]), k3.x, k3.y); s8[7] = fmaf(__uint_as_float(v[7]), k3.z, k3.w);
-                unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
-                uint32_t cnt = *hc;
-                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(blockIdx.x * 2 + half) * p.cand_cap;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float score = s8[jj];
-                  if (!(score >= thr)) {
-                    if (score != score) {
-                      atomicOr(p.flags, kFlagNaN);
-                    } else {
-                      if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(n0 + col0 + 8 * g8 + jj));
-                      else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: the query falls back to the scan
-                      ++cnt;
-                    }
-                  }
-                }
-                *hc = (unsigned short)min(cnt, 65535u);
-              }
-            }
           }
         }
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[as]);  // one arrival per warp
+      if (lane == 0) {  // one arrival per warp
+        if (CG == 2) mbar_arrive_cluster(tempty_lead0 + as * 8u);
+        else mbar_arrive(&tempty[as]);
+        if (MODE != 3) mbar_arrive(&cempty[as]);
+      }
       if (MODE == 1 && qidx < p.q) {
         float* out = p.seeds + (((size_t)qidx * p.seed_tiles + nt_idx) * 2 + half) * kSeedR;
 #pragma unroll
@@ -444,11 +496,33 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if ((p.debug & 32) && tid == 0 && blockIdx.x == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("[gemm_topk] cycles %lld ns %lld -> %.1f MHz\n", c1 - dbg_c0, t1 - dbg_t0, 1e3 * (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0));
+  }
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
+                 const GemmParams p) {
+  gemm_topk_body<MODE, 1>(tmx, tmq, p);
+}
+
+// CTA-pair instance: clusters of two CTAs (the two SMs of a TPC), tcgen05.mma.cta_group::2.
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
+                      const GemmParams p) {
+  gemm_topk_body<MODE, 2>(tmx, tmq, p);
 }
 
 // One warp per query: the rank-th smallest of the query's seed scores becomes its threshold.
@@ -497,23 +571,32 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
                              cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
   if (p.num_m_tiles * BM > kGemmMaxQueries) return cudaErrorInvalidValue;
+  if (p.num_n_tiles * p.num_m_tiles >= (1ll << 31)) return cudaErrorInvalidValue;
+  const bool pair = p.pair != 0;
+  if (pair && ((grid & 1) || (p.num_m_tiles & 1) || (p.seed_mode != 0 && p.seed_mode != 3))) return cudaErrorInvalidValue;
   static bool attr_set[16] = {};
   int dev = 0;
   cudaGetDevice(&dev);
   if (!attr_set[dev & 15]) {  // once per device: the driver call is not free
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    const int a = (int)Geo<1>::kSmemBytes, b = (int)Geo<2>::kSmemBytes;
+    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     if (e != cudaSuccess) return e;
     attr_set[dev & 15] = true;
   }
   const CUtensorMap* tx = reinterpret_cast<const CUtensorMap*>(tmap_x_host);
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
-  if (p.seed_mode == 0) gemm_topk_kernel<0><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
-  else if (p.seed_mode == 1) gemm_topk_kernel<1><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
-  else if (p.seed_mode == 3) gemm_topk_kernel<3><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
-  else gemm_topk_kernel<2><<<grid, kGemmThreads, kSmemBytes, st>>>(*tx, *tq, p);
+  const size_t sm1 = Geo<1>::kSmemBytes, sm2 = Geo<2>::kSmemBytes;
+  if (pair && p.seed_mode == 0) gemm_topk_pair_kernel<0><<<grid, kGemmThreads, sm2, st>>>(*tx, *tq, p);
+  else if (pair) gemm_topk_pair_kernel<3><<<grid, kGemmThreads, sm2, st>>>(*tx, *tq, p);
+  else if (p.seed_mode == 0) gemm_topk_kernel<0><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
+  else if (p.seed_mode == 1) gemm_topk_kernel<1><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
+  else if (p.seed_mode == 3) gemm_topk_kernel<3><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
+  else gemm_topk_kernel<2><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
   return cudaGetLastError();
 }
 

@@ -146,6 +146,8 @@ struct GemmParams {
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
   uint32_t* flags;
   int debug;            // timing experiments only (see gemm_topk.cu)
+  int pair;             // 1: CTA-pair kernel (cta_group::2); needs an even grid and an even number of query tiles;
+                        // the row tensor map then has a 128-row box and slices are per PAIR: (pair*2+half)
 };
 constexpr int kSeedR = 8;
 constexpr int kGemmMaxQueries = 4096;   // per launch (u16 hit counters [2 column halves][query] in shared memory)
