@@ -98,7 +98,7 @@ struct Ctrl {
 
 struct SearchCtx {
   cudaStream_t stream = nullptr;
-  DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
+  DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, slice_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
       fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
   PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl, h_out;
   DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
@@ -109,7 +109,7 @@ struct SearchCtx {
   std::vector<EvPair> evs;
   size_t ev_used = 0;
   void release() {
-    for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &cand_fb, &cand_fb_cnt,
+    for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &slice_cnt, &cand_fb, &cand_fb_cnt,
                       &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
       b->release();
     for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl, &h_out}) b->release();
@@ -736,8 +736,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->cand_fb_cnt.ensure((size_t)q * 4));
   CU_TRY(c->thresh.ensure((size_t)q * 4));
   CU_TRY(c->seeds.ensure((size_t)q * seed_tiles * 2 * kSeedR * 4));
-  CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));  // sentinels
-  CU_TRY(launch_fill_u32(c->cand_cnt.as<uint32_t>(), (uint32_t)cand_stride, q, st));
+  CU_TRY(c->slice_cnt.ensure((size_t)units * 2 * q * 2));  // written in full by the main pass: no pre-fill
+  // Usual case (expected candidates per query well below select_kernel's staging area): the select pass reads
+  // only the valid prefix of every slice.  Large k: pre-fill with sentinels and let it scan the whole block.
+  const bool slice_gather = 3 * hits <= kSelectStageKeys;
+  if (!slice_gather) CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));
 
   CUtensorMap tmx, tmq, tmx_half;
   if (pair && !make_tmap_2d(&tmx_half, iv.x16, (uint64_t)h->dpad16, (uint64_t)h->n_slots, (uint64_t)h->dpad16 * 2, 64, 128))
@@ -760,6 +763,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   gp.cand_cnt = c->cand_cnt.as<uint32_t>();
   gp.cand_stride = cand_stride;
   gp.cand_cap = cap;
+  gp.slice_cnt = c->slice_cnt.as<unsigned short>();
   gp.flags = &ctrl->flags;
   gp.seed_tiles = seed_tiles;
   gp.seed_stride = seed_stride;
@@ -779,6 +783,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   // select + exact rerank + certification
   SelectParams s{};
   fill_select(s, c->cand, c->cand_cnt, cand_stride, KP);
+  s.slice_cnt = c->slice_cnt.as<unsigned short>();
+  s.nslices = units * 2;
+  s.slice_cap = cap;
+  s.slice_q = q;
+  s.slice_gather = slice_gather ? 1 : 0;
   s.qlist = nullptr;
   s.nq_dev = nullptr;
   s.nq = q;
@@ -803,7 +812,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s2.list_len = K;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
   if (!last_chunk) CU_TRY(cudaMemsetAsync(&ctrl->fb_count, 0, 4, st));  // the next chunk starts an empty fallback list
-  h->n_launch += 9;
+  h->n_launch += 8;
   h->n_tensor_q += q;
   return GFI_OK;
 }

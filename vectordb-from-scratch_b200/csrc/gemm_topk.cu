@@ -418,8 +418,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
                       atomicOr(p.flags, kFlagNaN);
                     } else {
                       if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(slot0 + jj));
-                      else p.cand_cnt[qidx] = 0xffffffffu;  // overflow marker: the query falls back to the scan
-                      ++cnt;
+                      ++cnt;  // beyond the capacity only counted: select_kernel sees the overflow and falls back
                     }
                   }
                 }
@@ -461,16 +460,19 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
           }
           const int col0 = half * (BN / 2) + c0;
           if (MODE == 1) {
+            // Seed statistic: the minimum of each 32-row block (one insertion per block instead of 32 tests).
+            // The rank-th smallest block minimum is >= the rank-th smallest score, with equality unless two of
+            // the sample's `rank` best rows share a block -- a slightly looser threshold then, never a wrong one.
+            float m = fminf(sc[0], sc[1]);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (sc[j] < sd[kSeedR - 1]) {
-                sd[kSeedR - 1] = sc[j];
+            for (int j = 2; j < 32; j += 2) m = fmin3(m, sc[j], sc[j + 1]);
+            if (m < sd[kSeedR - 1]) {
+              sd[kSeedR - 1] = m;
 #pragma unroll
-                for (int i = kSeedR - 1; i > 0; --i) {
-                  const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
-                  sd[i - 1] = lo;
-                  sd[i] = hi;
-                }
+              for (int i = kSeedR - 1; i > 0; --i) {
+                const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
+                sd[i - 1] = lo;
+                sd[i] = hi;
               }
             }
           } else if (qidx < p.q) {
@@ -497,6 +499,15 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
 
   tc_fence_before();
   if (CG == 2) cluster_sync_all(); else __syncthreads();
+  if (MODE == 0 || MODE == 3) {
+    // publish this unit's per-query candidate counts (every entry, zeros included: nothing is pre-filled).
+    // A pair's CTAs own the query tiles of their own parity.
+    for (int i = tid; i < 2 * p.q; i += kGemmThreads) {
+      const int hf = i >= p.q ? 1 : 0, qi = i - hf * p.q;
+      if (CG == 1 || (uint32_t)((qi >> 7) & 1) == rank)
+        p.slice_cnt[(size_t)(unit * 2 + hf) * p.q + qi] = hitcnt[hf * kGemmMaxQueries + qi];
+    }
+  }
   if ((p.debug & 32) && tid == 0 && blockIdx.x == 0) {
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));

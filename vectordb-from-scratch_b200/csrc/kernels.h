@@ -108,6 +108,10 @@ struct SelectParams {
   const uint64_t* cand; const uint32_t* cand_cnt; int64_t cand_stride;
   int KP;                     // candidates reranked per query (power of two <= 1024)
   int list_len;               // > 0: the input is ascending lists of this length (scan path); 0: unordered slices
+  // tensor path: cand[q] is nslices slices of slice_cap keys; slice_cnt[slice][q] = keys the tensor pass produced
+  // for that (slice, query) (may exceed slice_cap: overflow).  Only the valid prefix of each slice is read.
+  const unsigned short* slice_cnt; int nslices; uint32_t slice_cap; int64_t slice_q;
+  int slice_gather;           // 1: read the slices' valid prefixes; 0: cand is sentinel-filled, scan it whole
   // certification (tensor path): every row that is not a candidate has approx score >= cutoff
   int certify;                // 0 = scan path (never falls back), 1 = tensor path
   const float* thresh;        // per-query score threshold used by the tensor kernel
@@ -140,16 +144,17 @@ struct GemmParams {
   int seed_mode; int64_t seed_tiles, seed_stride;
   float* seeds;         // [q][seed_tiles][2 column halves][R]
   const float* thresh;  // [q]
-  // main mode: cand[q][cand_stride] is pre-filled with sentinels; CTA b, column half h appends to the
-  // slice [(2b+h)*cand_cap, (2b+h+1)*cand_cap) of each query; cand_cnt[q] is pre-set to cand_stride and only
-  // overwritten (0xffffffff) when a slice overflows
+  // main mode: unit b (CTA or CTA pair), column half h appends to the slice [(2b+h)*cand_cap, (2b+h+1)*cand_cap)
+  // of cand[q][cand_stride]; the number of keys of every (slice, query) goes to slice_cnt (no pre-fill needed)
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
+  unsigned short* slice_cnt;  // [slices][q]: written for every (slice, query) at the end of the main pass
   uint32_t* flags;
   int debug;            // timing experiments only (see gemm_topk.cu)
   int pair;             // 1: CTA-pair kernel (cta_group::2); needs an even grid and an even number of query tiles;
                         // the row tensor map then has a 128-row box and slices are per PAIR: (pair*2+half)
 };
 constexpr int kSeedR = 8;
+constexpr int kSelectStageKeys = 2048;  // candidate keys select_kernel stages in shared memory per query
 constexpr int kGemmMaxQueries = 4096;   // per launch (u16 hit counters [2 column halves][query] in shared memory)
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
                              cudaStream_t st);

@@ -33,7 +33,7 @@ __device__ __forceinline__ float exact_step(float acc, float a, float b) {
   return __fadd_rn(acc, __fmul_rn(a, b));
 }
 
-constexpr int kSelCap = 2048;     // valid candidate keys kept in shared memory (else: passes over global memory)
+constexpr int kSelCap = kSelectStageKeys;     // valid candidate keys kept in shared memory (else: passes over global memory)
 constexpr int kTileFloats = 4096;  // rerank tile: GC candidates x CW floats, GC * CW = 4096
 
 // Exact 64-bit radix select: returns the `need`-th smallest (1-based) of the valid keys in src[0..cnt).
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   uint64_t* keys = s_dyn + p.KP;
   uint64_t* keys2 = keys + kSelCap;  // prefix keys of the sorted-list path (keys[] holds the heads meanwhile)
   __shared__ uint32_t hist[256];
-  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need;
+  __shared__ uint32_t s_count, s_nvalid, s_bucket, s_need, s_over;
   const int tid = threadIdx.x, lane = tid & 31;
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
   auto sel_stage = [&](uint64_t*, uint32_t pos, uint64_t key) { keys2[pos] = key; };
@@ -92,13 +92,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   for (int qq = blockIdx.x; qq < nq; qq += gridDim.x) {
     const uint32_t qg = p.qlist ? p.qlist[qq] : (uint32_t)qq;
     const uint64_t* cand = p.cand + (size_t)qg * p.cand_stride;
-    const uint32_t cnt_raw = p.cand_cnt[qg];
-    const bool overflow = cnt_raw > (uint32_t)p.cand_stride;
+    const uint32_t cnt_raw = p.slice_cnt ? (uint32_t)p.cand_stride : p.cand_cnt[qg];
+    bool overflow = cnt_raw > (uint32_t)p.cand_stride;
     const uint32_t cnt = overflow ? (uint32_t)p.cand_stride : cnt_raw;
     const int KP = p.KP;
 
     // ---- compact the useful keys into shared memory ----
-    if (tid == 0) { s_count = 0; s_nvalid = 0; }
+    if (tid == 0) { s_count = 0; s_nvalid = 0; s_over = 0; }
     __syncthreads();
     uint64_t bound = kKeySentinel - 1;
     const uint32_t L = p.list_len > 0 ? cnt / (uint32_t)p.list_len : 0;  // number of ascending lists
@@ -149,7 +149,22 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
           if (!more) break;
         }
       }
+    } else if (p.slice_cnt && p.slice_gather) {
+      // Tensor-path input: one thread per slice reads the slice's count, then its (few) valid keys.
+      for (int sl = tid; sl < p.nslices; sl += kSelThreads) {
+        uint32_t n = p.slice_cnt[(size_t)sl * p.slice_q + qg];
+        if (n > p.slice_cap) { s_over = 1; n = p.slice_cap; }
+        if (n) {
+          const uint64_t* src = cand + (size_t)sl * p.slice_cap;
+          const uint32_t base = atomicAdd(&s_nvalid, n);
+          for (uint32_t j = 0; j < n; ++j)
+            if (base + j < (uint32_t)kSelCap) keys[base + j] = src[j];
+        }
+      }
     } else {
+      if (p.slice_cnt)  // sentinel-filled tensor-path input (large KP): only the overflow check uses the counts
+        for (int sl = tid; sl < p.nslices; sl += kSelThreads)
+          if (p.slice_cnt[(size_t)sl * p.slice_q + qg] > p.slice_cap) s_over = 1;
       for (uint32_t i0 = 0; i0 < cnt; i0 += kSelThreads * 4) {
         uint64_t kk[4];
 #pragma unroll
@@ -174,10 +189,13 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     __syncthreads();
     const uint32_t nvalid = s_nvalid;
     const uint32_t kpeff = min((uint32_t)KP, nvalid);
-    const bool in_smem = nvalid <= (uint32_t)kSelCap;
+    // slices are not contiguous in global memory, so a query whose keys do not fit the staging area is
+    // treated as overflowed (it falls back to the exact scan)
+    if (p.slice_cnt && (s_over || (p.slice_gather && nvalid > (uint32_t)kSelCap))) overflow = true;
+    const bool in_smem = nvalid <= (uint32_t)kSelCap || (p.slice_cnt && p.slice_gather);
     const bool sorted_path = L && L * m_heads <= (uint32_t)kSelCap;
     const uint64_t* src = in_smem ? (sorted_path ? keys2 : keys) : cand;
-    const uint32_t src_n = in_smem ? nvalid : cnt;
+    const uint32_t src_n = in_smem ? min(nvalid, (uint32_t)kSelCap) : cnt;
 
     // ---- exact radix select of the KP-th smallest key (only when there are more than KP) ----
     uint64_t pivot = kKeySentinel - 1;  // everything valid is <= pivot
