@@ -316,6 +316,20 @@ def test_tensor_path_cosine_coefficient_epilogue_and_tombstones():
     assert idx.stats()["tensor_queries"] == 4 * q
 
 
+@pytest.mark.parametrize("metric", ["cosine", "euclidean"])
+def test_tensor_path_cta_pair_kernel(metric):
+    """The cta_group::2 (CTA pair, M = 256) instance of the tensor pass, behind set_option("pair", 1): same
+    answers as the single-CTA instance, for the raw (cosine) and the coefficient (euclidean) epilogue."""
+    n, d, q, k = 30000, 192, 300, 10      # 3 query tiles -> padded to 4: two tile pairs, one of them half empty
+    rows = oracle.gen_rows(71, 0, n, d, 1)
+    queries = oracle.gen_rows(72, 0, q, d, 1)
+    idx = build(metric, rows)
+    idx.set_option("pair", 1)
+    check_batch(idx, metric, rows, queries, k, ctx="pair kernel")
+    st = idx.stats()
+    assert st["tensor_queries"] == q and st["fallback_queries"] <= q // 4, st
+
+
 def test_tensor_path_with_mask_and_tombstones():
     n, d, q, k = 20000, 256, 48, 10
     rows = oracle.gen_rows(31, 0, n, d, 1)

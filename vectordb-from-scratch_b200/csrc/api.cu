@@ -556,7 +556,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
                          a.kmax <= 256 && h->dpad16 >= 64 && get_encode_fn() != nullptr;
 
   // ---- workspace ----
-  const int qpad = (q + 127) / 128 * 128;
+  // query tiles of 128; with the CTA-pair kernel enabled, an even number of them (the last may be all padding)
+  const int qpad = (h->opt_pair && q > 128) ? (q + 255) / 256 * 256 : (q + 127) / 128 * 128;
   CU_TRY(c->q32.ensure((size_t)q * h->dpad * 4));
   CU_TRY(c->qnorm.ensure((size_t)q * 4));
   CU_TRY(c->qsumsq.ensure((size_t)q * 4));

@@ -22,6 +22,7 @@ namespace {
 
 __global__ void eval_filter_kernel(const FilterProgram prog, const uint32_t* const* cols, int64_t n_slots,
                                    uint64_t* mask_words) {
+  griddep_wait();
   // one thread per slot; the 64 slots of a mask word are assembled with two ballots
   const int lane = threadIdx.x & 31;
   const int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll;
@@ -182,8 +183,7 @@ cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const*
                                uint64_t* mask_words, cudaStream_t st) {
   if (n_slots <= 0) return cudaSuccess;
   const int blocks = (int)std::min<int64_t>((n_slots + 255) / 256, 148 * 8);
-  eval_filter_kernel<<<blocks, 256, 0, st>>>(prog, d_cols, n_slots, mask_words);
-  return cudaGetLastError();
+  return launch_pdl(eval_filter_kernel, dim3(blocks), dim3(256), 0, st, prog, d_cols, n_slots, mask_words);
 }
 
 }  // namespace gfi

@@ -525,6 +525,7 @@ template <int MODE>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                  const GemmParams p) {
+  griddep_wait();
   gemm_topk_body<MODE, 1>(tmx, tmq, p);
 }
 
@@ -533,6 +534,7 @@ template <int MODE>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                       const GemmParams p) {
+  griddep_wait();
   gemm_topk_body<MODE, 2>(tmx, tmq, p);
 }
 
@@ -540,6 +542,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
 // Each lane keeps the kSeedR smallest of its strided share in registers (single pass), then the warp
 // pops the global minimum `rank` times.
 __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int qi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (qi >= p.q) return;
@@ -602,20 +605,19 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   const CUtensorMap* tx = reinterpret_cast<const CUtensorMap*>(tmap_x_host);
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
   const size_t sm1 = Geo<1>::kSmemBytes, sm2 = Geo<2>::kSmemBytes;
-  if (pair && p.seed_mode == 0) gemm_topk_pair_kernel<0><<<grid, kGemmThreads, sm2, st>>>(*tx, *tq, p);
-  else if (pair) gemm_topk_pair_kernel<3><<<grid, kGemmThreads, sm2, st>>>(*tx, *tq, p);
-  else if (p.seed_mode == 0) gemm_topk_kernel<0><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
-  else if (p.seed_mode == 1) gemm_topk_kernel<1><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
-  else if (p.seed_mode == 3) gemm_topk_kernel<3><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
-  else gemm_topk_kernel<2><<<grid, kGemmThreads, sm1, st>>>(*tx, *tq, p);
-  return cudaGetLastError();
+  const dim3 g(grid), b(kGemmThreads);
+  if (pair && p.seed_mode == 0) return launch_pdl(gemm_topk_pair_kernel<0>, g, b, sm2, st, *tx, *tq, p);
+  if (pair) return launch_pdl(gemm_topk_pair_kernel<3>, g, b, sm2, st, *tx, *tq, p);
+  if (p.seed_mode == 0) return launch_pdl(gemm_topk_kernel<0>, g, b, sm1, st, *tx, *tq, p);
+  if (p.seed_mode == 1) return launch_pdl(gemm_topk_kernel<1>, g, b, sm1, st, *tx, *tq, p);
+  if (p.seed_mode == 3) return launch_pdl(gemm_topk_kernel<3>, g, b, sm1, st, *tx, *tq, p);
+  return launch_pdl(gemm_topk_kernel<2>, g, b, sm1, st, *tx, *tq, p);
 }
 
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st) {
   if (p.q <= 0) return cudaSuccess;
   const int blocks = (p.q * 32 + 255) / 256;
-  seed_finalize_kernel<<<blocks, 256, 0, st>>>(p);
-  return cudaGetLastError();
+  return launch_pdl(seed_finalize_kernel, dim3(blocks), dim3(256), 0, st, p);
 }
 
 }  // namespace gfi

@@ -87,6 +87,7 @@ __global__ void row_stats_kernel(const IngestParams p) {
 // One warp per query: pad/copy, batch max|q|, reference-exact sum of squares and norm.  The query is
 // staged in shared memory so the sequential exact chain runs on pipelined shared loads.
 __global__ void prep_queries_kernel(const PrepQueriesParams p) {
+  griddep_wait();
   extern __shared__ float sq[];  // [warps per block][dpad] or unused when the query is too long
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qi = blockIdx.x * (blockDim.x >> 5) + warp;
@@ -98,23 +99,36 @@ __global__ void prep_queries_kernel(const PrepQueriesParams p) {
   for (int c = lane; c < p.dpad; c += 32) {
     const float v = c < p.d ? src[c] : 0.f;
     dst[c] = v;
-    if (mine) mine[c] = v;
+    if (mine) mine[c] = __fmul_rn(v, v);  // the squares, computed in parallel; only the additions are sequential
     m = fmaxf(m, fabsf(v));  // NaN is ignored by fmaxf; NaN queries surface as NaN distances later
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __syncwarp();
   if (lane == 0) {
-    if (p.qmaxabs) atomicMax(reinterpret_cast<unsigned int*>(p.qmaxabs), __float_as_uint(m));
-    const float* v = mine ? mine : src;
+    // batch max: most warps see a value that is already large enough and skip the (serialised) atomic
+    if (p.qmaxabs && __float_as_uint(m) > *reinterpret_cast<volatile unsigned int*>(p.qmaxabs))
+      atomicMax(reinterpret_cast<unsigned int*>(p.qmaxabs), __float_as_uint(m));
     float acc = -0.0f;
+    if (mine) {
+      // reference order (src/distance.rs: iterator sum from the first element): one dependent add per element,
+      // fed by 128-bit shared loads (dpad is a multiple of 4; the padding squares are +0 and d stops the walk)
+      int i = 0;
+      for (; i + 4 <= p.d; i += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(mine + i);
+        acc = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(acc, s4.x), s4.y), s4.z), s4.w);
+      }
+      for (; i < p.d; ++i) acc = __fadd_rn(acc, mine[i]);
+    } else {
 #pragma unroll 8
-    for (int i = 0; i < p.d; ++i) acc = __fadd_rn(acc, __fmul_rn(v[i], v[i]));
+      for (int i = 0; i < p.d; ++i) acc = __fadd_rn(acc, __fmul_rn(src[i], src[i]));
+    }
     p.qsumsq[qi] = acc;
     p.qnorm[qi] = __fsqrt_rn(acc);
   }
 }
 
 __global__ void convert_queries16_kernel(const PrepQueriesParams p) {
+  griddep_wait();
   const float qmax = *p.qmaxabs;
   float s = 1.f;
   if (qmax > 0.f && qmax <= 3.4028234664e38f)
@@ -207,12 +221,14 @@ cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st) {
     const int wpb = 4;
     const size_t smem = (size_t)wpb * p.dpad * 4;
     pp.use_smem = smem <= 48 * 1024 ? 1 : 0;
-    prep_queries_kernel<<<(p.q + wpb - 1) / wpb, wpb * 32, pp.use_smem ? smem : 0, st>>>(pp);
+    cudaError_t e = launch_pdl(prep_queries_kernel, dim3((p.q + wpb - 1) / wpb), dim3(wpb * 32), pp.use_smem ? smem : 0, st, pp);
+    if (e != cudaSuccess) return e;
   }
   if (p.q16) {
     const int64_t total = (int64_t)p.qpad * p.dpad16;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, 148 * 8);
-    convert_queries16_kernel<<<blocks, 256, 0, st>>>(p);
+    cudaError_t e = launch_pdl(convert_queries16_kernel, dim3(blocks), dim3(256), 0, st, p);
+    if (e != cudaSuccess) return e;
   }
   return cudaGetLastError();
 }

@@ -84,6 +84,7 @@ struct RowMeta {
 
 template <int METRIC, int QT, int LPR, bool SEG>
 __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+  griddep_wait();
   constexpr int G = 32 / LPR;              // rows processed concurrently by one warp (LPR lanes per row)
   constexpr bool FAST = (QT == 1) && !SEG;  // single query, whole rows per stage: query lives in registers
   constexpr int kQRegs = 8;                 // float4 per lane per row on the FAST path (dpad <= 256 * G)
@@ -362,8 +363,7 @@ cudaError_t launch_scan_metric(const ScanParams& p, int QT, int grid, size_t sme
       if (e != cudaSuccess) return e;                                                                     \
       attr_set[dev & 15] = true;                                                                          \
     }                                                                                                     \
-    kern<<<grid, kScanThreads, smem, st>>>(p);                                                            \
-    return cudaGetLastError();                                                                            \
+    return launch_pdl(kern, dim3(grid), dim3(kScanThreads), smem, st, p);                                 \
   }
   switch (QT) {
     GFI_SCAN_CASE(1)
@@ -386,6 +386,7 @@ cudaError_t launch_scan_shape(const ScanParams& p, int QT, int grid, size_t smem
 // Compacts the eligible (live and unmasked) slots into a list (unordered: keys carry the slot, so the
 // processing order is irrelevant to the result).  One warp-aggregated atomic per 32 slots.
 __global__ void compact_eligible_kernel(const IndexView iv, const MaskView mask, uint32_t* list, uint32_t* count) {
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; s0 < iv.n_slots;
        s0 += (int64_t)gridDim.x * blockDim.x) {
@@ -414,7 +415,7 @@ cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, u
                                     cudaStream_t st) {
   if (iv.n_slots == 0) return cudaSuccess;
   const int blocks = (int)std::min<int64_t>((iv.n_slots + 255) / 256, 148 * 8);
-  compact_eligible_kernel<<<blocks, 256, 0, st>>>(iv, mask, list, count);
+  return launch_pdl(compact_eligible_kernel, dim3(blocks), dim3(256), 0, st, iv, mask, list, count);
   return cudaGetLastError();
 }
 

@@ -79,6 +79,7 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
 
 // ---- K3a: per query, pick the KP best candidate keys (by approximate score) ----------------------
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
+  griddep_wait();
   extern __shared__ __align__(16) uint64_t s_dyn[];  // sel[KP] | keys[kSelCap] | (sorted-list path only) keys2[kSelCap]
   uint64_t* sel = s_dyn;
   uint64_t* keys = s_dyn + p.KP;
@@ -250,6 +251,7 @@ __device__ __forceinline__ void warp_bitonic_sort(uint64_t* arr, int N, int lane
 
 template <int METRIC>
 __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const SelectParams p) {
+  griddep_wait();
   __shared__ __align__(16) float s_tiles[kRrWarps][2 * kRrTile];
   __shared__ float s_q[kRrWarps][2][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -474,6 +476,7 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
 __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const uint32_t* counts, int G,
                                   int64_t q, int64_t kstride, const uint32_t* ks, uint64_t* out_ids,
                                   float* out_dist, uint32_t* out_counts, int64_t out_kstride) {
+  griddep_wait();
   const int lane = threadIdx.x & 31;
   const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (w >= q) return;
@@ -519,8 +522,7 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
   if (grid <= 0) return cudaSuccess;
   if (p.KP < 32 || p.KP > kMaxKP || (p.KP & (p.KP - 1))) return cudaErrorInvalidValue;
   const size_t sel_smem = ((size_t)p.KP + (size_t)kSelCap * (p.list_len > 0 ? 2 : 1)) * 8;
-  select_kernel<<<grid, kSelThreads, sel_smem, st>>>(p);
-  cudaError_t e = cudaGetLastError();
+  cudaError_t e = launch_pdl(select_kernel, dim3(grid), dim3(kSelThreads), sel_smem, st, p);
   if (e != cudaSuccess) return e;
   SelectParams pp = p;
   const int nq_max = p.nq_dev ? p.nq_max : p.nq;
@@ -529,12 +531,11 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
   const int64_t warps = (int64_t)nq_max * (pp.warp_per_candidate ? p.KP : p.KP / 32);
   const int blocks = (int)std::min<int64_t>((warps + kRrWarps - 1) / kRrWarps, 148 * 16);
   switch (p.iv.metric) {
-    case kMetricL2: rerank_finalize_kernel<kMetricL2><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
-    case kMetricCos: rerank_finalize_kernel<kMetricCos><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
-    case kMetricDot: rerank_finalize_kernel<kMetricDot><<<blocks, kRrWarps * 32, 0, st>>>(pp); break;
+    case kMetricL2: return launch_pdl(rerank_finalize_kernel<kMetricL2>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
+    case kMetricCos: return launch_pdl(rerank_finalize_kernel<kMetricCos>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
+    case kMetricDot: return launch_pdl(rerank_finalize_kernel<kMetricDot>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
     default: return cudaErrorInvalidValue;
   }
-  return cudaGetLastError();
 }
 
 cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t* counts, int G, int64_t q,
@@ -543,9 +544,8 @@ cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t*
   if (q <= 0) return cudaSuccess;
   if (G > 32) return cudaErrorInvalidValue;
   const int64_t blocks = (q * 32 + 255) / 256;
-  merge_topk_kernel<<<(unsigned)blocks, 256, 0, st>>>(ids, dist, counts, G, q, kstride, ks, out_ids, out_dist,
-                                                      out_counts, out_kstride);
-  return cudaGetLastError();
+  return launch_pdl(merge_topk_kernel, dim3((unsigned)blocks), dim3(256), 0, st, ids, dist, counts, G, q, kstride, ks,
+                    out_ids, out_dist, out_counts, out_kstride);
 }
 
 }  // namespace gfi
