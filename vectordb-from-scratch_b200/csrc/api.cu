@@ -720,15 +720,19 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const bool pair = h->opt_pair && ((qpad / 128) % 2 == 0) && main_grid >= 2;
   if (pair) main_grid &= ~1;
   const int units = pair ? main_grid / 2 : main_grid;  // candidate slices are per (query, unit, column half)
-  // candidate slots per slice: 4x the expected hits of a slice (+ slack), power of two
-  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits / std::max(2 * units, 1) + 8)));
-  const int64_t cand_stride = (int64_t)units * 2 * cap;  // per query
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
-  // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`
+  // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`; the
+  // sample is capped so that the per-(query, tile) seed lists stay below 64 MiB, and the expectation that results
+  // from the cap (hits_eff >= hits) is what sizes the candidate slices and picks the select path below
   int64_t seed_tiles = (int64_t)std::ceil((double)rank * (double)h->n_slots / (double)hits / 256.0);
-  seed_tiles = std::max<int64_t>(1, std::min<int64_t>(seed_tiles, std::min<int64_t>(num_n_tiles, 256)));
+  const int64_t seed_tiles_max = std::max<int64_t>(64, std::min<int64_t>(4096, (64ll << 20) / ((int64_t)q * 2 * kSeedR * 4)));
+  seed_tiles = std::max<int64_t>(1, std::min<int64_t>(seed_tiles, std::min<int64_t>(num_n_tiles, seed_tiles_max)));
   const int64_t seed_stride = std::max<int64_t>(1, num_n_tiles / seed_tiles);
+  const int hits_eff = (int)std::min<double>(1 << 20, std::max<double>(hits, (double)rank * (double)h->n_slots / ((double)seed_tiles * 256.0)));
+  // candidate slots per slice: 4x the expected hits of a slice (+ slack), power of two
+  const uint32_t cap = (uint32_t)std::min(4096, pow2_at_least(std::max(16, 4 * hits_eff / std::max(2 * units, 1) + 8)));
+  const int64_t cand_stride = (int64_t)units * 2 * cap;  // per query
   const int num_m_tiles = qpad / 128;
 
   CU_TRY(c->cand.ensure((size_t)q * cand_stride * 8));
@@ -740,7 +744,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->slice_cnt.ensure((size_t)units * 2 * q * 2));  // written in full by the main pass: no pre-fill
   // Usual case (expected candidates per query well below select_kernel's staging area): the select pass reads
   // only the valid prefix of every slice.  Large k: pre-fill with sentinels and let it scan the whole block.
-  const bool slice_gather = 3 * hits <= kSelectStageKeys;
+  const bool slice_gather = 3 * hits_eff <= kSelectStageKeys;
   if (!slice_gather) CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));
 
   CUtensorMap tmx, tmq, tmx_half;

@@ -552,15 +552,24 @@ __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
   float sd[kSeedR];
 #pragma unroll
   for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
-  for (int64_t i = lane; i < total; i += 32) {
-    const float v = s[i];
-    if (v < sd[kSeedR - 1]) {  // false for NaN
-      sd[kSeedR - 1] = v;
+  for (int64_t i0 = 0; i0 < total; i0 += 32 * 8) {  // 8 independent loads in flight per lane
+    float vv[8];
 #pragma unroll
-      for (int j = kSeedR - 1; j > 0; --j) {
-        const float lo = fminf(sd[j - 1], sd[j]), hi = fmaxf(sd[j - 1], sd[j]);
-        sd[j - 1] = lo;
-        sd[j] = hi;
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + 32 * u + lane;
+      vv[u] = i < total ? __ldg(s + i) : kInf;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float v = vv[u];
+      if (v < sd[kSeedR - 1]) {  // false for NaN
+        sd[kSeedR - 1] = v;
+#pragma unroll
+        for (int j = kSeedR - 1; j > 0; --j) {
+          const float lo = fminf(sd[j - 1], sd[j]), hi = fmaxf(sd[j - 1], sd[j]);
+          sd[j - 1] = lo;
+          sd[j] = hi;
+        }
       }
     }
   }

@@ -96,11 +96,22 @@ __global__ void prep_queries_kernel(const PrepQueriesParams p) {
   float* dst = p.q32 + (size_t)qi * p.dpad;
   float* mine = p.use_smem ? sq + (size_t)warp * p.dpad : nullptr;
   float m = 0.f;
-  for (int c = lane; c < p.dpad; c += 32) {
-    const float v = c < p.d ? src[c] : 0.f;
-    dst[c] = v;
-    if (mine) mine[c] = __fmul_rn(v, v);  // the squares, computed in parallel; only the additions are sequential
-    m = fmaxf(m, fabsf(v));  // NaN is ignored by fmaxf; NaN queries surface as NaN distances later
+  for (int c0 = 0; c0 < p.dpad; c0 += 32 * 8) {  // 8 independent loads in flight per lane
+    float v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 32 * u + lane;
+      v[u] = c < p.d ? __ldg(src + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int c = c0 + 32 * u + lane;
+      if (c < p.dpad) {
+        dst[c] = v[u];
+        if (mine) mine[c] = __fmul_rn(v[u], v[u]);  // squares in parallel; only the additions are sequential
+      }
+      m = fmaxf(m, fabsf(v[u]));  // NaN is ignored by fmaxf; NaN queries surface as NaN distances later
+    }
   }
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   __syncwarp();
