@@ -261,12 +261,12 @@ def main():
         # the step's inputs live in pinned host memory (numpy view of a pinned torch tensor)
         queries_pin = torch.from_numpy(queries_h).pin_memory()
         queries_h = queries_pin.numpy()
-        for _ in range(2):
+        for _ in range(3):
             idx.search_arrays(queries_h, ks_h, mask=mask_h)
         barrier()
         st_e0 = idx.stats()
         t0 = time.perf_counter()
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(3, min(args.steps, 50))
         for _ in range(e2e_steps):
             ids_h, dist_h, cnt_h = idx.search_arrays(queries_h, ks_h, mask=mask_h)
         t_e2e = (time.perf_counter() - t0) / e2e_steps
@@ -276,7 +276,7 @@ def main():
         # sharded end to end: H2D of the replicated queries, local search, all-gather, merge, D2H on rank 0
         qpin = torch.from_numpy(queries_h).pin_memory()
         res_pin = torch.zeros((q, k), dtype=torch.int64).pin_memory()
-        e2e_steps = max(3, min(args.steps, 10))
+        e2e_steps = max(3, min(args.steps, 50))
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):

@@ -4,5 +4,3 @@ python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/plain_rr.log 2>&
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:rerank_finalize -s 2 -c 1 \
     -o gpurun_out/prof_rerank_c2 -f python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/ncu_rr.log 2>&1
 echo "ncu rerank exit $?"
-bash scripts/gpu_launches.sh c2
-python scripts/launch_summary.py gpurun_out/launches_c2.csv 2>&1 | grep -E "prep|seed_fin|select|rerank"

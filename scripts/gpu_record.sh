@@ -24,4 +24,17 @@ python scripts/prof_one.py --workload c3a --steps 2 > gpurun_out/plain_c3a.log 2
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 1 -c 1 \
     -o gpurun_out/prof_scan_c3a -f python scripts/prof_one.py --workload c3a --steps 2 > gpurun_out/ncu_c3a.log 2>&1
 echo "ncu scan c3a exit $?" >> $log
+python scripts/prof_one.py --workload c5 --rows 2000000 --steps 2 > gpurun_out/plain_c5.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_topk -s 3 -c 1 \
+    -o gpurun_out/prof_gemm_c5 -f python scripts/prof_one.py --workload c5 --rows 2000000 --steps 2 > gpurun_out/ncu_c5.log 2>&1
+echo "ncu gemm c5 exit $?" >> $log
+python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/plain_rr.log 2>&1 && \
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:rerank_finalize -s 2 -c 1 \
+    -o gpurun_out/prof_rerank_c2 -f python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/ncu_rr.log 2>&1
+echo "ncu rerank c2 exit $?" >> $log
+# in-kernel cycle / clock diagnostics of the tensor pass (gemm_debug bit 5) with the epilogue, the loads and the
+# MMAs switched off in turn (bits 2, 0-1, 4): the evidence for DESIGN.md section 5's power-wall / TMEM-port notes
+python scripts/prof_one.py --workload c2 --steps 2 --debug-sweep > gpurun_out/clock_diag_c2.log 2>&1
+python scripts/prof_one.py --workload c2 --steps 2 --debug-sweep --opt pair=1 > gpurun_out/clock_diag_c2_pair.log 2>&1
+python scripts/prof_one.py --workload c5 --rows 4000000 --steps 2 --debug-sweep > gpurun_out/clock_diag_c5_4Mrows.log 2>&1
 grep -E "passed|failed|exit" $log | tail -30

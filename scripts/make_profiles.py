@@ -111,7 +111,20 @@ if traffic:
     print("wrote traffic", traffic)
 
 for rep, out in (("prof_gemm_c2.ncu-rep", f"{tag}_ncu_gemm_topk_c2.txt"), ("prof_scan_c3a.ncu-rep", f"{tag}_ncu_scan_topk_c3a.txt"),
-                 ("prof_gemm_c5.ncu-rep", f"{tag}_ncu_gemm_topk_c5_2Mrows.txt")):
+                 ("prof_gemm_c5.ncu-rep", f"{tag}_ncu_gemm_topk_c5_2Mrows.txt"),
+                 ("prof_rerank_c2.ncu-rep", f"{tag}_ncu_rerank_c2.txt")):
     p = os.path.join(G, rep)
     if os.path.exists(p):
         summarise(p, os.path.join(P, out))
+
+# in-kernel cycle / clock diagnostics (scripts/gpu_record.sh)
+for name in ("clock_diag_c2.log", "clock_diag_c2_pair.log", "clock_diag_c5_4Mrows.log"):
+    src = os.path.join(G, name)
+    if os.path.exists(src):
+        keep = [l for l in open(src) if l.startswith("{") or ("[gemm_topk]" in l and "ns" in l)]
+        # the seed pass prints too (a few ten thousand cycles); keep the main pass lines only
+        keep = [l for l in keep if l.startswith("{") or int(l.split("cycles")[1].split()[0]) > 500000]
+        open(os.path.join(P, f"{tag}_{name}"), "w").writelines(
+            ["# gemm_debug bits: 32 = print cycles/ns of CTA 0; +4 no epilogue; +7 no loads after the ring fill, no epilogue; "
+             "+23 also no MMA issue (barrier handshakes only).  Results of debug runs are invalid by design.\n"] + keep)
+        print("wrote", name)
