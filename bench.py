@@ -181,9 +181,10 @@ def main():
     ks_h = np.full(q, k, dtype=np.uint32)
     dq = torch.from_numpy(queries_h).to(dev)
     dks = torch.from_numpy(ks_h.astype(np.int32)).to(dev)
-    out_ids = torch.zeros((q, k), dtype=torch.int64, device=dev)
-    out_d = torch.zeros((q, k), dtype=torch.float32, device=dev)
-    out_c = torch.zeros((q,), dtype=torch.int32, device=dev)
+    # one packed block [ids | dist | counts] per rank: the sharded exchange is a single all-gather
+    from vectordb_from_scratch_b200.sharded import packed_layout, packed_views
+    pack = torch.zeros((packed_layout(q, k)[2],), dtype=torch.uint8, device=dev)
+    out_ids, out_d, out_c = packed_views(pack, q, k)
     m_ids, m_d, m_c = torch.zeros_like(out_ids), torch.zeros_like(out_d), torch.zeros_like(out_c)
     # a real (non-legacy) stream: libgfi launches on the handle it is given and torch events time that stream
     tstream = torch.cuda.Stream(device=dev)
@@ -206,14 +207,15 @@ def main():
     def local_search(_q, _k):
         idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, out_ids.data_ptr(), out_d.data_ptr(),
                           out_c.data_ptr(), k, stream=stream, d_mask=d_mask_ptr, mask_bits=mask_bits)
-        return out_ids, out_d, out_c
+        return out_ids, out_d, out_c, pack
 
     def merge(all_ids, all_d, all_c, _k):
         idx.merge_topk_device(all_ids.data_ptr(), all_d.data_ptr(), all_c.data_ptr(), world, q, k, dks.data_ptr(),
-                              m_ids.data_ptr(), m_d.data_ptr(), m_c.data_ptr(), k, stream=stream)
+                              m_ids.data_ptr(), m_d.data_ptr(), m_c.data_ptr(), k, stream=stream,
+                              shard_stride_bytes=pack.numel())
         return m_ids, m_d, m_c
 
-    sharded = ShardedSearch(local_search, merge)
+    sharded = ShardedSearch(local_search, merge, packed=True)
 
     def barrier():
         if world > 1:

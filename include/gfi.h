@@ -158,6 +158,16 @@ int32_t gfi_merge_topk_device(const uint64_t *d_ids, const float *d_dist, const 
                               uint64_t *d_out_ids, float *d_out_dist, uint32_t *d_out_counts,
                               int64_t out_kstride, void *stream);
 
+/*
+ * Same merge over PACKED per-shard blocks: shard g's ids / distances / counts start at the given base pointers
+ * plus g * shard_stride_bytes (a multiple of 8).  A shard that lets gfi_search_device write its three outputs
+ * into one contiguous block [ids | dist | counts] needs a single all-gather of that block per search.
+ */
+int32_t gfi_merge_topk_device_strided(const uint64_t *d_ids, const float *d_dist, const uint32_t *d_counts,
+                                      int32_t G, int64_t q, int64_t kstride, int64_t shard_stride_bytes,
+                                      const uint32_t *d_ks, uint64_t *d_out_ids, float *d_out_dist,
+                                      uint32_t *d_out_counts, int64_t out_kstride, void *stream);
+
 /* DimensionMismatch payload of the last GFI_ERR_DIMENSION_MISMATCH on this thread. */
 void gfi_last_mismatch(int64_t *expected, int64_t *actual);
 /* Thread-local message for the last error on this thread ("" if none). */

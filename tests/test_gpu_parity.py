@@ -395,6 +395,21 @@ def test_device_search_and_merge_kernel():
         assert out_c[i].item() == k
         assert [int(x) for x in out_ids[i].cpu()] == [p[1] for p in ref_merge[i]] == [int(x) for x in exp[i][0]]
         assert np.array_equal(out_d[i].cpu().numpy(), exp[i][1])
+    # packed per-shard blocks [ids | dist | counts] (what ONE all-gather per search delivers) + strided merge
+    from vectordb_from_scratch_b200.sharded import packed_layout, packed_views
+    size = packed_layout(q, k)[2]
+    packed = torch.zeros((G, size), dtype=torch.uint8, device="cuda")
+    p_ids, p_d, p_c = packed_views(packed, q, k)
+    for g in range(G):
+        shards[g].search_device(dq.data_ptr(), q, dks.data_ptr(), k, p_ids[g].data_ptr(), p_d[g].data_ptr(),
+                                p_c[g].data_ptr(), k, stream=stream)
+        shards[g].search_status()
+    out2_ids, out2_d, out2_c = torch.zeros_like(out_ids), torch.zeros_like(out_d), torch.zeros_like(out_c)
+    shards[0].merge_topk_device(p_ids.data_ptr(), p_d.data_ptr(), p_c.data_ptr(), G, q, k, dks.data_ptr(),
+                                out2_ids.data_ptr(), out2_d.data_ptr(), out2_c.data_ptr(), k, stream=stream,
+                                shard_stride_bytes=size)
+    torch.cuda.synchronize()
+    assert torch.equal(out2_ids, out_ids) and torch.equal(out2_d, out_d) and torch.equal(out2_c, out_c)
 
 
 # ---------------------------------------------------------------- full-size checks (BASELINE.json configs)

@@ -47,8 +47,30 @@ def _worker(rank, world, port, ret):
 
     merged, _, _ = ShardedSearch(local_search, merge).search(torch.from_numpy(queries), ks)
     exp = oracle.search_batch("euclidean", rows, queries, ks)
-    ok = all([p[1] for p in merged[i]] == [int(x) for x in exp[i][0]] and
-             np.array_equal(np.array([p[0] for p in merged[i]], np.float32), exp[i][1]) for i in range(q))
+
+    def matches(m):
+        return all([p[1] for p in m[i]] == [int(x) for x in exp[i][0]] and
+                   np.array_equal(np.array([p[0] for p in m[i]], np.float32), exp[i][1]) for i in range(q))
+
+    ok = matches(merged)
+
+    # packed exchange: the three outputs are views of one byte block, ONE all-gather, strided views into the merge
+    from vectordb_from_scratch_b200.sharded import packed_layout, packed_views
+
+    def local_search_packed(qs, kk):
+        ids, dd, cnt = local_search(qs, kk)
+        pack = torch.zeros((packed_layout(q, k)[2],), dtype=torch.uint8)
+        pi, pd, pc = packed_views(pack, q, k)
+        pi.copy_(ids); pd.copy_(dd); pc.copy_(cnt)
+        return pi, pd, pc, pack
+
+    def merge_packed(all_ids, all_d, all_c, kk):
+        assert tuple(all_ids.shape) == (world, q, k) and tuple(all_c.shape) == (world, q)
+        assert all_ids.stride(0) * 8 == packed_layout(q, k)[2] == all_c.stride(0) * 4  # the shard stride
+        return numpy_merge(all_ids.numpy(), all_d.numpy(), all_c.numpy(), kk), None, None
+
+    merged2, _, _ = ShardedSearch(local_search_packed, merge_packed, packed=True).search(torch.from_numpy(queries), ks)
+    ok = ok and matches(merged2)
     ret[rank] = bool(ok)
     dist.destroy_process_group()
 

@@ -728,6 +728,12 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   int64_t seed_tiles = (int64_t)std::ceil((double)rank * (double)h->n_slots / (double)hits / 256.0);
   const int64_t seed_tiles_max = std::max<int64_t>(64, std::min<int64_t>(4096, (64ll << 20) / ((int64_t)q * 2 * kSeedR * 4)));
   seed_tiles = std::max<int64_t>(1, std::min<int64_t>(seed_tiles, std::min<int64_t>(num_n_tiles, seed_tiles_max)));
+  {
+    // whole waves: trim the sample (by at most 20%) so the seed pass does not end in a mostly idle round
+    const int64_t mt = qpad / 128, items = seed_tiles * mt, waves = (items + grid_sm - 1) / grid_sm;
+    const int64_t trimmed = (waves - 1) * grid_sm / mt;
+    if (waves > 1 && items % grid_sm != 0 && trimmed * 5 >= seed_tiles * 4) seed_tiles = trimmed;
+  }
   const int64_t seed_stride = std::max<int64_t>(1, num_n_tiles / seed_tiles);
   const int hits_eff = (int)std::min<double>(1 << 20, std::max<double>(hits, (double)rank * (double)h->n_slots / ((double)seed_tiles * 256.0)));
   // candidate slots per slice: 4x the expected hits of a slice (+ slack), power of two
@@ -1401,8 +1407,18 @@ int32_t gfi_search_status(gfi_index* h) {
 int32_t gfi_merge_topk_device(const uint64_t* d_ids, const float* d_dist, const uint32_t* d_counts, int32_t G,
                               int64_t q, int64_t kstride, const uint32_t* d_ks, uint64_t* d_out_ids,
                               float* d_out_dist, uint32_t* d_out_counts, int64_t out_kstride, void* stream) {
-  CU_TRY(launch_merge(d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids, d_out_dist, d_out_counts,
+  CU_TRY(launch_merge(d_ids, d_dist, d_counts, G, q, kstride, 0, d_ks, d_out_ids, d_out_dist, d_out_counts,
                       out_kstride, (cudaStream_t)stream));
+  return GFI_OK;
+}
+
+int32_t gfi_merge_topk_device_strided(const uint64_t* d_ids, const float* d_dist, const uint32_t* d_counts,
+                                      int32_t G, int64_t q, int64_t kstride, int64_t shard_stride_bytes,
+                                      const uint32_t* d_ks, uint64_t* d_out_ids, float* d_out_dist,
+                                      uint32_t* d_out_counts, int64_t out_kstride, void* stream) {
+  if (shard_stride_bytes <= 0 || (shard_stride_bytes & 7)) return fail(GFI_ERR_INDEX, "shard stride must be a positive multiple of 8 bytes");
+  CU_TRY(launch_merge(d_ids, d_dist, d_counts, G, q, kstride, shard_stride_bytes, d_ks, d_out_ids, d_out_dist,
+                      d_out_counts, out_kstride, (cudaStream_t)stream));
   return GFI_OK;
 }
 

@@ -127,7 +127,7 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
 
 // ---- K5: merge of per-shard results ---------------------------------------------------
 cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t* counts, int G, int64_t q,
-                         int64_t kstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,
+                         int64_t kstride, int64_t gstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,
                          uint32_t* out_counts, int64_t out_kstride, cudaStream_t st);
 
 // ---- K2: tcgen05 GEMM + fused threshold filter ----------------------------------------

@@ -473,8 +473,10 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
 }
 
 // K5: one warp per query merges G sorted lists (lane g owns list g; G <= 32).
+// `gstride` = bytes between consecutive shards' blocks of each array (0: the arrays are dense [G][q][kstride]);
+// a non-zero stride lets all three arrays live in ONE packed per-shard block, i.e. one all-gather per search.
 __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const uint32_t* counts, int G,
-                                  int64_t q, int64_t kstride, const uint32_t* ks, uint64_t* out_ids,
+                                  int64_t q, int64_t kstride, int64_t gstride, const uint32_t* ks, uint64_t* out_ids,
                                   float* out_dist, uint32_t* out_counts, int64_t out_kstride) {
   griddep_wait();
   const int lane = threadIdx.x & 31;
@@ -485,9 +487,12 @@ __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const 
   const uint64_t* my_ids = nullptr;
   const float* my_dist = nullptr;
   if (lane < G) {
-    len = counts[(size_t)lane * q + w];
-    my_ids = ids + ((size_t)lane * q + w) * kstride;
-    my_dist = dist + ((size_t)lane * q + w) * kstride;
+    const size_t gi = gstride ? (size_t)lane * (size_t)(gstride / 8) : (size_t)lane * q * kstride;
+    const size_t gd = gstride ? (size_t)lane * (size_t)(gstride / 4) : (size_t)lane * q * kstride;
+    const size_t gc = gstride ? (size_t)lane * (size_t)(gstride / 4) : (size_t)lane * q;
+    len = counts[gc + w];
+    my_ids = ids + gi + (size_t)w * kstride;
+    my_dist = dist + gd + (size_t)w * kstride;
   }
   uint32_t produced = 0;
   while (produced < k) {
@@ -539,13 +544,13 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
 }
 
 cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t* counts, int G, int64_t q,
-                         int64_t kstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,
+                         int64_t kstride, int64_t gstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,
                          uint32_t* out_counts, int64_t out_kstride, cudaStream_t st) {
   if (q <= 0) return cudaSuccess;
-  if (G > 32) return cudaErrorInvalidValue;
+  if (G > 32 || gstride < 0 || (gstride & 7)) return cudaErrorInvalidValue;
   const int64_t blocks = (q * 32 + 255) / 256;
-  return launch_pdl(merge_topk_kernel, dim3((unsigned)blocks), dim3(256), 0, st, ids, dist, counts, G, q, kstride, ks,
-                    out_ids, out_dist, out_counts, out_kstride);
+  return launch_pdl(merge_topk_kernel, dim3((unsigned)blocks), dim3(256), 0, st, ids, dist, counts, G, q, kstride, gstride,
+                    ks, out_ids, out_dist, out_counts, out_kstride);
 }
 
 }  // namespace gfi

@@ -203,9 +203,14 @@ class GpuFlatIndex:
         self._chk(self._L.gfi_search_status(self._h))
 
     def merge_topk_device(self, d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids, d_out_dist, d_out_counts,
-                          out_kstride, stream=0):
-        self._chk(self._L.gfi_merge_topk_device(d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids,
-                                                d_out_dist, d_out_counts, out_kstride, stream or None))
+                          out_kstride, stream=0, shard_stride_bytes=0):
+        if shard_stride_bytes:
+            self._chk(self._L.gfi_merge_topk_device_strided(d_ids, d_dist, d_counts, G, q, kstride,
+                                                            shard_stride_bytes, d_ks, d_out_ids, d_out_dist,
+                                                            d_out_counts, out_kstride, stream or None))
+        else:
+            self._chk(self._L.gfi_merge_topk_device(d_ids, d_dist, d_counts, G, q, kstride, d_ks, d_out_ids,
+                                                    d_out_dist, d_out_counts, out_kstride, stream or None))
 
     # -- maintenance / introspection --
     def flush(self):
