@@ -345,7 +345,8 @@ def main():
         "e2e": {"value": e2e_qps, "unit": "queries/s", "h2d_bytes_per_step": int(q * d * 4 + q * 4 + (mask_bits + 7) // 8),
                 "d2h_bytes_per_step": int(q * k * 12 + q * 4 + 16), "ms_per_step": t_e2e * 1e3,
                 "dominant_kernel_ms": e2e_kernel_ms},
-        "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+        # libgfi counts its own launches per search; the sharded path adds one merge kernel per step
+        "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]) + (args.steps if world > 1 else 0),
         "roofline": roof, "cpu_baseline": cpu, "clocks": sampler.summary(),
         "scanned_gbs_fp32_equiv": n * world * d * 4 / (ms_per_step * 1e-3) / 1e9,
         "value_definition": "world * batch / step time: each rank scores the batch against its own shard (weak scaling)",

@@ -63,7 +63,7 @@ if os.path.exists(rec):
             out.append(line.rstrip()[:6000])
     open(os.path.join(P, f"{tag}_bench_lines_1gpu.log"), "w").write("\n".join(out) + "\n")
     print("wrote bench lines")
-for name in ("bench_2gpu.log",):
+for name in ("bench_2gpu.log", "bench_8gpu.log"):
     p = os.path.join(G, name)
     if os.path.exists(p):
         keep = [l for l in open(p) if l.startswith("{")]
