@@ -307,7 +307,8 @@ def main():
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": ncu_traffic(wl), "kernel": "gemm_topk_kernel (main pass)", "kernel_ms": kern_ms,
                 "peak_source": f"{pk_kind} MEASURED_PEAKS.json bf16 " + ("sustained" if long_step else "burst"),
-                "hbm_gbs_scanned": hbm_gbs}
+                "hbm_gbs_scanned": hbm_gbs,
+                "frac_of_sustained_peak": achieved / pk["bf16_tflops_sustained"]}
         if (n * d * 2 / 1e9) / pk["hbm_gbs"] > (flops / 1e12) / peak:
             # low arithmetic intensity (few queries per row byte): the launch is bounded by HBM, not the tensor pipe
             roof.update({"bound": "hbm", "achieved": hbm_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
