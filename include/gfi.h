@@ -168,6 +168,18 @@ int32_t gfi_merge_topk_device_strided(const uint64_t *d_ids, const float *d_dist
                                       const uint32_t *d_ks, uint64_t *d_out_ids, float *d_out_dist,
                                       uint32_t *d_out_counts, int64_t out_kstride, void *stream);
 
+/*
+ * Exact distances of explicit (query, row id) pairs: DistanceMetric::distance (src/distance.rs:20-33), bit-identical
+ * to the reference, for m candidate ids per query (cand_ids [q][m], out_dist [q][m]).  This is what HNSW
+ * construction and search evaluate for their candidate lists (src/hnsw/graph.rs:221-232 `metric.distance(&node_vec,
+ * &n.vector)`, search_layer), batched onto the GPU copy of the rows.  out_status [q][m] (may be NULL): 0 ok; 1 the
+ * id is not in the index (the reference's `nodes.get(nid)` = None; distance = +inf); 2 cosine with a zero-norm
+ * operand (the reference's Err(InvalidVector); distance = +inf).  With out_status == NULL a status-2 pair makes the
+ * call return GFI_ERR_INVALID_VECTOR.  NaN distances are returned as NaN (distance() does not panic; sort_by does).
+ */
+int32_t gfi_distances(gfi_index *h, const float *queries, int64_t q, int64_t dim, const uint64_t *cand_ids,
+                      int64_t m, float *out_dist, uint8_t *out_status);
+
 /* DimensionMismatch payload of the last GFI_ERR_DIMENSION_MISMATCH on this thread. */
 void gfi_last_mismatch(int64_t *expected, int64_t *actual);
 /* Thread-local message for the last error on this thread ("" if none). */

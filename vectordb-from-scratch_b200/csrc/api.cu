@@ -9,6 +9,7 @@
 // (stream + workspace) from a pool so concurrent `&self` callers never share state.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <limits>
 #include <chrono>
 
 #include <algorithm>
@@ -1419,6 +1420,78 @@ int32_t gfi_merge_topk_device_strided(const uint64_t* d_ids, const float* d_dist
   if (shard_stride_bytes <= 0 || (shard_stride_bytes & 7)) return fail(GFI_ERR_INDEX, "shard stride must be a positive multiple of 8 bytes");
   CU_TRY(launch_merge(d_ids, d_dist, d_counts, G, q, kstride, shard_stride_bytes, d_ks, d_out_ids, d_out_dist,
                       d_out_counts, out_kstride, (cudaStream_t)stream));
+  return GFI_OK;
+}
+
+int32_t gfi_distances(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint64_t* cand_ids, int64_t m,
+                      float* out_dist, uint8_t* out_status) {
+  if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (q < 0 || m < 0 || (q > 0 && m > 0 && (!queries || !cand_ids || !out_dist))) return fail(GFI_ERR_INDEX, "bad arguments");
+  if (q == 0 || m == 0) return GFI_OK;
+  int32_t rc = ensure_flushed(h);
+  if (rc != GFI_OK) return rc;
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  bool empty;
+  if ((rc = precheck(h, dim, &empty)) != GFI_OK) return rc;
+  const float kInf = std::numeric_limits<float>::infinity();
+  if (empty) {  // nothing stored: every id is absent
+    for (int64_t i = 0; i < q * m; ++i) { out_dist[i] = kInf; if (out_status) out_status[i] = 1; }
+    return GFI_OK;
+  }
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  SearchCtx* c = acquire_ctx(h);
+  if (!c) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
+  struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
+  cudaStream_t st = c->stream;
+  const size_t nq = (size_t)q, np = (size_t)q * (size_t)m;
+  CU_TRY(c->q_in.ensure(nq * dim * 4));
+  CU_TRY(c->q32.ensure(nq * h->dpad * 4));
+  CU_TRY(c->qnorm.ensure(nq * 4));
+  CU_TRY(c->qsumsq.ensure(nq * 4));
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  CU_TRY(c->cand.ensure(np * 8));                 // candidate ids
+  CU_TRY(c->out_dist.ensure(np * 4));
+  CU_TRY(c->out_counts.ensure(np));               // status bytes
+  CU_TRY(c->h_dist.ensure(np * 4));
+  CU_TRY(c->h_counts.ensure(np));
+  CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, queries, nq * dim * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(c->cand.p, cand_ids, np * 8, cudaMemcpyHostToDevice, st));
+  Ctrl* ctrl = reinterpret_cast<Ctrl*>(c->ctrl.p);
+  PrepQueriesParams pq{};
+  pq.q_in = c->q_in.as<float>();
+  pq.q32 = c->q32.as<float>();
+  pq.q16 = nullptr;
+  pq.qnorm = c->qnorm.as<float>();
+  pq.qsumsq = c->qsumsq.as<float>();
+  pq.qmaxabs = reinterpret_cast<float*>(&ctrl->qmaxabs_bits);
+  pq.q = (int)q;
+  pq.qpad = (int)q;
+  pq.d = (int)h->dim;
+  pq.dpad = h->dpad;
+  pq.dpad16 = h->dpad16;
+  CU_TRY(launch_prep_queries(pq, st));
+  ScorePairsParams sp{};
+  sp.iv = h->view();
+  sp.q32 = c->q32.as<float>();
+  sp.qnorm = c->qnorm.as<float>();
+  sp.cand_ids = c->cand.as<uint64_t>();
+  sp.q = q;
+  sp.m = m;
+  sp.out_dist = c->out_dist.as<float>();
+  sp.out_status = c->out_counts.as<uint8_t>();
+  sp.flags = &ctrl->flags;
+  CU_TRY(launch_score_pairs(sp, st));
+  h->n_launch += 2;
+  CU_TRY(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, np * 4, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaMemcpyAsync(c->h_counts.p, c->out_counts.p, np, cudaMemcpyDeviceToHost, st));
+  CU_TRY(cudaStreamSynchronize(st));
+  memcpy(out_dist, c->h_dist.p, np * 4);
+  const uint8_t* hs = reinterpret_cast<const uint8_t*>(c->h_counts.p);
+  if (out_status) memcpy(out_status, hs, np);
+  else
+    for (size_t i = 0; i < np; ++i)  // no per-pair status wanted: the first error fails the call, as `?` would
+      if (hs[i] == 2) return fail(GFI_ERR_INVALID_VECTOR, "Cannot compute cosine distance with zero vector");
   return GFI_OK;
 }
 

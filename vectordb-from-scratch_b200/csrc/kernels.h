@@ -125,6 +125,18 @@ struct SelectParams {
 };
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st);
 
+// ---- K6: exact distances of explicit (query, row id) pairs (HNSW candidate evaluation) ------------
+struct ScorePairsParams {
+  IndexView iv;
+  const float* q32; const float* qnorm;   // prepared queries [q][dpad], reference-exact norms
+  const uint64_t* cand_ids;               // [q][m]
+  int64_t q, m;
+  float* out_dist;                        // [q][m]; +inf where status != 0
+  uint8_t* out_status;                    // [q][m]: 0 ok, 1 id not in the index, 2 zero-norm cosine operand
+  uint32_t* flags;
+};
+cudaError_t launch_score_pairs(const ScorePairsParams& p, cudaStream_t st);
+
 // ---- K5: merge of per-shard results ---------------------------------------------------
 cudaError_t launch_merge(const uint64_t* ids, const float* dist, const uint32_t* counts, int G, int64_t q,
                          int64_t kstride, int64_t gstride, const uint32_t* ks, uint64_t* out_ids, float* out_dist,

@@ -521,6 +521,82 @@ __global__ void merge_topk_kernel(const uint64_t* ids, const float* dist, const 
   if (lane == 0) out_counts[w] = produced;
 }
 
+// K6: exact distance of explicit (query, row id) pairs -- DistanceMetric::distance (src/distance.rs:20-33) as the
+// HNSW code calls it for candidate lists (src/hnsw/graph.rs:221-232, search_layer).  One warp per pair: lane 0 finds
+// the row by binary search over the id column (slot order == id order), the warp stages row and query chunks in
+// shared memory with coalesced loads and lane 0 walks them with the reference's sequential f32 chain.
+constexpr int kSpWarps = 4, kSpChunk = 1024;
+template <int METRIC>
+__global__ void __launch_bounds__(kSpWarps * 32) score_pairs_kernel(const ScorePairsParams p) {
+  griddep_wait();
+  __shared__ __align__(16) float s_x[kSpWarps][kSpChunk];
+  __shared__ __align__(16) float s_qv[kSpWarps][kSpChunk];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const IndexView& iv = p.iv;
+  const int64_t total = p.q * p.m;
+  for (int64_t w = (int64_t)blockIdx.x * kSpWarps + wib; w < total; w += (int64_t)gridDim.x * kSpWarps) {
+    const int64_t qi = w / p.m;
+    int64_t slot = -1;
+    if (lane == 0) {
+      const uint64_t id = p.cand_ids[w];
+      int64_t lo = 0, hi = iv.n_slots;  // lower bound of id in the ascending id column
+      while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (iv.ids[mid] < id) lo = mid + 1; else hi = mid;
+      }
+      if (lo < iv.n_slots && iv.ids[lo] == id && ((iv.live[lo >> 5] >> (lo & 31)) & 1u)) slot = lo;
+    }
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (slot < 0) {
+      if (lane == 0) {
+        p.out_dist[w] = __int_as_float(0x7f800000);
+        p.out_status[w] = 1;
+      }
+      continue;
+    }
+    const float* xr = iv.x32 + (size_t)slot * iv.dpad;
+    const float* qr = p.q32 + (size_t)qi * iv.dpad;
+    float acc = -0.0f;
+    for (int c0 = 0; c0 < iv.d; c0 += kSpChunk) {
+      const int nf = min(kSpChunk, iv.dpad - c0);  // multiple of 4
+      for (int t = lane * 4; t < nf; t += 128) {
+        *reinterpret_cast<float4*>(&s_x[wib][t]) = __ldg(reinterpret_cast<const float4*>(xr + c0 + t));
+        *reinterpret_cast<float4*>(&s_qv[wib][t]) = __ldg(reinterpret_cast<const float4*>(qr + c0 + t));
+      }
+      __syncwarp();
+      if (lane == 0) {
+        const int lim = min(kSpChunk, iv.d - c0);
+#pragma unroll 8
+        for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, s_qv[wib][i], s_x[wib][i]);
+      }
+      __syncwarp();
+    }
+    if (lane == 0) {
+      float dist;
+      uint8_t status = 0;
+      if (METRIC == kMetricL2) {
+        dist = __fsqrt_rn(acc);
+      } else if (METRIC == kMetricDot) {
+        dist = -acc;
+      } else {
+        const float xn = iv.norm[slot], qn = p.qnorm[qi];
+        if (xn == 0.f || qn == 0.f) {
+          dist = __int_as_float(0x7f800000);
+          status = 2;
+        } else {
+          float sim = __fdiv_rn(acc, __fmul_rn(qn, xn));
+          if (sim < -1.0f) sim = -1.0f;
+          else if (sim > 1.0f) sim = 1.0f;
+          dist = __fsub_rn(1.0f, sim);
+        }
+      }
+      if (dist == 0.f) dist = 0.f;  // -0.0 -> +0.0, as everywhere in this library
+      p.out_dist[w] = dist;
+      p.out_status[w] = status;
+    }
+  }
+}
+
 }  // namespace
 
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st) {
@@ -539,6 +615,18 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
     case kMetricL2: return launch_pdl(rerank_finalize_kernel<kMetricL2>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
     case kMetricCos: return launch_pdl(rerank_finalize_kernel<kMetricCos>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
     case kMetricDot: return launch_pdl(rerank_finalize_kernel<kMetricDot>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_score_pairs(const ScorePairsParams& p, cudaStream_t st) {
+  const int64_t total = p.q * p.m;
+  if (total <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((total + kSpWarps - 1) / kSpWarps, 148 * 8);
+  switch (p.iv.metric) {
+    case kMetricL2: return launch_pdl(score_pairs_kernel<kMetricL2>, dim3(blocks), dim3(kSpWarps * 32), 0, st, p);
+    case kMetricCos: return launch_pdl(score_pairs_kernel<kMetricCos>, dim3(blocks), dim3(kSpWarps * 32), 0, st, p);
+    case kMetricDot: return launch_pdl(score_pairs_kernel<kMetricDot>, dim3(blocks), dim3(kSpWarps * 32), 0, st, p);
     default: return cudaErrorInvalidValue;
   }
 }

@@ -163,6 +163,21 @@ class GpuFlatIndex:
                                      mbits, out_ids.ctypes.data, out_dist.ctypes.data, cnt.ctypes.data, kmax))
         return out_ids, out_dist, cnt
 
+    def distances(self, queries, cand_ids):
+        """Exact DistanceMetric::distance (src/distance.rs:20-33) of explicit (query, row id) pairs: queries [q,d],
+        cand_ids [q,m] -> (dist [q,m] f32, status [q,m] u8: 0 ok, 1 id absent, 2 zero-norm cosine operand).  The
+        batched form of the candidate evaluation in the reference's HNSW (src/hnsw/graph.rs:221-232)."""
+        qs = np.ascontiguousarray(queries, dtype=np.float32)
+        ids = np.ascontiguousarray(cand_ids, dtype=np.uint64)
+        q, d = qs.shape
+        assert ids.ndim == 2 and ids.shape[0] == q
+        m = ids.shape[1]
+        out = np.full((q, m), np.inf, dtype=np.float32)
+        status = np.zeros((q, m), dtype=np.uint8)
+        self._chk(self._L.gfi_distances(self._h, qs.ctypes.data if qs.size else None, q, d,
+                                        ids.ctypes.data if ids.size else None, m, out.ctypes.data, status.ctypes.data))
+        return out, status
+
     def set_metadata(self, id, fields):
         """Replace the metadata of `id` (dict str -> str): VectorStore::insert_with_metadata's
         `self.metadata.insert(internal_id, metadata)` (src/storage.rs:169), kept as columns in HBM."""

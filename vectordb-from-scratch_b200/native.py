@@ -77,6 +77,7 @@ def lib():
         "gfi_search_device": (i32, [vp, vp, i64, vp, u32, vp, i64, vp, vp, vp, i64, vp]),
         "gfi_search_status": (i32, [vp]),
         "gfi_merge_topk_device": (i32, [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, i64, vp]),
+        "gfi_distances": (i32, [vp, vp, i64, i64, vp, i64, vp, vp]),
         "gfi_merge_topk_device_strided": (i32, [vp, vp, vp, i32, i64, i64, i64, vp, vp, vp, vp, i64, vp]),
         "gfi_get_stats": (i32, [vp, c.POINTER(GfiStats)]),
         "gfi_set_option": (i32, [vp, c.c_char_p, i64]),
