@@ -7,20 +7,23 @@
 // (src/storage.rs:302-310) over FlatIndex::search (src/flat_index.rs:52-65): each database
 // tile is read from HBM once and reused for every query of the batch.
 //
-// Structure (one persistent CTA per SM, 384 threads, warp-specialised):
+// Structure (one persistent CTA per SM, 384 threads, warp-specialised; one kernel instance per MODE):
 //   warp 0      TMA producer: 2-D tiled bulk loads (SWIZZLE_128B) of a 128x64 query block and a
 //               256x64 row block per k-step into a 4-stage shared-memory ring (mbarrier full/empty)
-//   warp 1      MMA issuer: one lane issues 4 x tcgen05.mma (M=128,N=256,K=16) per k-step into one
-//               of two 256-column TMEM accumulators; tcgen05.commit releases ring slots and
+//   warp 1      MMA issuer: one elected lane issues 4 x tcgen05.mma (M=128,N=256,K=16) per k-step into
+//               one of two 256-column TMEM accumulators; tcgen05.commit releases ring slots and
 //               publishes finished accumulators
-//   warp 2      coefficient stager: per row of the tile the epilogue pair (a, b) -- metric, per-row
-//               fp16 scale, tombstone and filter bit (b = +inf) -- loaded one item ahead and
-//               published through an mbarrier, so the epilogue never waits on global memory
-//   warps 4-11  epilogue, thread == (query, half of the tile's columns): tcgen05.ld 32 columns at
-//               a time, one FMA per value (score = acc * a[row] + b[row]), a min tree and ONE
-//               compare per 32 values against the query's threshold; the rare survivors are
-//               appended with plain stores to a slice of the candidate buffer that is private to
-//               this (query, CTA, half) -- no atomics.
+//   warps 2-3   coefficient stagers (coefficient epilogue only): per row of the tile the pair (a, b) --
+//               metric, per-row fp16 scale, tombstone and filter bit (b = +inf) -- loaded one item ahead
+//               and published through an mbarrier, so the epilogue never waits on global memory
+//   warps 4-11  epilogue, thread == (query, half of the tile's columns): two tcgen05.ld of 32 columns in
+//               flight; coefficient mode: one FMA per value (score = acc * a[row] + b[row]) and 3-input
+//               min trees; raw mode (cosine, rows stored normalised): 3-input max trees on the raw
+//               accumulators; ONE compare per 32 values against the query's threshold.  The rare
+//               survivors are appended with plain stores to a slice of the candidate buffer that is
+//               private to this (query, unit, half) -- no atomics; per-slice counts are published at the
+//               end of the kernel.
+// A CTA-pair instance (tcgen05.mma.cta_group::2, clusters of two CTAs) exists behind an option; see Geo<>.
 // The thresholds come from a seed pass of the same kernel over an evenly strided sample of
 // tiles (seed_mode = 1).  Scores are approximate (fp16 inputs); select_rerank.cu re-scores the
 // best candidates with the reference's exact arithmetic and certifies the result.
@@ -46,7 +49,9 @@ constexpr uint32_t kTmemCols = 512;
 // and a 32 KB row block per k-step.  CG == 2: a CTA pair (two SMs of one TPC) issues tcgen05.mma.cta_group::2,
 // M = 256: each CTA holds its own 128 queries and HALF of the row block (16 KB), the tensor cores fetch the other
 // half from the peer's shared memory.  Per SM that cuts the bytes taken in through the L2->SM port from 48 to
-// 32 KB per k-step -- the port (64 B/clk) is what bounds the CG == 1 kernel -- and leaves room for 6 ring stages.
+// 32 KB per k-step and leaves room for 6 ring stages.  Measured on B200: 96.5% tensor-pipe
+// utilisation per cycle without the epilogue (87.7% for CG == 1), but the board is power-limited and the SM clock
+// drops accordingly -- same wall time -- so the launcher uses CG == 2 only on request.
 template <int CG> struct Geo {
   static constexpr int kStages = CG == 2 ? 6 : 4;
   static constexpr int kBRows = BN / CG;               // rows of the row block held by one CTA
@@ -64,12 +69,9 @@ template <int CG> struct Geo {
                                      ((uint32_t)((BM * CG) >> 4) << 24);
 };
 
-// UMMA shared-memory descriptor for a K-major SWIZZLE_128B tile (rows of 128 bytes, 8-row groups
-// 1024 bytes apart): start>>4 | LBO(16B, unused)<<16 | SBO(1024B)<<32 | version 1<<46 | SW128 (2)<<61.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
-         (2ull << 61);
-}
+// UMMA shared-memory descriptors (K-major SWIZZLE_128B tiles: rows of 128 bytes, 8-row groups 1024 bytes apart) are
+// built in the MMA issuer: start>>4 | LBO(16 B, unused)<<16 in the low word, SBO(1024 B)>>4 | version 1<<14 |
+// SWIZZLE_128B (2)<<29 in the high word.
 
 __device__ __forceinline__ float pow2_scale_inv(float maxabs) {
   // inverse of the power-of-two scale chosen in ingest.cu / convert_queries16_kernel
@@ -331,8 +333,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
 
-      // one lane polls, the warp follows: 32x fewer try_wait probes competing with the MMA / TMA warps' own
-      // barrier traffic (acquire by lane 0 + __syncwarp orders the other lanes' reads)
+      // (a warp-wide try_wait is one instruction: polling from a single lane + __syncwarp measured slower)
       if (MODE != 3) mbar_wait(&cfull[as], aph);
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
