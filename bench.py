@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--impl", default="gfi", choices=["gfi", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="name=value passed to gfi_set_option (experiments)")
     args = ap.parse_args()
     wl = args.workload
     metric, n, d, kind, seed, q, k = WORKLOADS[wl]
@@ -177,6 +178,9 @@ def main():
     first = rank * n  # weak scaling: rank r owns global rows/ids [r*n, (r+1)*n)
     idx.add_generated(seed, first, n, kind, first)
     idx.set_option("profile", 1)
+    for o in args.opt:
+        oname, oval = o.split("=")
+        idx.set_option(oname, int(oval))
     queries_h = synth.gen_rows(seed + 1, 0, q, d, kind)
     ks_h = np.full(q, k, dtype=np.uint32)
     dq = torch.from_numpy(queries_h).to(dev)
@@ -263,17 +267,18 @@ def main():
         # the step's inputs live in pinned host memory (numpy view of a pinned torch tensor)
         queries_pin = torch.from_numpy(queries_h).pin_memory()
         queries_h = queries_pin.numpy()
+        # the per-kernel event timing of the `value` leg is switched off here: it is not part of the user's call,
+        # and small batches are replayed from a CUDA graph only without it
+        idx.set_option("profile", 0)
         for _ in range(3):
             idx.search_arrays(queries_h, ks_h, mask=mask_h)
         barrier()
-        st_e0 = idx.stats()
         t0 = time.perf_counter()
         e2e_steps = max(3, min(args.steps, 50))
         for _ in range(e2e_steps):
             ids_h, dist_h, cnt_h = idx.search_arrays(queries_h, ks_h, mask=mask_h)
         t_e2e = (time.perf_counter() - t0) / e2e_steps
-        st_e1 = idx.stats()
-        e2e_kernel_ms = sum(st_e1[k2] - st_e0[k2] for k2 in ("tensor_kernel_ns", "scan_kernel_ns")) / e2e_steps / 1e6
+        e2e_kernel_ms = None
     else:
         # sharded end to end: H2D of the replicated queries, local search, all-gather, merge, D2H on rank 0
         qpin = torch.from_numpy(queries_h).pin_memory()

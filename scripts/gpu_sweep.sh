@@ -2,11 +2,10 @@
 mkdir -p gpurun_out
 log=gpurun_out/sweep.log
 : > $log
-run() { echo "=== $*" >> $log; timeout ${TMO:-300} "$@" >> $log 2>&1; echo "=== exit $?" >> $log; }
-TMO=400 run python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 120 -k "not full_size" -x
-TMO=120 run python scripts/prof_one.py --workload c2 --steps 5 --opt gemm_debug=32
-TMO=120 run python scripts/prof_one.py --workload c5 --rows 4000000 --steps 2 --opt gemm_debug=32
-TMO=120 run python scripts/prof_one.py --workload c3a --steps 5
-TMO=120 run python scripts/prof_one.py --workload c4 --steps 5
-TMO=120 run python scripts/prof_one.py --workload c1 --steps 50
-grep -E "^\{|exit [1-9]|passed|failed|rror|MHz" $log | grep -v "cycles [0-9]\{4,6\} " | cut -c1-300
+GFI_HOST_TRACE=1 timeout 200 python bench.py --steps 50 --warmup 3 --no-cpu-baseline >> $log 2>&1
+grep "gfi trace" $log | tail -6
+grep -E "^\{" $log | python -c "
+import sys, json
+for l in sys.stdin:
+    d = json.loads(l); print(d['config']['workload'][:40], 'step %.2f us  e2e %.2f us  kernel %.2f us' % (d['ms_per_step']*1e3, d['e2e']['ms_per_step']*1e3, d['roofline']['kernel_ms']*1e3))
+"

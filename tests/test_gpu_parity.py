@@ -360,6 +360,46 @@ def test_tensor_path_falls_back_when_not_certifiable():
     assert st["tensor_queries"] == 32 and st["fallback_queries"] > 0, st
 
 
+def test_repeated_small_searches_stay_exact_across_mutations():
+    """Back-to-back small host searches reuse a pooled search context (stream, device and pinned buffers): the
+    answers must track new query data, changes of k and batch shape, buffer growth by a large batch in between,
+    removals and masked searches."""
+    n, d = 5000, 96
+    rows = oracle.gen_rows(61, 0, n, d, 1)
+    idx = build("euclidean", rows)
+    live = np.ones(n, dtype=bool)
+    ids = np.arange(n, dtype=np.uint64)
+
+    def check(qseed, q, k, ctx):
+        queries = oracle.gen_rows(qseed, 0, q, d, 1)
+        got_ids, got_d, cnt = idx.search_arrays(queries, k)
+        exp = oracle.search_batch("euclidean", rows[live], queries, k, ids=ids[live], threads=4)
+        for i, (eids, ed) in enumerate(exp):
+            assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"{ctx} q{i}")
+
+    for rep in range(5):                      # same shape, different queries each time
+        check(700 + rep, 1, 10, f"rep{rep}")
+    check(710, 1, 5, "other k")
+    for rep in range(3):
+        check(720 + rep, 4, 10, f"q4 rep{rep}")
+    check(730, 300, 10, "tensor batch in between")   # grows the context's buffers
+    for rep in range(3):
+        check(740 + rep, 1, 10, f"after big rep{rep}")
+    for r in (17, 4000, 4999):
+        idx.remove(r)
+        live[r] = False
+    for rep in range(3):
+        check(750 + rep, 1, 10, f"after remove rep{rep}")
+    elig = np.zeros(n, dtype=bool)
+    elig[::7] = True
+    q1 = oracle.gen_rows(760, 0, 1, d, 1)
+    g_ids, g_d, g_c = idx.search_arrays(q1, 10, mask=elig)
+    e_ids, e_d = oracle.search_batch("euclidean", rows[live], q1, 10, ids=ids[live], eligible=elig[live])[0]
+    assert_topk_matches(g_ids[0, :g_c[0]], g_d[0, :g_c[0]], e_ids, e_d, ctx="masked")
+    for rep in range(3):
+        check(770 + rep, 1, 10, f"after mask rep{rep}")
+
+
 # ---------------------------------------------------------------- device-pointer API + merge kernel
 def test_device_search_and_merge_kernel():
     import torch
