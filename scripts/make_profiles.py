@@ -126,5 +126,6 @@ for name in ("clock_diag_c2.log", "clock_diag_c2_pair.log", "clock_diag_c5_4Mrow
         keep = [l for l in keep if l.startswith("{") or int(l.split("cycles")[1].split()[0]) > 500000]
         open(os.path.join(P, f"{tag}_{name}"), "w").writelines(
             ["# gemm_debug bits: 32 = print cycles/ns of CTA 0; +4 no epilogue; +7 no loads after the ring fill, no epilogue; "
-             "+23 also no MMA issue (barrier handshakes only).  Results of debug runs are invalid by design.\n"] + keep)
+             "+23 also no MMA issue (barrier handshakes only); +19 no loads, no MMA issue, epilogue ON (epilogue alone).  "
+             "Results of debug runs are invalid by design.\n"] + keep)
         print("wrote", name)

@@ -59,7 +59,7 @@ def timed(steps):
 
 if a.debug_sweep:
     idx.search_arrays(queries, ks)
-    for dbg in (32, 32 + 4, 32 + 7, 32 + 23):  # bit5: print cycles / clock of CTA 0
+    for dbg in (32, 32 + 4, 32 + 7, 32 + 23, 32 + 19):  # bit5: print cycles / clock of CTA 0; 51 = epilogue only
         idx.set_option("gemm_debug", dbg)
         try:
             r = timed(a.steps)
