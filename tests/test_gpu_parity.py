@@ -330,6 +330,54 @@ def test_tensor_path_cta_pair_kernel(metric):
     assert st["tensor_queries"] == q and st["fallback_queries"] <= q // 4, st
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot"])
+def test_tensor_path_rows_of_wildly_different_magnitude(metric):
+    """Row norms spread over 24 orders of magnitude (and a batch of queries with its own spread): the fp16 shadow
+    uses per-row scales (normalised rows for cosine), the certification bound is relative to the largest row, and
+    whatever cannot be certified must come back exact through the fallback."""
+    n, d, q, k = 12000, 96, 40, 10
+    rng = np.random.default_rng(11)
+    rows = oracle.gen_rows(131, 0, n, d, 1) * (10.0 ** rng.uniform(-12, 12, size=(n, 1))).astype(np.float32)
+    queries = oracle.gen_rows(132, 0, q, d, 1) * (10.0 ** rng.uniform(-6, 6, size=(q, 1))).astype(np.float32)
+    rows, queries = rows.astype(np.float32), queries.astype(np.float32)
+    idx = build(metric, rows)
+    check_batch(idx, metric, rows, queries, k, ctx=f"magnitudes {metric}")
+    assert idx.stats()["tensor_queries"] == q
+
+
+def test_tensor_path_error_semantics_in_a_batch():
+    """One bad query fails the whole batch, as the sequential batch loop's `collect::<Result<_>>` does
+    (src/storage.rs:302-310): a zero vector under cosine -> InvalidVector, a NaN element -> the NaN panic's status;
+    a NaN / zero ROW does the same for every query that reaches it."""
+    n, d, q = 9000, 64, 48
+    rows = oracle.gen_rows(141, 0, n, d, 1)
+    queries = oracle.gen_rows(142, 0, q, d, 1)
+    cos = build("cosine", rows)
+    bad = queries.copy()
+    bad[17] = 0.0
+    with pytest.raises(gfi.InvalidVector):
+        cos.search_arrays(bad, 10)
+    bad = queries.copy()
+    bad[5, 3] = np.nan
+    with pytest.raises(gfi.NaNDistance):
+        cos.search_arrays(bad, 10)
+    cos.search_arrays(queries, 10)                     # the index still answers clean batches
+    assert cos.stats()["tensor_queries"] >= q
+    l2 = build("euclidean", rows)
+    l2.add(n, np.full(d, np.nan, dtype=np.float32))    # a stored NaN row poisons every search (flat_index.rs:62)
+    with pytest.raises(gfi.NaNDistance):
+        l2.search_arrays(queries, 10)
+    l2.remove(n)
+    ids, dist, cnt = l2.search_arrays(queries, 10)
+    exp = oracle.search_batch("euclidean", rows, queries, 10, threads=4)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(ids[i, :cnt[i]], dist[i, :cnt[i]], eids, ed, ctx=f"after nan row q{i}")
+    cz = build("cosine", rows)
+    cz.add(n, np.zeros(d, dtype=np.float32))           # zero row under cosine: Err(InvalidVector) for every query
+    with pytest.raises(gfi.InvalidVector):
+        cz.search_arrays(queries, 10)
+
+
 def test_tensor_path_with_mask_and_tombstones():
     n, d, q, k = 20000, 256, 48, 10
     rows = oracle.gen_rows(31, 0, n, d, 1)
