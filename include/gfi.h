@@ -200,6 +200,8 @@ typedef struct gfi_stats {
   /* with option "profile"=1: CUDA-event time of the dominant kernel of each search, summed */
   int64_t scan_kernel_ns, scan_kernel_count;     /* K1 flat_scan_topk launches */
   int64_t tensor_kernel_ns, tensor_kernel_count; /* K2 flat_gemm_topk main-pass launches */
+  /* group commit of concurrent plain gfi_search calls (option "coalesce", default on) */
+  int64_t coalesced_batches, coalesced_requests; /* combined searches run, calls they served */
 } gfi_stats;
 int32_t gfi_get_stats(gfi_index *h, gfi_stats *out);
 

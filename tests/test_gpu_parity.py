@@ -560,6 +560,41 @@ def test_concurrent_searches_from_many_threads():
         assert_topk_matches(results[0][0][i], results[0][1][i], eids, ed, ctx=f"concurrent q{i}")
 
 
+def test_concurrent_single_queries_are_coalesced_and_isolated():
+    """Group commit (N1 micro-batching inside the library): single-query calls from many threads are combined into
+    shared scans while another search is running; every caller gets exactly its own answer -- or its own error."""
+    import threading
+    n, d, k, T, per = 150000, 64, 10, 24, 12
+    rows = oracle.gen_rows(151, 0, n, d, 1)
+    idx = build("cosine", rows)
+    queries = oracle.gen_rows(152, 0, T * per, d, 1)
+    queries[5 * per + 3] = 0.0                      # one caller's query is a zero vector: InvalidVector for IT only
+    got, errs = {}, {}
+
+    def worker(t):
+        for j in range(per):
+            i = t * per + j
+            try:
+                got[i] = idx.search(queries[i], k if i % 3 else 3)   # mixed k per call
+            except gfi.InvalidVector as e:
+                errs[i] = e
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert list(errs) == [5 * per + 3]
+    good = [i for i in range(T * per) if i != 5 * per + 3]
+    exp = oracle.search_batch("cosine", rows, queries[good], [k if i % 3 else 3 for i in good], threads=8)
+    for i, (eids, ed) in zip(good, exp):
+        assert_topk_matches([a for a, _ in got[i]], [b for _, b in got[i]], eids, ed, ctx=f"coalesced call {i}")
+    st = idx.stats()
+    assert st["coalesced_requests"] >= 2 * st["coalesced_batches"] > 0, st   # batches really formed
+    idx.set_option("coalesce", 0)
+    assert idx.search(queries[0], 3) == got[0]       # call 0 asked for k = 3
+
+
 def test_large_batch_is_chunked():
     """q above the tensor kernel's per-launch query limit (4096) is cut into chunks transparently."""
     n, d, q, k = 20000, 64, 4500, 5

@@ -39,7 +39,7 @@ class GfiStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "n_slots", "n_live", "searches", "queries", "scan_queries", "tensor_queries", "fallback_queries",
         "kernel_launches", "bytes_fp32", "bytes_fp16", "scan_kernel_ns", "scan_kernel_count",
-        "tensor_kernel_ns", "tensor_kernel_count")]
+        "tensor_kernel_ns", "tensor_kernel_count", "coalesced_batches", "coalesced_requests")]
 
 
 def lib():
