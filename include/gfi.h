@@ -113,6 +113,10 @@ int32_t gfi_compact(gfi_index *h);
  *              own post-filter, src/storage.rs:249-290, needs no mask: the caller over-fetches).
  *   out_ids / out_dist : q x kstride, out_counts[i] = min(ks[i], eligible rows)
  * The first failing query fails the batch (collect::<Result<_>>(), storage.rs:306-309).
+ * Any k is accepted without a mask (k beyond the kernels' list capacity of 1016 is served in exact passes);
+ * with a mask k is limited to 1016.  Thread-safe and re-entrant; calls that arrive while another plain search
+ * (no mask, q <= 256) is running are combined into one batched search (group commit, option "coalesce"), each
+ * caller receiving exactly the outcome -- results or error -- of its own call.
  */
 int32_t gfi_search(gfi_index *h, const float *queries, int64_t q, int64_t dim, const uint32_t *ks,
                    const uint64_t *mask, int64_t mask_bits, uint64_t *out_ids, float *out_dist,

@@ -3,7 +3,5 @@ mkdir -p gpurun_out
 log=gpurun_out/sweep.log
 : > $log
 run() { echo "=== $*" >> $log; timeout ${TMO:-300} "$@" >> $log 2>&1; echo "=== exit $?" >> $log; }
-TMO=900 run python -m pytest tests -q -m gpu --timeout 600 -x
+TMO=600 run python -m pytest tests/test_gpu_parity.py -q -m gpu --timeout 300 -x -k "list_capacity or k1000 or per_query_k"
 grep -E "^\{|exit [1-9]|passed|failed|rror|assert" $log | cut -c1-420
-bash scripts/gpu_clients.sh > /dev/null 2>&1
-cat gpurun_out/clients_probe.log | cut -c1-330

@@ -739,10 +739,30 @@ def test_device_side_filter_matches_host_truth_table():
         store.index.search_filtered(queries, k, '{"op": "xor", "filters": []}')
 
 
-def test_k_above_list_capacity_is_a_loud_error():
-    rows = oracle.gen_rows(99, 0, 2000, 16, 0)
-    idx = build("euclidean", rows)
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot"])
+def test_k_above_the_kernels_list_capacity(metric):
+    """FlatIndex::search accepts any k (src/flat_index.rs:63).  Beyond 1016 the library answers in exact passes over
+    the rows not returned yet; the concatenation is the exact ascending top-k."""
+    n, d = 5000, 24
+    rows = oracle.gen_rows(99, 0, n, d, 1)
+    idx = build(metric, rows, ids=np.arange(n, dtype=np.uint64) * 5 + 3)   # sparse ids: the passes mask by slot
+    ids = np.arange(n, dtype=np.uint64) * 5 + 3
+    queries = oracle.gen_rows(100, 0, 4, d, 1)
+    ks = [1500, 10, 2500, 1017]                      # mixed batch: small and large k together
+    got_ids, got_d, cnt = idx.search_arrays(queries, np.array(ks, dtype=np.uint32))
+    exp = oracle.search_batch(metric, rows, queries, ks, ids=ids)
+    for i, (eids, ed) in enumerate(exp):
+        assert cnt[i] == ks[i]
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"big k q{i}")
+    # k larger than the index: everything, once, in order
+    idx.remove(int(ids[7]))
+    g2, d2, c2 = idx.search_arrays(queries[:1], 9000)
+    live = np.ones(n, dtype=bool)
+    live[7] = False
+    eids, ed = oracle.search_batch(metric, rows[live], queries[:1], 9000, ids=ids[live])[0]
+    assert c2[0] == n - 1
+    assert_topk_matches(g2[0, :c2[0]], d2[0, :c2[0]], eids, ed, ctx="k > n")
+    # with a caller mask the capacity still applies, loudly
     with pytest.raises(gfi.IndexError_) as e:
-        idx.search(rows[0], 1500)
+        idx.search_arrays(queries[:1], 1500, mask=np.ones(int(ids[-1]) + 1, dtype=bool))
     assert "k too large" in str(e.value)
-    assert len(idx.search(rows[0], 1016)) == 1016

@@ -36,6 +36,7 @@ namespace {
 
 thread_local std::string tl_error;
 thread_local int64_t tl_expected = 0, tl_actual = 0;
+thread_local bool tl_mask_by_slot = false;  // search_impl: the host mask passed in is indexed by slot (big-k passes)
 
 int32_t fail(int32_t code, const std::string& msg) {
   tl_error = msg;
@@ -204,6 +205,7 @@ struct gfi_index {
   int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
                              // gain -- the pass is power-limited either way -- so off by default
   int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
+  std::atomic<uint64_t> layout_gen{0};  // bumped whenever rows change slots (compaction)
   int opt_profile = 0;
   // Group commit of concurrent plain searches (micro-batching of concurrent Index::search
   // calls).  While one batch runs, arriving calls queue up; the next leader takes everything queued as ONE batch
@@ -1288,7 +1290,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
                (mask || filter_json) ? c->mask.as<uint64_t>() : nullptr, mask_bits,
                reinterpret_cast<uint64_t*>(blk + off_ids), reinterpret_cast<float*>(blk + off_dist),
                reinterpret_cast<uint32_t*>(blk + off_cnt), (int64_t)kout};
-  a.mask_by_slot = filter_json != nullptr;
+  a.mask_by_slot = filter_json != nullptr || tl_mask_by_slot;
   rc = enqueue_search(h, c, a, st);
   c->ctrl_dev = nullptr;
   if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
@@ -1312,6 +1314,83 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   if (host_trace)
     fprintf(stderr, "[gfi trace] q=%lld enqueue %.1f us, wait %.1f us, unpack %.1f us\n", (long long)q, t_enq - t_begin,
             t_sync - t_enq, now_us() - t_sync);
+  return GFI_OK;
+}
+
+// k beyond the kernels' list capacity (FlatIndex::search accepts any k, src/flat_index.rs:63).  Queries with
+// k <= kMaxListK run as one ordinary batch; each larger one is answered in passes of kMaxListK results: a pass is an
+// exact search over the rows not returned yet (slot-indexed eligibility mask), so the concatenation of the passes
+// is the exact ascending top-k.  ceil(k / kMaxListK) scans per such query -- the rare path, kept simple.
+constexpr uint32_t kMaxListK = 1016;
+static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                            uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
+  if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
+  std::vector<int64_t> small, big;
+  for (int64_t i = 0; i < q; ++i) {
+    if ((int64_t)ks[i] > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
+    (ks[i] > kMaxListK ? big : small).push_back(i);
+  }
+  int32_t rc;
+  if (!small.empty()) {
+    uint32_t km = 1;
+    for (int64_t i : small) km = std::max(km, ks[i]);
+    std::vector<float> qs(small.size() * (size_t)dim);
+    std::vector<uint32_t> k2(small.size()), cnt(small.size());
+    std::vector<uint64_t> ids(small.size() * (size_t)km);
+    std::vector<float> dist(small.size() * (size_t)km);
+    for (size_t j = 0; j < small.size(); ++j) {
+      memcpy(qs.data() + j * dim, queries + small[j] * dim, (size_t)dim * 4);
+      k2[j] = ks[small[j]];
+    }
+    rc = search_impl(h, qs.data(), (int64_t)small.size(), dim, k2.data(), nullptr, 0, nullptr, ids.data(), dist.data(),
+                     cnt.data(), km);
+    if (rc != GFI_OK) return rc;
+    for (size_t j = 0; j < small.size(); ++j) {
+      const int64_t i = small[j];
+      out_counts[i] = cnt[j];
+      memcpy(out_ids + i * kstride, ids.data() + j * km, (size_t)cnt[j] * 8);
+      memcpy(out_dist + i * kstride, dist.data() + j * km, (size_t)cnt[j] * 4);
+    }
+  }
+  std::vector<uint64_t> tmp_ids(kMaxListK);
+  std::vector<float> tmp_dist(kMaxListK);
+  for (int64_t i : big) {
+    for (int attempt = 0;; ++attempt) {
+      if ((rc = ensure_flushed(h)) != GFI_OK) return rc;
+      const uint64_t gen = h->layout_gen.load();
+      int64_t n_slots;
+      {
+        std::shared_lock<std::shared_mutex> g(h->mu);
+        n_slots = h->n_slots;
+      }
+      std::vector<uint64_t> mask((size_t)(n_slots + 63) / 64 + 1, ~0ull);
+      uint32_t got = 0;
+      bool stale = false;
+      while (got < ks[i]) {
+        const uint32_t kp = std::min<uint32_t>(kMaxListK, ks[i] - got);
+        uint32_t cnt = 0;
+        tl_mask_by_slot = n_slots > 0;
+        rc = search_impl(h, queries + i * dim, 1, dim, &kp, n_slots > 0 ? mask.data() : nullptr, n_slots, nullptr,
+                         tmp_ids.data(), tmp_dist.data(), &cnt, kMaxListK);
+        tl_mask_by_slot = false;
+        if (rc != GFI_OK) return rc;
+        {
+          std::shared_lock<std::shared_mutex> g(h->mu);
+          if (h->layout_gen.load() != gen) { stale = true; break; }  // rows moved (compaction): start over
+          for (uint32_t j = 0; j < cnt; ++j) {
+            uint32_t slot;
+            if (lookup_slot(h, tmp_ids[j], &slot) && (int64_t)slot < n_slots) mask[slot >> 6] &= ~(1ull << (slot & 63));
+          }
+        }
+        memcpy(out_ids + i * kstride + got, tmp_ids.data(), (size_t)cnt * 8);
+        memcpy(out_dist + i * kstride + got, tmp_dist.data(), (size_t)cnt * 4);
+        got += cnt;
+        if (cnt < kp) break;  // fewer rows than asked for: FlatIndex::search returns what exists
+      }
+      if (!stale) { out_counts[i] = got; break; }
+      if (attempt >= 3) return fail(GFI_ERR_INDEX, "index kept being compacted during a large-k search");
+    }
+  }
   return GFI_OK;
 }
 
@@ -1370,6 +1449,11 @@ static void run_coalesced(gfi_index* h, std::vector<gfi_index::CoReq*>& batch) {
 int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
                    const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
                    uint32_t* out_counts, int64_t kstride) {
+  if (h && !mask && q > 0 && ks) {
+    bool bigk = false;
+    for (int64_t i = 0; i < q; ++i) bigk = bigk || ks[i] > kMaxListK;
+    if (bigk) return search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride);
+  }
   // masked searches, large batches and malformed calls take the direct path
   // (indexes below 32 MB are launch-latency-bound: independent calls on separate streams overlap on the GPU and
   // beat a serialised batch -- measured 68-75k vs 53k q/s at 10k x 128 -- so only large ones are coalesced)
@@ -1715,6 +1799,7 @@ namespace {
 // Rebuilds the slot array: live rows only, ordered by internal id.  Caller holds the unique lock.
 int32_t compact_locked(gfi_index* h) {
   int32_t rc;
+  ++h->layout_gen;
   if ((rc = set_device(h)) != GFI_OK) return rc;
   if (h->n_slots == 0) { h->needs_reorder = false; return GFI_OK; }
   // permutation: runs are keyed by id0 and disjoint, so walking the map yields ids in order
