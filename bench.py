@@ -325,7 +325,8 @@ def main():
         nbytes = float(n_elig) * d * 4 + (n / 8 if wl in FILTER_PCT else 0)
         achieved = nbytes / (kern_ms * 1e-3) / 1e9
         roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(wl), "kernel": "scan_topk_kernel",
+                "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(wl + "_scan") or ncu_traffic(wl),
+                "kernel": "scan_topk_kernel",
                 "kernel_ms": kern_ms, "peak_source": f"{pk_kind} MEASURED_PEAKS.json hbm_gbs",
                 "full_scan_equiv_gbs": float(n) * d * 4 / (kern_ms * 1e-3) / 1e9, "eligible_rows": n_elig}
 

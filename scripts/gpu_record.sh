@@ -11,7 +11,8 @@ TMO=900 run python -m pytest tests -q -m gpu --timeout 800
 TMO=300 run python -c "import __graft_entry__ as g; g.smoke()"
 TMO=900 run python bench.py --steps 20 --warmup 3
 TMO=900 run python bench.py --impl reference --steps 2 --warmup 1
-for wl in c1 c3a c3b c4 c4f50 c4f1 c5; do TMO=900 run python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu-baseline; done
+for wl in c1 c3a c3b c4 c4f50 c4f1 c5; do TMO=900 run python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline; done
+for wl in c3a c4; do TMO=900 run python bench.py --workload $wl --steps 20 --warmup 3 --no-cpu-baseline --opt tensor_auto=0; done
 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/plain_bench.log 2>&1 && \
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/launches_bench_c2.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
@@ -20,9 +21,15 @@ python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/plain_c2.log 2>&
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_topk -s 3 -c 1 \
     -o gpurun_out/prof_gemm_c2 -f python scripts/prof_one.py --workload c2 --steps 2 > gpurun_out/ncu_c2.log 2>&1
 echo "ncu gemm c2 exit $?" >> $log
+# C3a (q = 1 on 10M x 768): the cost model routes it to the tensor pass over the fp16 rows; the fp32 scan kernel is
+# captured with that route switched off (it still serves filtered searches, small indexes and the fallback)
 python scripts/prof_one.py --workload c3a --steps 2 > gpurun_out/plain_c3a.log 2>&1 && \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_topk -s 3 -c 1 \
+    -o gpurun_out/prof_gemm_c3a -f python scripts/prof_one.py --workload c3a --steps 2 > gpurun_out/ncu_c3a.log 2>&1
+echo "ncu gemm c3a exit $?" >> $log
+python scripts/prof_one.py --workload c3a --steps 2 --opt tensor_auto=0 > gpurun_out/plain_c3a_scan.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_topk -s 1 -c 1 \
-    -o gpurun_out/prof_scan_c3a -f python scripts/prof_one.py --workload c3a --steps 2 > gpurun_out/ncu_c3a.log 2>&1
+    -o gpurun_out/prof_scan_c3a -f python scripts/prof_one.py --workload c3a --steps 2 --opt tensor_auto=0 > gpurun_out/ncu_c3a_scan.log 2>&1
 echo "ncu scan c3a exit $?" >> $log
 python scripts/prof_one.py --workload c5 --rows 2000000 --steps 2 > gpurun_out/plain_c5.log 2>&1 && \
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_topk -s 3 -c 1 \

@@ -102,7 +102,7 @@ def traffic_bytes(rep):
 
 
 traffic = {}
-for wl, rep in (("c2", "prof_gemm_c2.ncu-rep"), ("c3a", "prof_scan_c3a.ncu-rep")):
+for wl, rep in (("c2", "prof_gemm_c2.ncu-rep"), ("c3a", "prof_gemm_c3a.ncu-rep"), ("c3a_scan", "prof_scan_c3a.ncu-rep")):
     p = os.path.join(G, rep)
     if os.path.exists(p):
         traffic[wl] = {"bytes_per_launch": traffic_bytes(p), "source": f"profiles/{tag}_ncu_*: dram__bytes_read.sum + dram__bytes_write.sum, one launch"}
@@ -111,6 +111,7 @@ if traffic:
     print("wrote traffic", traffic)
 
 for rep, out in (("prof_gemm_c2.ncu-rep", f"{tag}_ncu_gemm_topk_c2.txt"), ("prof_scan_c3a.ncu-rep", f"{tag}_ncu_scan_topk_c3a.txt"),
+                 ("prof_gemm_c3a.ncu-rep", f"{tag}_ncu_gemm_topk_c3a.txt"),
                  ("prof_gemm_c5.ncu-rep", f"{tag}_ncu_gemm_topk_c5_2Mrows.txt"),
                  ("prof_rerank_c2.ncu-rep", f"{tag}_ncu_rerank_c2.txt")):
     p = os.path.join(G, rep)

@@ -691,7 +691,12 @@ def test_full_size_c3_c4_properties():
     qs = synth.gen_rows(55, 0, 64, d, 1)
     t_ids, t_d, t_c = idx.search_arrays(qs, k)            # batch 64: tcgen05 path (C3b)
     assert idx.stats()["tensor_queries"] == 64 and np.all(t_c == k) and np.all(np.diff(t_d, axis=1) >= 0)
-    s_ids, s_d, s_c = idx.search_arrays(qs[:2], k)        # single queries: scan path (C3a)
+    a_ids, a_d, a_c = idx.search_arrays(qs[:2], k)        # small batch on a large index: the cost model picks
+    st = idx.stats()                                      # the tensor path too (fp16 rows are half the bytes)
+    assert st["tensor_queries"] == 66 and st["scan_queries"] == 0, st
+    assert np.array_equal(a_ids, t_ids[:2]) and np.array_equal(a_d, t_d[:2])
+    idx.set_option("tensor_auto", 0)
+    s_ids, s_d, s_c = idx.search_arrays(qs[:2], k)        # forced onto the fp32 scan path (C3a as specified)
     assert idx.stats()["scan_queries"] == 2
     assert np.array_equal(s_ids, t_ids[:2]) and np.array_equal(s_d, t_d[:2])
 

@@ -108,6 +108,7 @@ struct SearchCtx {
   DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
   void* ctrl_dev = nullptr;  // control block of the search being enqueued (inside out_blk or `ctrl`)
   bool pending_status = false;  // device search issued, status not yet collected
+  int64_t auto_tensor_q = 0;     // queries of the search being enqueued that took the tensor path by the cost model
   // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
   struct EvPair { cudaEvent_t a, b; int kind; };
   std::vector<EvPair> evs;
@@ -204,6 +205,9 @@ struct gfi_index {
   int opt_seed_rank = 8;
   int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
                              // gain -- the pass is power-limited either way -- so off by default
+  int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
+  std::atomic<bool> auto_tensor_off{false};   // set when such searches keep falling back (uncertifiable data)
+  std::atomic<int64_t> auto_q{0}, auto_fb{0};
   int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
   std::atomic<uint64_t> layout_gen{0};  // bumped whenever rows change slots (compaction)
   int opt_profile = 0;
@@ -572,10 +576,25 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   if (a.mask_by_slot) iv.ids_identity = 1;  // only mask indexing looks at this flag
   MaskView mv{a.d_mask, a.mask_bits};
 
+  // Small batches on LARGE indexes also take the tensor path: both paths are then HBM-bound, and the fp16 shadow is
+  // half the bytes of the fp32 rows (measured, q = 1: 10M x 768 4.21 -> 2.40 ms, 10M x 384 2.20 -> 1.16 ms).  The
+  // cost model compares streaming times; the tensor path's fixed passes (seed, select, rerank) are ~0.25 ms.
+  // Unfiltered searches only (a selective mask makes the gather scan cheaper still), and only while the index's
+  // small-batch searches keep being certified (an uncertified query pays for both paths).
+  bool small_q_tensor = false;
+  if (h->opt_tensor_auto && !h->auto_tensor_off && q < h->opt_tensor_min_q && h->opt_tensor_min_q <= kGemmMaxQueries &&
+      a.d_mask == nullptr) {
+    const double rows = (double)h->n_slots;
+    const double scan_s = std::ceil(q / 4.0) * rows * h->dpad * 4.0 / 7.0e12;
+    const double tensor_s = rows * h->dpad16 * 2.0 / 6.5e12 + 0.25e-3;
+    small_q_tensor = tensor_s < 0.8 * scan_s;
+  }
   const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
                          !(h->metric == GFI_METRIC_COSINE && h->zero_rows_ever > 0) &&
-                         q >= h->opt_tensor_min_q && q <= kGemmMaxQueries && h->n_slots >= h->opt_tensor_min_rows &&
-                         a.kmax <= 256 && h->dpad16 >= 64 && get_encode_fn() != nullptr;
+                         (q >= h->opt_tensor_min_q || small_q_tensor) && q <= kGemmMaxQueries &&
+                         h->n_slots >= h->opt_tensor_min_rows && a.kmax <= 256 && h->dpad16 >= 64 &&
+                         get_encode_fn() != nullptr;
+  c->auto_tensor_q = (tensor_ok && q < h->opt_tensor_min_q) ? q : 0;
 
   // ---- workspace ----
   // query tiles of 128; with the CTA-pair kernel enabled, an even number of them (the last may be all padding)
@@ -1302,6 +1321,10 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   const char* hb = c->h_out.as<char>();
   const Ctrl* hc = reinterpret_cast<const Ctrl*>(hb);
   h->n_fallback_q += hc->uncertified;
+  if (c->auto_tensor_q > 0) {  // keep the cost-model route only while it pays: < 1/4 of its queries falling back
+    const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc->uncertified);
+    if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;
+  }
   if ((rc = flags_to_status(hc->flags)) != GFI_OK) return rc;
   const uint32_t* hcnt = reinterpret_cast<const uint32_t*>(hb + off_cnt);
   const float* hdist = reinterpret_cast<const float*>(hb + off_dist);
@@ -1784,6 +1807,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;
   else if (n == "pair") h->opt_pair = (int)value;
+  else if (n == "tensor_auto") { h->opt_tensor_auto = (int)value; h->auto_tensor_off = false; h->auto_q = 0; h->auto_fb = 0; }
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "coalesce") h->opt_coalesce = (int)value;
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
