@@ -566,6 +566,7 @@ struct SearchArgs {
   uint32_t* d_out_counts;
   int64_t kstride;
   bool mask_by_slot = false;  // the mask is indexed by slot (device-evaluated filter), not by internal id
+  int64_t mask_popcount = -1;  // eligible bits of a host mask when known (cost model), else -1
 };
 
 // Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
@@ -579,15 +580,22 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   // Small batches on LARGE indexes also take the tensor path: both paths are then HBM-bound, and the fp16 shadow is
   // half the bytes of the fp32 rows (measured, q = 1: 10M x 768 4.21 -> 2.40 ms, 10M x 384 2.20 -> 1.16 ms).  The
   // cost model compares streaming times; the tensor path's fixed passes (seed, select, rerank) are ~0.25 ms.
-  // Unfiltered searches only (a selective mask makes the gather scan cheaper still), and only while the index's
-  // small-batch searches keep being certified (an uncertified query pays for both paths).
+  // With a caller mask the scan gathers only the eligible rows (~4.7 TB/s of touched bytes) while the tensor pass
+  // still streams every fp16 row, so the comparison needs the mask's population (known for host masks; a
+  // device-evaluated filter keeps the scan).  Only while the index's small-batch searches keep being certified (an
+  // uncertified query pays for both paths).
   bool small_q_tensor = false;
   if (h->opt_tensor_auto && !h->auto_tensor_off && q < h->opt_tensor_min_q && h->opt_tensor_min_q <= kGemmMaxQueries &&
-      a.d_mask == nullptr) {
+      (a.d_mask == nullptr || a.mask_popcount >= 0)) {
+    // streaming rates and fixed costs as measured on B200: fp32 scan 7.2 TB/s + 0.05 ms,
+    // gather scan 4.7 TB/s of touched bytes + 0.15 ms, tensor pass over fp16 rows 7.0 TB/s + 0.12 ms
     const double rows = (double)h->n_slots;
-    const double scan_s = std::ceil(q / 4.0) * rows * h->dpad * 4.0 / 7.0e12;
-    const double tensor_s = rows * h->dpad16 * 2.0 / 6.5e12 + 0.25e-3;
-    small_q_tensor = tensor_s < 0.8 * scan_s;
+    const double passes = std::ceil(q / 4.0);
+    const double scan_s = a.d_mask == nullptr
+                              ? passes * (rows * h->dpad * 4.0 / 7.2e12 + 0.05e-3)
+                              : passes * ((double)std::min<int64_t>(a.mask_popcount, h->n_slots) * h->dpad * 4.0 / 4.7e12 + 0.15e-3);
+    const double tensor_s = rows * h->dpad16 * 2.0 / 7.0e12 + 0.12e-3;
+    small_q_tensor = tensor_s < 0.9 * scan_s;
   }
   const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
                          !(h->metric == GFI_METRIC_COSINE && h->zero_rows_ever > 0) &&
@@ -1310,6 +1318,14 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
                reinterpret_cast<uint64_t*>(blk + off_ids), reinterpret_cast<float*>(blk + off_dist),
                reinterpret_cast<uint32_t*>(blk + off_cnt), (int64_t)kout};
   a.mask_by_slot = filter_json != nullptr || tl_mask_by_slot;
+  if (mask && !tl_mask_by_slot && h->n_slots * (int64_t)h->dpad * 4 >= (1ll << 30)) {  // cost model input (large indexes)
+    // an estimate is enough: every 64th word of the mask (one word of every 8th cache line; a full pass over 10M
+    // bits costs more than the model saves)
+    int64_t pc = 0, seen = 0;
+    const size_t full = (size_t)(mask_bits / 64);
+    for (size_t w = 0; w < full; w += 64, ++seen) pc += __builtin_popcountll(mask[w]);
+    a.mask_popcount = seen ? (int64_t)((double)pc / (double)(seen * 64) * (double)mask_bits) : 0;
+  }
   rc = enqueue_search(h, c, a, st);
   c->ctrl_dev = nullptr;
   if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
