@@ -1642,6 +1642,10 @@ int32_t gfi_search_status(gfi_index* h) {
   prof_collect(h, c);
   const Ctrl* hc = c->h_ctrl.as<Ctrl>();
   h->n_fallback_q += hc->uncertified;
+  if (c->auto_tensor_q > 0) {  // same bookkeeping as the host path (the block describes the last search issued)
+    const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc->uncertified);
+    if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;
+  }
   return flags_to_status(hc->flags);
 }
 
