@@ -701,6 +701,27 @@ def test_full_size_c3_c4_properties():
     assert np.array_equal(s_ids, t_ids[:2]) and np.array_equal(s_d, t_d[:2])
 
 
+def test_full_size_cost_model_route_switches_off_on_uncertifiable_data():
+    """A 1.6 GB index whose top-k boundary is always an exact tie (64 copies of every vector): single queries first
+    take the tensor pass by the cost model, every one of them falls back to the exact scan, and after 32 such
+    queries the index stops using the route.  Answers are exact throughout."""
+    base_n, copies, d, k = 6250, 64, 1024, 10
+    base = oracle.gen_rows(171, 0, base_n, d, 1)
+    rows = np.tile(base, (copies, 1))                      # row i is base[i % base_n]
+    idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
+    idx.add_batch(np.arange(rows.shape[0], dtype=np.uint64), rows)
+    queries = oracle.gen_rows(172, 0, 48, d, 1)
+    exp = oracle.search_batch("euclidean", base, queries, 1)   # nearest distinct vector of every query
+    for i in range(48):
+        ids, dist, cnt = idx.search_arrays(queries[i:i + 1], k)
+        b = int(exp[i][0][0])
+        assert [int(x) for x in ids[0]] == [b + j * base_n for j in range(k)]      # ties: lower id first
+        assert np.all(dist[0] == exp[i][1][0])
+    st = idx.stats()
+    assert st["fallback_queries"] >= 32 and st["scan_queries"] >= 8, st            # route taken, then dropped
+    assert st["tensor_queries"] < 48, st
+
+
 # ---------------------------------------------------------------- device-side MetadataFilter evaluation (N2)
 def test_device_side_filter_matches_host_truth_table():
     """Filters in the reference's JSON form evaluated on the GPU (csrc/filter.cu) against the host truth
