@@ -269,6 +269,33 @@ def test_mask_pushdown_and_post_filter(sel):
         assert np.array_equal(np.array([x for _, x in got], np.float32), ed)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("metric,d", [("euclidean", 384), ("cosine", 100), ("dot", 768)])
+def test_gather_scan_merges_runs_of_adjacent_eligible_rows(metric, d):
+    """The gather scan copies a run of adjacent eligible slots as ONE bulk copy (scan.cu producer): runs of every
+    length from 1 to 70 (longer than a 32-entry chunk and than a stage), isolated rows, an all-eligible stretch and
+    tombstones cutting runs must give the oracle's answer bit for bit."""
+    n, k = 40000, 10
+    rows = oracle.gen_rows(16, 0, n, d, 1)
+    queries = oracle.gen_rows(17, 0, 3, d, 1)
+    elig = np.zeros(n, dtype=bool)
+    pos, run = 0, 1
+    while pos + run + 3 < n // 2:  # run lengths 1, 2, ..., 70, 1, 2, ... separated by gaps of 1-3
+        elig[pos:pos + run] = True
+        pos += run + 1 + (run % 3)
+        run = run % 70 + 1
+    elig[n // 2:n // 2 + 5000] = True  # one long stretch
+    elig[n // 2 + 6000::7] = True      # isolated rows
+    idx = build(metric, rows, flags=1)
+    check_batch(idx, metric, rows, queries, k, eligible=elig, mask=elig, ctx="runs")
+    removed = np.arange(3, n, 11)
+    for i in removed:
+        idx.remove(int(i))
+    elig2 = elig.copy()
+    elig2[removed] = False
+    check_batch(idx, metric, rows, queries, k, eligible=elig2, mask=elig, ctx="runs + tombstones")
+
+
 # ---------------------------------------------------------------- tensor (tcgen05) path vs oracle
 TENSOR_CASES = [  # metric, n, d, kind, q, k
     ("cosine", 20000, 768, 1, 64, 10),     # C2 scaled down
@@ -498,6 +525,51 @@ def test_device_search_and_merge_kernel():
                                 shard_stride_bytes=size)
     torch.cuda.synchronize()
     assert torch.equal(out2_ids, out_ids) and torch.equal(out2_d, out_d) and torch.equal(out2_c, out_c)
+
+
+def test_device_side_route_of_small_batches_with_a_device_mask():
+    """A mask that lives on the device has a population the host does not know: the choice between the gather scan
+    and the masked tensor pass is made on the device from the compaction's count (kernels.h RouteParams).  Both
+    outcomes must give the oracle's answer bit for bit, and the statistics must say which kernel answered."""
+    import torch
+    from vectordb_from_scratch_b200.index import pack_mask
+    n, d, q, k = 600_000, 384, 3, 10  # large enough for the tensor pass to be worth considering
+    rows = oracle.gen_rows(6, 0, n, d, 0)
+    queries = oracle.gen_rows(7, 0, q, d, 0)
+    idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
+    idx.add_generated(6, 0, n, 0, 0)
+    for i in (5, 77, 4097, n - 1):
+        idx.remove(i)
+    dq = torch.from_numpy(queries).cuda()
+    dks = torch.full((q,), k, dtype=torch.int32, device="cuda")
+    out_ids = torch.zeros((q, k), dtype=torch.int64, device="cuda")
+    out_d = torch.zeros((q, k), dtype=torch.float32, device="cuda")
+    out_c = torch.zeros((q,), dtype=torch.int32, device="cuda")
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    rng = np.random.default_rng(3)
+    # The previous mask's population predicts whether the tensor kernels are worth enqueuing at all, so a dense mask
+    # right after a sparse one is still answered by the scan once (a misprediction costs time, never correctness).
+    masks = {0.02: rng.random(n) < 0.02, 0.95: rng.random(n) < 0.95}
+    for sel, route in ((0.02, "scan"), (0.95, "scan"), (0.95, "tensor"), (0.02, "scan"), (0.02, "scan")):
+        elig = masks[sel]
+        words, bits = pack_mask(elig)
+        dmask = torch.from_numpy(words.view(np.int64)).cuda()
+        st0 = idx.stats()
+        idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, out_ids.data_ptr(), out_d.data_ptr(), out_c.data_ptr(),
+                          k, stream=ts.cuda_stream, d_mask=dmask.data_ptr(), mask_bits=bits)
+        idx.search_status()
+        torch.cuda.synchronize()
+        st1 = idx.stats()
+        live = elig.copy()
+        live[[5, 77, 4097, n - 1]] = False
+        exp = oracle.search_batch("euclidean", rows, queries, k, eligible=live, threads=8)
+        for i, (eids, ed) in enumerate(exp):
+            assert out_c[i].item() == k
+            assert_topk_matches(out_ids[i].cpu().numpy().astype(np.uint64), out_d[i].cpu().numpy(), eids, ed,
+                                ctx=f"route {route} q{i}")
+        dscan, dtensor = st1["scan_queries"] - st0["scan_queries"], st1["tensor_queries"] - st0["tensor_queries"]
+        assert (dscan, dtensor) == ((q, 0) if route == "scan" else (0, q)), (route, dscan, dtensor)
 
 
 # ---------------------------------------------------------------- full-size checks (BASELINE.json configs)

@@ -98,6 +98,11 @@ struct Ctrl {
   uint32_t fb_count;
   uint32_t uncertified;
   uint32_t qmaxabs_bits;
+  // device-side route of a small batch with a device-resident mask (kernels.h, RouteParams)
+  uint32_t skip_tensor;
+  uint32_t tensor_nq;
+  uint32_t routed_scan;
+  uint32_t elig_count;  // population of the mask + 1 when a gather scan or the route kernel saw it, else 0
 };
 
 struct SearchCtx {
@@ -206,6 +211,7 @@ struct gfi_index {
   int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
                              // gain -- the pass is power-limited either way -- so off by default
   int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
+  std::atomic<int64_t> last_mask_pop{-1};     // population of the last device-resident mask searched (route predictor)
   std::atomic<bool> auto_tensor_off{false};   // set when such searches keep falling back (uncertifiable data)
   std::atomic<int64_t> auto_q{0}, auto_fb{0};
   int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
@@ -580,22 +586,33 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   // Small batches on LARGE indexes also take the tensor path: both paths are then HBM-bound, and the fp16 shadow is
   // half the bytes of the fp32 rows (measured, q = 1: 10M x 768 4.21 -> 2.40 ms, 10M x 384 2.20 -> 1.16 ms).  The
   // cost model compares streaming times; the tensor path's fixed passes (seed, select, rerank) are ~0.25 ms.
-  // With a caller mask the scan gathers only the eligible rows (~4.7 TB/s of touched bytes) while the tensor pass
+  // With a caller mask the scan gathers only the eligible rows (adjacent rows merged into one copy) while the tensor pass
   // still streams every fp16 row, so the comparison needs the mask's population (known for host masks; a
   // device-evaluated filter keeps the scan).  Only while the index's small-batch searches keep being certified (an
   // uncertified query pays for both paths).
   bool small_q_tensor = false;
-  if (h->opt_tensor_auto && !h->auto_tensor_off && q < h->opt_tensor_min_q && h->opt_tensor_min_q <= kGemmMaxQueries &&
-      (a.d_mask == nullptr || a.mask_popcount >= 0)) {
+  bool device_route = false;  // the population of the mask is only known on the device: route there
+  if (h->opt_tensor_auto && !h->auto_tensor_off && q < h->opt_tensor_min_q && h->opt_tensor_min_q <= kGemmMaxQueries) {
     // streaming rates and fixed costs as measured on B200: fp32 scan 7.2 TB/s + 0.05 ms,
-    // gather scan 4.7 TB/s of touched bytes + 0.15 ms, tensor pass over fp16 rows 7.0 TB/s + 0.12 ms
+    // gather scan 5.3 TB/s of touched bytes + 0.06 ms, tensor pass over fp16 rows 7.0 TB/s + 0.12 ms
     const double rows = (double)h->n_slots;
     const double passes = std::ceil(q / 4.0);
-    const double scan_s = a.d_mask == nullptr
-                              ? passes * (rows * h->dpad * 4.0 / 7.2e12 + 0.05e-3)
-                              : passes * ((double)std::min<int64_t>(a.mask_popcount, h->n_slots) * h->dpad * 4.0 / 4.7e12 + 0.15e-3);
     const double tensor_s = rows * h->dpad16 * 2.0 / 7.0e12 + 0.12e-3;
-    small_q_tensor = tensor_s < 0.9 * scan_s;
+    if (a.d_mask != nullptr && a.mask_popcount < 0) {
+      // worth a route kernel only where the tensor pass could win at all (every row eligible)
+      device_route = tensor_s < 0.9 * gather_scan_seconds(rows, h->dpad * 4.0, passes);
+      // ... and not when the previous device-resident mask was so sparse that the scan won by a wide margin: the
+      // tensor kernels are then not even enqueued (~30 us of launches that would exit at once).  A wrong guess
+      // costs time only, and every masked search reports its population for the next one.
+      const int64_t last = h->last_mask_pop.load();
+      if (last >= 0 && !(tensor_s < 1.2 * gather_scan_seconds((double)last, h->dpad * 4.0, passes))) device_route = false;
+      small_q_tensor = device_route;
+    } else {
+      const double pop = (double)std::min<int64_t>(std::max<int64_t>(a.mask_popcount, 0), h->n_slots);
+      const double scan_s = a.d_mask == nullptr ? passes * (rows * h->dpad * 4.0 / 7.2e12 + 0.05e-3)
+                                                : gather_scan_seconds(pop, h->dpad * 4.0, passes);
+      small_q_tensor = tensor_s < 0.9 * scan_s;
+    }
   }
   const bool tensor_ok = h->use_x16 && !(h->flags & GFI_FLAG_NO_TENSOR) && h->unsafe_rows_ever == 0 &&
                          !(h->metric == GFI_METRIC_COSINE && h->zero_rows_ever > 0) &&
@@ -603,6 +620,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
                          h->n_slots >= h->opt_tensor_min_rows && a.kmax <= 256 && h->dpad16 >= 64 &&
                          get_encode_fn() != nullptr;
   c->auto_tensor_q = (tensor_ok && q < h->opt_tensor_min_q) ? q : 0;
+  device_route = device_route && tensor_ok && q < h->opt_tensor_min_q;
 
   // ---- workspace ----
   // query tiles of 128; with the CTA-pair kernel enabled, an even number of them (the last may be all padding)
@@ -674,7 +692,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   }
   if (nstages < 2) return fail(GFI_ERR_INDEX, "k and dimension too large for the scan kernel's shared memory");
   if (h->opt_scan_qt > 0) QT = std::min(QT, pow2_at_least(h->opt_scan_qt));
-  if (!tensor_ok) { while (QT > 1 && QT / 2 >= q) QT >>= 1; }
+  while (QT > 1 && QT / 2 >= q) QT >>= 1;  // (also on the tensor path: its fallback never has more than q queries)
   {
     const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
     nstages = (int)std::min<size_t>(kScanMaxStages, (227 * 1024 - fixed) / ((size_t)stage_floats * 4));
@@ -685,6 +703,22 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     CU_TRY(c->gather.ensure(((size_t)h->n_slots + 8) * 4));
     CU_TRY(cudaMemsetAsync(c->gather.p, 0, 16, st));
     CU_TRY(launch_compact_eligible(iv, mv, c->gather.as<uint32_t>() + 4, c->gather.as<uint32_t>(), st));
+    ++h->n_launch;
+  }
+  if (device_route) {
+    RouteParams rp{};
+    rp.elig_count = c->gather.as<uint32_t>();
+    rp.q = q;
+    rp.row_bytes = h->dpad * 4.0;
+    rp.passes = std::ceil(q / 4.0);
+    rp.tensor_s = (double)h->n_slots * h->dpad16 * 2.0 / 7.0e12 + 0.12e-3;
+    rp.skip = &ctrl->skip_tensor;
+    rp.tensor_nq = &ctrl->tensor_nq;
+    rp.fb_count = &ctrl->fb_count;
+    rp.fb_list = c->fb_list.as<uint32_t>();
+    rp.routed_scan = &ctrl->routed_scan;
+    rp.elig_out = &ctrl->elig_count;
+    CU_TRY(launch_route(rp, st));
     ++h->n_launch;
   }
   const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
@@ -703,6 +737,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     sp.flags = &ctrl->flags;
     sp.gather_list = gather ? c->gather.as<uint32_t>() + 4 : nullptr;
     sp.gather_count = gather ? c->gather.as<uint32_t>() : nullptr;
+    sp.elig_out = (gather && a.d_mask != nullptr) ? &ctrl->elig_count : nullptr;
     sp.rows_per_stage = R;
     sp.seg_floats = segf;
     sp.nseg = nseg;
@@ -827,11 +862,12 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   gp.flags = &ctrl->flags;
   gp.seed_tiles = seed_tiles;
   gp.seed_stride = seed_stride;
+  gp.skip = device_route ? &ctrl->skip_tensor : nullptr;
   gp.debug = h->opt_gemm_debug;
   // seed pass
   gp.seed_mode = 1;
   CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, seed_tiles * num_m_tiles), st));
-  SeedFinalizeParams sf{c->seeds.as<float>(), q, seed_tiles, rank, c->thresh.as<float>()};
+  SeedFinalizeParams sf{c->seeds.as<float>(), q, seed_tiles, rank, c->thresh.as<float>(), gp.skip};
   CU_TRY(launch_seed_finalize(sf, st));
   // main pass
   // cosine without a caller mask: raw-accumulator epilogue (rows are stored pre-normalised, one coefficient)
@@ -849,8 +885,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s.slice_q = q;
   s.slice_gather = slice_gather ? 1 : 0;
   s.qlist = nullptr;
-  s.nq_dev = nullptr;
-  s.nq = q;
+  s.nq_dev = device_route ? &ctrl->tensor_nq : nullptr;  // 0 when the device-side route chose the scan
+  s.nq = device_route ? 0 : q;
   s.certify = 1;
   s.thresh = c->thresh.as<float>();
   const float dd = (float)h->dim;
@@ -862,7 +898,9 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   sp.qlist = c->fb_list.as<uint32_t>();
   sp.nq_dev = &ctrl->fb_count;
   sp.nq = 0;
+  if (device_route) prof_begin(h, c, 0, st);  // this launch is the search itself when the device picks the scan
   CU_TRY(launch_scan(sp, QT, scan_grid, st));
+  if (device_route) prof_end(h, c, st);
   SelectParams s2{};
   fill_select(s2, c->cand_fb, c->cand_fb_cnt, scan_stride, K);
   s2.qlist = c->fb_list.as<uint32_t>();
@@ -1337,6 +1375,9 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   const char* hb = c->h_out.as<char>();
   const Ctrl* hc = reinterpret_cast<const Ctrl*>(hb);
   h->n_fallback_q += hc->uncertified;
+  h->n_tensor_q -= hc->routed_scan;  // device-side route: counted as tensor queries at enqueue
+  h->n_scan_q += hc->routed_scan;
+  if (hc->elig_count) h->last_mask_pop = (int64_t)hc->elig_count - 1;
   if (c->auto_tensor_q > 0) {  // keep the cost-model route only while it pays: < 1/4 of its queries falling back
     const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc->uncertified);
     if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;
@@ -1642,6 +1683,9 @@ int32_t gfi_search_status(gfi_index* h) {
   prof_collect(h, c);
   const Ctrl* hc = c->h_ctrl.as<Ctrl>();
   h->n_fallback_q += hc->uncertified;
+  h->n_tensor_q -= hc->routed_scan;
+  h->n_scan_q += hc->routed_scan;
+  if (hc->elig_count) h->last_mask_pop = (int64_t)hc->elig_count - 1;
   if (c->auto_tensor_q > 0) {  // same bookkeeping as the host path (the block describes the last search issued)
     const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc->uncertified);
     if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;

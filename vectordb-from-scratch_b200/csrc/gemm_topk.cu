@@ -527,6 +527,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                  const GemmParams p) {
   griddep_wait();
+  if (p.skip && *p.skip) return;  // device-side route: the scan answers this batch
   gemm_topk_body<MODE, 1>(tmx, tmq, p);
 }
 
@@ -536,6 +537,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
 gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                       const GemmParams p) {
   griddep_wait();
+  if (p.skip && *p.skip) return;
   gemm_topk_body<MODE, 2>(tmx, tmq, p);
 }
 
@@ -544,6 +546,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
 // pops the global minimum `rank` times.
 __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
   griddep_wait();
+  if (p.skip && *p.skip) return;
   const int lane = threadIdx.x & 31;
   const int qi = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (qi >= p.q) return;

@@ -54,6 +54,7 @@ struct ScanParams {
   uint32_t* flags;
   const uint32_t* gather_list;   // compacted eligible slots (filtered / tombstoned scans), or null
   const uint32_t* gather_count;  // device-side length of gather_list
+  uint32_t* elig_out;            // or null: receives *gather_count + 1 (the host learns the mask's population)
   int rows_per_stage, seg_floats, nseg;
   int lanes_per_row;        // 8: 4 rows per warp at a time (dpad <= 256); 32: one row per warp (longer rows)
   int nstages;              // ring depth (<= kScanMaxStages)
@@ -161,6 +162,7 @@ struct GemmParams {
   uint64_t* cand; uint32_t* cand_cnt; int64_t cand_stride; uint32_t cand_cap;
   unsigned short* slice_cnt;  // [slices][q]: written for every (slice, query) at the end of the main pass
   uint32_t* flags;
+  const uint32_t* skip; // device word or null: non-zero = the device-side route chose the scan, exit at once
   int debug;            // timing experiments only (see gemm_topk.cu)
   int pair;             // 1: CTA-pair kernel (cta_group::2); needs an even grid and an even number of query tiles;
                         // the row tensor map then has a 128-row box and slices are per PAIR: (pair*2+half)
@@ -172,8 +174,32 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
                              cudaStream_t st);
 struct SeedFinalizeParams {
   const float* seeds; int q; int64_t seed_tiles; int rank; float* thresh;
+  const uint32_t* skip;  // as GemmParams::skip
 };
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st);
+
+// ---- device-side route of a masked small batch (scan.cu) --------------------------------
+// Seconds of a gather scan over `pop` eligible rows of `row_bytes` (measured on B200, 10M x 384: 5.3 TB/s of touched
+// bytes at 50 % selectivity -- partially used DRAM pages -- plus ~0.06 ms of compaction, select and rerank).
+__host__ __device__ inline double gather_scan_seconds(double pop, double row_bytes, double passes) {
+  return passes * (pop * row_bytes / 5.3e12 + 0.06e-3);
+}
+// With a mask that lives on the device (caller's device pointer, device-evaluated MetadataFilter) the host does not
+// know how many rows are eligible, so the choice between the gather scan (touches eligible fp32 rows only) and the
+// masked tensor pass (streams every fp16 row) is made ON the device from the compaction's count: either the
+// tensor kernels run as enqueued, or they exit at once and every query goes to the predicated scan that already
+// follows them as the certification fallback.
+struct RouteParams {
+  const uint32_t* elig_count;  // written by compact_eligible_kernel
+  int q;
+  double row_bytes, passes, tensor_s;
+  uint32_t* skip;        // out: 1 = scan route
+  uint32_t* tensor_nq;   // out: queries the tensor path's select/rerank handle (q or 0)
+  uint32_t* fb_count; uint32_t* fb_list;  // scan route: all q queries
+  uint32_t* routed_scan; // stats
+  uint32_t* elig_out;    // population + 1, read back with the call's control block
+};
+cudaError_t launch_route(const RouteParams& p, cudaStream_t st);
 
 // ---- device-side MetadataFilter evaluation (filter.cu) ---------------------------------
 constexpr int kFilterEq = 0, kFilterNe = 1, kFilterExists = 2, kFilterAnd = 3, kFilterOr = 4;

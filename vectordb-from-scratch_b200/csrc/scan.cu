@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
   // one bulk copy per row, so ineligible rows cost no bandwidth at all
   const uint32_t* glist = p.gather_list;
   const uint32_t n = glist ? *p.gather_count : (uint32_t)iv.n_slots;
+  if (glist && p.elig_out && blockIdx.x == 0 && tid == 0) *p.elig_out = n + 1u;
   const int R = p.rows_per_stage, nseg = SEG ? p.nseg : 1, segw = p.seg_floats;
   const uint32_t nblocks = (n + R - 1) / R;
   const int rstride = SEG ? segw : dpad;
@@ -149,8 +150,25 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
           if (!SEG && glist) {
             if (lane == 0) mbar_arrive_expect_tx(&full[stage], (uint32_t)rows * dpad * 4u);
             __syncwarp();
-            for (int r = lane; r < rows; r += 32)
-              bulk_g2s(dst + (size_t)r * dpad, iv.x32 + (size_t)glist[row0 + r] * dpad, dpad * 4u, &full[stage]);
+            // Listed slots that are adjacent in the slot array are adjacent in HBM AND in the stage, so a run of
+            // them is ONE copy.  The copy engine retires about one bulk operation per ~90 cycles whatever its
+            // size: at 50 % selectivity (mean run 2 rows) merging halves the operation count, which is what
+            // bounded the gather scan (4.7 TB/s of touched bytes with one copy per 1.5 KB row).  Runs are cut at
+            // 32-entry chunk boundaries (one ballot per chunk, no cross-chunk state).
+            for (int base = 0; base < rows; base += 32) {
+              const int r = base + lane;
+              const bool in = r < rows;
+              const uint32_t s = in ? __ldg(glist + row0 + r) : 0u;
+              const uint32_t sprev = __shfl_up_sync(0xffffffffu, s, 1);
+              const bool head = in && (lane == 0 || sprev + 1u != s);
+              const uint32_t heads = __ballot_sync(0xffffffffu, head);
+              if (head) {
+                const uint32_t above = (lane == 31) ? 0u : (heads >> (lane + 1));
+                const int end = above ? lane + __ffs(above) : min(32, rows - base);
+                bulk_g2s(dst + (size_t)r * dpad, iv.x32 + (size_t)s * dpad, (uint32_t)(end - lane) * dpad * 4u,
+                         &full[stage]);
+              }
+            }
           } else if (!SEG) {
             if (lane == 0) {
               const uint32_t bytes = (uint32_t)rows * dpad * 4u;
@@ -383,40 +401,119 @@ cudaError_t launch_scan_shape(const ScanParams& p, int QT, int grid, size_t smem
   return cudaErrorInvalidValue;
 }
 
-// Compacts the eligible (live and unmasked) slots into a list (unordered: keys carry the slot, so the
-// processing order is irrelevant to the result).  One warp-aggregated atomic per 32 slots.
-__global__ void compact_eligible_kernel(const IndexView iv, const MaskView mask, uint32_t* list, uint32_t* count) {
+// Compacts the eligible (live and unmasked) slots into a list.  A block takes tiles of 8192 slots: every thread
+// owns one 32-slot eligibility word (read straight from the live / mask words when ids are the identity, built by
+// ballots from the id column otherwise), a block-wide exclusive scan places the words, ONE atomic per tile
+// reserves the tile's range, and the warps expand their words with coalesced stores.  Inside a tile the list is
+// ascending, so adjacent eligible slots are adjacent in the list (the gather scan copies such runs as one bulk
+// copy); tiles land in atomic order, which is irrelevant to the result (keys carry the slot).
+// (The first version issued one atomic per 32 slots on a single counter: 312k serialised atomics at 10M slots.)
+constexpr int kCompactThreads = 256;
+template <bool IDENT>
+__global__ void __launch_bounds__(kCompactThreads) compact_eligible_kernel(const IndexView iv, const MaskView mask,
+                                                                          uint32_t* list, uint32_t* count) {
   griddep_wait();
-  const int lane = threadIdx.x & 31;
-  for (int64_t s0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; s0 < iv.n_slots;
-       s0 += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t s = s0 + lane;
-    bool e = false;
-    if (s < iv.n_slots) {
-      e = (iv.live[s >> 5] >> (s & 31)) & 1u;
-      if (e && mask.bits) {
-        const uint64_t id = iv.ids_identity ? (uint64_t)s : iv.ids[s];
-        e = (id < (uint64_t)mask.nbits) && ((mask.bits[id >> 6] >> (id & 63)) & 1ull);
+  __shared__ uint32_t s_warp[kCompactThreads / 32];
+  __shared__ uint32_t s_base;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t nwords = (iv.n_slots + 31) >> 5;
+  const int64_t ntiles = (nwords + kCompactThreads - 1) / kCompactThreads;
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int64_t w = tile * kCompactThreads + tid;  // this thread's word: slots [32w, 32w + 32)
+    uint32_t e = 0;
+    if (w < nwords) {
+      e = __ldg(iv.live + w);
+      const int64_t left = iv.n_slots - (w << 5);
+      if (left < 32) e &= (1u << left) - 1u;
+      if (IDENT && mask.bits) {
+        const int64_t bleft = mask.nbits - (w << 5);  // ids >= nbits are ineligible
+        uint32_t m = 0;
+        if (bleft > 0) {
+          m = (uint32_t)(__ldg(mask.bits + (w >> 1)) >> ((w & 1) * 32));
+          if (bleft < 32) m &= (1u << bleft) - 1u;
+        }
+        e &= m;
       }
     }
-    const unsigned m = __ballot_sync(0xffffffffu, e);
-    if (m) {
-      uint32_t base = 0;
-      if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(m));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (e) list[base + __popc(m & ((1u << lane) - 1u))] = (uint32_t)s;
+    if (!IDENT && mask.bits) {
+      // ids are arbitrary: the warp walks its 32 words together, a lane per slot, and ballots the mask bits
+      const int64_t w0 = tile * kCompactThreads + warp * 32;
+      uint32_t mine = 0;
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+        bool bit = false;
+        if ((ej >> lane) & 1u) {
+          const uint64_t id = __ldg(iv.ids + ((w0 + j) << 5) + lane);
+          bit = (id < (uint64_t)mask.nbits) && ((__ldg(mask.bits + (id >> 6)) >> (id & 63)) & 1ull);
+        }
+        const uint32_t word = __ballot_sync(0xffffffffu, bit);
+        if (lane == j) mine = word;
+      }
+      e = mine;
+    }
+    // block-wide exclusive scan of the words' populations
+    const uint32_t cnt = (uint32_t)__popc(e);
+    uint32_t incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t woff = 0, total = 0;
+#pragma unroll
+    for (int i = 0; i < kCompactThreads / 32; ++i) {
+      const uint32_t t = s_warp[i];
+      if (i < warp) woff += t;
+      total += t;
+    }
+    if (tid == 0) s_base = total ? atomicAdd(count, total) : 0u;
+    __syncthreads();
+    const uint32_t off = s_base + woff + incl - cnt;
+    if (total) {
+      const uint32_t slot0 = (uint32_t)((tile * kCompactThreads + warp * 32) << 5);
+      for (int j = 0; j < 32; ++j) {
+        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+        const uint32_t oj = __shfl_sync(0xffffffffu, off, j);
+        if ((ej >> lane) & 1u) list[oj + __popc(ej & ((1u << lane) - 1u))] = slot0 + (uint32_t)(j << 5) + lane;
+      }
+    }
+    __syncthreads();  // s_warp / s_base are reused by the next tile
+  }
+}
+
+__global__ void route_kernel(const RouteParams p) {
+  griddep_wait();
+  const double scan_s = gather_scan_seconds((double)*p.elig_count, p.row_bytes, p.passes);
+  const bool scan = !(p.tensor_s < 0.9 * scan_s);
+  for (int i = threadIdx.x; i < p.q; i += blockDim.x)
+    if (scan) p.fb_list[i] = (uint32_t)i;
+  if (threadIdx.x == 0) {
+    *p.elig_out = *p.elig_count + 1u;
+    *p.skip = scan ? 1u : 0u;
+    *p.tensor_nq = scan ? 0u : (uint32_t)p.q;
+    if (scan) {
+      *p.fb_count = (uint32_t)p.q;
+      *p.routed_scan = (uint32_t)p.q;
     }
   }
 }
 
 }  // namespace
 
+cudaError_t launch_route(const RouteParams& p, cudaStream_t st) {
+  return launch_pdl(route_kernel, dim3(1), dim3(32), 0, st, p);
+}
+
 cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, uint32_t* list, uint32_t* count,
                                     cudaStream_t st) {
   if (iv.n_slots == 0) return cudaSuccess;
-  const int blocks = (int)std::min<int64_t>((iv.n_slots + 255) / 256, 148 * 8);
-  return launch_pdl(compact_eligible_kernel, dim3(blocks), dim3(256), 0, st, iv, mask, list, count);
-  return cudaGetLastError();
+  const int64_t tiles = (iv.n_slots + 32 * kCompactThreads - 1) / (32 * kCompactThreads);
+  const int blocks = (int)std::min<int64_t>(tiles, 148 * 8);
+  if (iv.ids_identity || !mask.bits)
+    return launch_pdl(compact_eligible_kernel<true>, dim3(blocks), dim3(kCompactThreads), 0, st, iv, mask, list, count);
+  return launch_pdl(compact_eligible_kernel<false>, dim3(blocks), dim3(kCompactThreads), 0, st, iv, mask, list, count);
 }
 
 size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats) {
