@@ -79,31 +79,57 @@ def peaks():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks and throttle reasons during the timed region."""
+    """Samples SM clocks and throttle reasons during the timed region: NVML in-process (about a millisecond per
+    sample) when it loads, else the `nvidia-smi` query of the profiling recipe (tens of milliseconds per sample)."""
+
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, gpu):
         super().__init__(daemon=True)
-        self.gpu, self.stop_flag, self.rows = gpu, threading.Event(), []
+        self.gpu, self.stop_flag, self.rows, self.source = gpu, threading.Event(), [], "nvidia-smi"
+        self.nv = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML orders devices by PCI bus id; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            phys = int(vis.split(",")[gpu]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else gpu
+            self.nv = (pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys))
+            self.source = "nvml"
+        except Exception:
+            self.nv = None
+
+    def sample_nvml(self):
+        nv, h = self.nv
+        sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        bits = [nv.nvmlClocksThrottleReasonHwSlowdown, nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown, nv.nvmlClocksThrottleReasonSwPowerCap]
+        return [str(sm), str(mx)] + ["Active" if r & b else "Not Active" for b in bits]
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
+                if self.nv:
+                    self.rows.append(self.sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                    self.rows.append([x.strip() for x in out.stdout.strip().split(",")])
             except Exception:
-                pass
-            self.stop_flag.wait(0.05)
+                if self.nv:
+                    self.nv, self.source = None, "nvidia-smi"
+            self.stop_flag.wait(0.005 if self.nv else 0.05)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({self.NAMES[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": reasons, "samples": len(sm), "source": self.source}
 
 
 def cpu_reference_run(wl, steps, warmup, sample_q=None):

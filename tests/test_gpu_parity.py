@@ -269,7 +269,33 @@ def test_mask_pushdown_and_post_filter(sel):
         assert np.array_equal(np.array([x for _, x in got], np.float32), ed)
 
 
-@pytest.mark.gpu
+def test_mask_by_internal_id_with_gaps_in_the_id_space():
+    """The caller's mask is indexed by INTERNAL ID (bit i <=> id i); with gaps in the id space the compaction builds
+    each 32-slot eligibility word from the id column (compact_eligible_kernel<false>).  Ids beyond the mask's length
+    are ineligible."""
+    n, d, k = 9000, 96, 10
+    rows = oracle.gen_rows(61, 0, n, d, 1)
+    queries = oracle.gen_rows(62, 0, 5, d, 1)
+    rng = np.random.default_rng(4)
+    ids = np.sort(rng.choice(40000, n, replace=False)).astype(np.uint64)
+    for flags in (1, 0):
+        idx = build("cosine", rows, ids=ids, flags=flags)
+        for r in (3, 500, 8999):
+            idx.remove(int(ids[r]))
+        live = np.ones(n, dtype=bool)
+        live[[3, 500, 8999]] = False
+        for nbits in (40000, 25000):
+            mask = rng.random(nbits) < 0.3
+            elig_rows = np.zeros(n, dtype=bool)
+            inside = ids < nbits
+            elig_rows[inside] = mask[ids[inside].astype(np.int64)]
+            got_ids, got_d, cnt = idx.search_arrays(queries, k, mask=mask)
+            exp = oracle.search_batch("cosine", rows[live], queries, k, ids=ids[live], eligible=elig_rows[live], threads=4)
+            for i, (eids, ed) in enumerate(exp):
+                assert cnt[i] == len(eids)
+                assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"id mask {nbits} q{i}")
+
+
 @pytest.mark.parametrize("metric,d", [("euclidean", 384), ("cosine", 100), ("dot", 768)])
 def test_gather_scan_merges_runs_of_adjacent_eligible_rows(metric, d):
     """The gather scan copies a run of adjacent eligible slots as ONE bulk copy (scan.cu producer): runs of every

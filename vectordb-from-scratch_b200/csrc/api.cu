@@ -834,7 +834,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->slice_cnt.ensure((size_t)units * 2 * q * 2));  // written in full by the main pass: no pre-fill
   // Usual case (expected candidates per query well below select_kernel's staging area): the select pass reads
   // only the valid prefix of every slice.  Large k: pre-fill with sentinels and let it scan the whole block.
-  const bool slice_gather = 3 * hits_eff <= kSelectStageKeys;
+  // (the staging area grows with the expected candidate count up to 16384 keys = 128 KB of shared memory: k = 100
+  // means KP = 512 and ~4096 expected candidates, which the sentinel path answered with 8 radix passes over
+  // 150 KB of global memory per query -- 156 us on C3a)
+  const int sel_cap = std::max(kSelectStageKeys, std::min(16384, pow2_at_least(3 * hits_eff)));
+  const bool slice_gather = 3 * hits_eff <= sel_cap;
   if (!slice_gather) CU_TRY(cudaMemsetAsync(c->cand.p, 0xff, (size_t)q * cand_stride * 8, st));
 
   CUtensorMap tmx, tmq, tmx_half;
@@ -884,6 +888,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s.slice_cap = cap;
   s.slice_q = q;
   s.slice_gather = slice_gather ? 1 : 0;
+  s.sel_cap = sel_cap;
   s.qlist = nullptr;
   s.nq_dev = device_route ? &ctrl->tensor_nq : nullptr;  // 0 when the device-side route chose the scan
   s.nq = device_route ? 0 : q;

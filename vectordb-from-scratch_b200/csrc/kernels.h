@@ -113,6 +113,7 @@ struct SelectParams {
   // for that (slice, query) (may exceed slice_cap: overflow).  Only the valid prefix of each slice is read.
   const unsigned short* slice_cnt; int nslices; uint32_t slice_cap; int64_t slice_q;
   int slice_gather;           // 1: read the slices' valid prefixes; 0: cand is sentinel-filled, scan it whole
+  int sel_cap;                // candidate keys staged in shared memory per query (0 = kSelectStageKeys; <= 16384)
   // certification (tensor path): every row that is not a candidate has approx score >= cutoff
   int certify;                // 0 = scan path (never falls back), 1 = tensor path
   const float* thresh;        // per-query score threshold used by the tensor kernel

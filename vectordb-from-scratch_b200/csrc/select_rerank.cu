@@ -33,7 +33,8 @@ __device__ __forceinline__ float exact_step(float acc, float a, float b) {
   return __fadd_rn(acc, __fmul_rn(a, b));
 }
 
-constexpr int kSelCap = kSelectStageKeys;     // valid candidate keys kept in shared memory (else: passes over global memory)
+// (valid candidate keys kept in shared memory: SelectParams::sel_cap, default kSelectStageKeys; else passes over
+// global memory)
 constexpr int kTileFloats = 4096;  // rerank tile: GC candidates x CW floats, GC * CW = 4096
 
 // Exact 64-bit radix select: returns the `need`-th smallest (1-based) of the valid keys in src[0..cnt).
@@ -81,6 +82,7 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
 __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams p) {
   griddep_wait();
   extern __shared__ __align__(16) uint64_t s_dyn[];  // sel[KP] | keys[kSelCap] | (sorted-list path only) keys2[kSelCap]
+  const uint32_t kSelCap = p.sel_cap > 0 ? (uint32_t)p.sel_cap : (uint32_t)kSelectStageKeys;
   uint64_t* sel = s_dyn;
   uint64_t* keys = s_dyn + p.KP;
   uint64_t* keys2 = keys + kSelCap;  // prefix keys of the sorted-list path (keys[] holds the heads meanwhile)
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     uint64_t bound = kKeySentinel - 1;
     const uint32_t L = p.list_len > 0 ? cnt / (uint32_t)p.list_len : 0;  // number of ascending lists
     const uint32_t m_heads = L ? min((uint32_t)p.list_len, ((uint32_t)KP + L - 1) / L + 1) : 0;
-    if (L && L * m_heads <= (uint32_t)kSelCap) {
+    if (L && L * m_heads <= kSelCap) {
       // Scan-path input: L ascending lists.  (a) The KP-th smallest of the lists' first m_heads keys
       // bounds the KP-th smallest overall from above; (b) the keys <= that bound are a prefix of each
       // list, so one thread per list walks its prefix (batches of 4 independent loads).
@@ -142,7 +144,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
           for (int u = 0; u < 4; ++u) {
             if (more && kk[u] <= bound) {
               const uint32_t pos = atomicAdd(&s_nvalid, 1u);
-              if (pos < (uint32_t)kSelCap) sel_stage(keys, pos, kk[u]);
+              if (pos < kSelCap) sel_stage(keys, pos, kk[u]);
             } else {
               more = false;
             }
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
           const uint64_t* src = cand + (size_t)sl * p.slice_cap;
           const uint32_t base = atomicAdd(&s_nvalid, n);
           for (uint32_t j = 0; j < n; ++j)
-            if (base + j < (uint32_t)kSelCap) keys[base + j] = src[j];
+            if (base + j < kSelCap) keys[base + j] = src[j];
         }
       }
     } else {
@@ -182,7 +184,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
             if (lane == 0) base = atomicAdd(&s_nvalid, (uint32_t)__popc(m));
             base = __shfl_sync(0xffffffffu, base, 0);
             const uint32_t pos = base + __popc(m & ((1u << lane) - 1u));
-            if (valid && pos < (uint32_t)kSelCap) keys[pos] = kk[u];
+            if (valid && pos < kSelCap) keys[pos] = kk[u];
           }
         }
       }
@@ -192,11 +194,11 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     const uint32_t kpeff = min((uint32_t)KP, nvalid);
     // slices are not contiguous in global memory, so a query whose keys do not fit the staging area is
     // treated as overflowed (it falls back to the exact scan)
-    if (p.slice_cnt && (s_over || (p.slice_gather && nvalid > (uint32_t)kSelCap))) overflow = true;
-    const bool in_smem = nvalid <= (uint32_t)kSelCap || (p.slice_cnt && p.slice_gather);
-    const bool sorted_path = L && L * m_heads <= (uint32_t)kSelCap;
+    if (p.slice_cnt && (s_over || (p.slice_gather && nvalid > kSelCap))) overflow = true;
+    const bool in_smem = nvalid <= kSelCap || (p.slice_cnt && p.slice_gather);
+    const bool sorted_path = L && L * m_heads <= kSelCap;
     const uint64_t* src = in_smem ? (sorted_path ? keys2 : keys) : cand;
-    const uint32_t src_n = in_smem ? min(nvalid, (uint32_t)kSelCap) : cnt;
+    const uint32_t src_n = in_smem ? min(nvalid, kSelCap) : cnt;
 
     // ---- exact radix select of the KP-th smallest key (only when there are more than KP) ----
     uint64_t pivot = kKeySentinel - 1;  // everything valid is <= pivot
@@ -602,7 +604,19 @@ __global__ void __launch_bounds__(kSpWarps * 32) score_pairs_kernel(const ScoreP
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st) {
   if (grid <= 0) return cudaSuccess;
   if (p.KP < 32 || p.KP > kMaxKP || (p.KP & (p.KP - 1))) return cudaErrorInvalidValue;
-  const size_t sel_smem = ((size_t)p.KP + (size_t)kSelCap * (p.list_len > 0 ? 2 : 1)) * 8;
+  const size_t sel_cap = p.sel_cap > 0 ? (size_t)p.sel_cap : (size_t)kSelectStageKeys;
+  const size_t sel_smem = ((size_t)p.KP + sel_cap * (p.list_len > 0 ? 2 : 1)) * 8;
+  if (sel_smem > 48 * 1024) {
+    if (sel_smem > 200 * 1024) return cudaErrorInvalidValue;
+    static unsigned long long big_smem_set = 0;  // bit per device (function attributes are per device); a racing
+    int dev = 0;                                 // duplicate cudaFuncSetAttribute call is harmless
+    cudaGetDevice(&dev);
+    if (!((big_smem_set >> (dev & 63)) & 1ull)) {
+      cudaError_t ea = cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      if (ea != cudaSuccess) return ea;
+      big_smem_set |= 1ull << (dev & 63);
+    }
+  }
   cudaError_t e = launch_pdl(select_kernel, dim3(grid), dim3(kSelThreads), sel_smem, st, p);
   if (e != cudaSuccess) return e;
   SelectParams pp = p;
