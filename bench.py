@@ -138,7 +138,13 @@ def cpu_reference_run(wl, steps, warmup, sample_q=None):
     import numpy as np
     import oracle
     metric, n, d, kind, seed, q, k = WORKLOADS[wl]
-    cores = oracle.max_threads()
+    # all the host cores this process may run on (not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1,
+    # which would silently time a single-threaded baseline at N > 1; the oracle passes num_threads() explicitly)
+    try:
+        cores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = os.cpu_count() or 1
+    cores = max(cores, oracle.max_threads())
     # bound the CPU work to about 15 s: one query costs about n*d*4 cycles on one core
     per_query_s = max(n * d * 4 / 2.5e9, 1e-5)
     if sample_q is None:
