@@ -103,6 +103,8 @@ struct Ctrl {
   uint32_t tensor_nq;
   uint32_t routed_scan;
   uint32_t elig_count;  // population of the mask + 1 when a gather scan or the route kernel saw it, else 0
+  uint32_t scan_done;   // CTAs of a fused-tail scan that have finished (ScanParams::done_ctr)
+  uint32_t pad_[3];
 };
 
 struct SearchCtx {
@@ -205,6 +207,7 @@ struct gfi_index {
   int opt_kp = 0;          // 0 = auto
   int opt_hits = 0;        // 0 = auto
   int opt_scan_qt = 0;     // 0 = auto
+  int opt_fused_tail = 1;  // small single-pass scans finish inside the scan kernel (experiments: 0 = separate K3)
   int opt_grid = 0;        // 0 = sm_count
   int opt_tensor_min_rows = 8192;
   int opt_seed_rank = 8;
@@ -778,9 +781,26 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     sp.qlist = nullptr;
     sp.nq_dev = nullptr;
     sp.nq = q;
+    // small single-pass searches: the scan's last CTA does the select / rerank / emit itself (scan.cu)
+    const bool fused = h->opt_fused_tail && q <= QT && nseg == 1 && K <= 64 &&
+                       scan_fused_tail_bytes(scan_grid, K, h->dpad) <= (size_t)nstages * stage_floats * 4;
+    if (fused) {
+      sp.fused = 1;
+      sp.done_ctr = &ctrl->scan_done;
+      sp.ks = a.d_ks;
+      sp.out_ids = a.d_out_ids;
+      sp.out_dist = a.d_out_dist;
+      sp.out_counts = a.d_out_counts;
+      sp.kstride = a.kstride;
+    }
     prof_begin(h, c, 0, st);
     CU_TRY(launch_scan(sp, QT, scan_grid, st));
     prof_end(h, c, st);
+    if (fused) {
+      h->n_launch += 1;
+      h->n_scan_q += q;
+      return GFI_OK;
+    }
     SelectParams s{};
     fill_select(s, c->cand, c->cand_cnt, scan_stride, K);
     s.qlist = nullptr;
@@ -1872,6 +1892,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "kp") h->opt_kp = (int)value;
   else if (n == "hits") h->opt_hits = (int)value;
   else if (n == "scan_qt") h->opt_scan_qt = (int)value;
+  else if (n == "fused_tail") h->opt_fused_tail = (int)value;
   else if (n == "grid") h->opt_grid = (int)value;
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;

@@ -59,7 +59,15 @@ struct ScanParams {
   int lanes_per_row;        // 8: 4 rows per warp at a time (dpad <= 256); 32: one row per warp (longer rows)
   int nstages;              // ring depth (<= kScanMaxStages)
   int stage_floats;         // floats per ring stage (rows_per_stage * row stride in the stage)
+  // Fused tail (small single-pass searches, K <= 64): the LAST CTA to finish selects the K best keys of all CTAs,
+  // re-scores them with the reference's arithmetic, sorts and emits -- the whole of K3 without two more launches
+  // (a 10k x 128 single-query search is pure latency: three dependent kernels of ~10 us each).
+  int fused;                // 1 = on (nq <= QT, nseg == 1, the ring is large enough: see scan_fused_tail_bytes)
+  uint32_t* done_ctr;       // zeroed per call
+  const uint32_t* ks;       // per-query k
+  uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
 };
+size_t scan_fused_tail_bytes(int grid, int K, int dpad);
 // eligible (live and unmasked) slots -> list[0..*count)
 cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, uint32_t* list, uint32_t* count,
                                     cudaStream_t st);

@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact.cuh"
 #include "kernels.h"
 
 namespace gfi {
@@ -82,8 +83,106 @@ struct RowMeta {
   float norm[kMaxRounds];
 };
 
+// Fused tail, run by the last CTA of a small single-pass search (ScanParams::fused): K3 in place.  Per query:
+// (A) all CTAs' K-lists into shared memory; (B) the K-th smallest of the lists' first few keys bounds the K-th
+// smallest overall, the keys below the bound are ranked by counting (keys are unique: they carry the slot) and the
+// K smallest land in ascending order; (C) a warp per candidate pulls the row, lane 0 walks it with the reference's
+// sequential arithmetic (exact.cuh); (D) the exact keys are ranked again and the first k emitted -- the same
+// select -> rerank -> sort -> truncate as select_kernel + rerank_finalize_kernel (src/flat_index.rs:53-63).
+template <int METRIC>
+__device__ __noinline__ void scan_fused_tail(const ScanParams& p, int nq, const float* qs, unsigned char* scratch,
+                                             uint64_t* ctl, int tid) {
+  constexpr int NT = kScanThreads, NWARP = NT / 32;
+  // (control words in the dynamic allocation: a static __shared__ here would push the kernel past the 227 KB limit)
+  uint64_t& s_bound = ctl[0];
+  uint32_t& s_n = reinterpret_cast<uint32_t*>(ctl + 1)[0];
+  uint32_t& s_m = reinterpret_cast<uint32_t*>(ctl + 1)[1];
+  const IndexView& iv = p.iv;
+  const int K = p.K, L = (int)gridDim.x, dpad = iv.dpad, LK = L * K;
+  const int lane = tid & 31, warp = tid >> 5;
+  uint64_t* sel = reinterpret_cast<uint64_t*>(scratch);  // [K] best approximate keys, ascending
+  uint64_t* ex = sel + K;                                // [K] exact keys
+  uint64_t* keys = ex + K;                               // [L*K] every CTA's list
+  uint64_t* cands = keys + LK;                           // [L*K] heads, then the keys below the bound
+  float* tiles = reinterpret_cast<float*>(keys);         // rerank: one row per warp (keys/cands are dead by then)
+  for (int qi = 0; qi < nq; ++qi) {
+    const uint32_t qg = p.qlist ? p.qlist[qi] : (uint32_t)qi;
+    const uint64_t* cand = p.cand + (size_t)qg * p.cand_stride;
+    if (tid == 0) { s_n = 0; s_m = 0; s_bound = kKeySentinel - 1; }
+    __syncthreads();
+    uint32_t nv = 0;
+    for (int i = tid; i < LK; i += NT) {
+      const uint64_t k64 = __ldcg(cand + i);  // written by the other CTAs: read at L2
+      keys[i] = k64;
+      nv += k64 != kKeySentinel;
+    }
+    for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
+    if (lane == 0 && nv) atomicAdd(&s_n, nv);
+    __syncthreads();
+    const uint32_t nvalid = s_n, kpeff = min((uint32_t)K, nvalid);
+    if (nvalid > (uint32_t)K) {
+      const int m = min(K, (K + L - 1) / L + 1), nh = L * m;  // nh <= K + 2L
+      for (int h = tid; h < nh; h += NT) cands[h] = keys[(h / m) * K + (h % m)];
+      __syncthreads();
+      for (int h = tid; h < nh; h += NT) {
+        const uint64_t key = cands[h];
+        if (key != kKeySentinel) {
+          uint32_t below = 0;
+          for (int j = 0; j < nh; ++j) below += cands[j] < key;
+          if (below == (uint32_t)K - 1) s_bound = key;  // (with fewer than K valid heads the bound stays open)
+        }
+      }
+      __syncthreads();
+    }
+    const uint64_t bound = s_bound;
+    for (int i = tid; i < LK; i += NT) {
+      const uint64_t k64 = keys[i];
+      if (k64 <= bound) cands[atomicAdd(&s_m, 1u)] = k64;  // the sentinel is above any bound
+    }
+    __syncthreads();
+    const int M = (int)s_m;  // >= kpeff
+    for (int i = tid; i < M; i += NT) {
+      const uint64_t key = cands[i];
+      uint32_t below = 0;
+      for (int j = 0; j < M; ++j) below += cands[j] < key;
+      if (below < (uint32_t)K) sel[below] = key;
+    }
+    __syncthreads();
+    const float qn = p.qnorm[qg];
+    const float* qv = qs + (size_t)qi * dpad;
+    for (int c = warp; c < (int)kpeff; c += NWARP) {
+      const uint32_t slot = (uint32_t)(sel[c] & 0xffffffffu);
+      float* xr = tiles + (size_t)warp * dpad;
+      const float4* x4 = reinterpret_cast<const float4*>(iv.x32 + (size_t)slot * dpad);
+      for (int t = lane; t < (dpad >> 2); t += 32) reinterpret_cast<float4*>(xr)[t] = __ldg(x4 + t);
+      __syncwarp();
+      if (lane == 0) {
+        float acc = -0.0f;
+#pragma unroll 8
+        for (int i = 0; i < iv.d; ++i) acc = exact_step<METRIC>(acc, qv[i], xr[i]);
+        ex[c] = pack_key(exact_finish<METRIC>(acc, METRIC == kMetricCos ? iv.norm[slot] : 1.f, qn, p.flags), slot);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (METRIC == kMetricCos && nvalid > 0 && qn == 0.f && tid == 0) atomicOr(p.flags, kFlagZeroNorm);
+    const uint32_t kq = min(p.ks[qg], kpeff);
+    for (int i = tid; i < (int)kpeff; i += NT) {
+      const uint64_t key = ex[i];
+      uint32_t below = 0;
+      for (int j = 0; j < (int)kpeff; ++j) below += ex[j] < key;
+      if (below < kq) {
+        p.out_ids[(size_t)qg * p.kstride + below] = iv.ids[(uint32_t)(key & 0xffffffffu)];
+        p.out_dist[(size_t)qg * p.kstride + below] = key_f32((uint32_t)(key >> 32));
+      }
+    }
+    if (tid == 0) p.out_counts[qg] = kq;
+    __syncthreads();
+  }
+}
+
 template <int METRIC, int QT, int LPR, bool SEG>
-__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid_constant__ ScanParams p) {
   griddep_wait();
   constexpr int G = 32 / LPR;              // rows processed concurrently by one warp (LPR lanes per row)
   constexpr bool FAST = (QT == 1) && !SEG;  // single query, whole rows per stage: query lives in registers
@@ -366,6 +465,17 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const ScanPa
     }
     __syncthreads();
   }
+  if (!SEG && p.fused) {
+    uint64_t* ctl = empty + kScanMaxStages;  // 4 words behind the barriers (scan_smem_bytes)
+    uint32_t& s_last = reinterpret_cast<uint32_t*>(ctl + 2)[0];
+    __threadfence();  // this CTA's lists before its ticket
+    __syncthreads();
+    if (tid == 0) s_last = atomicAdd(p.done_ctr, 1u) == gridDim.x - 1 ? 1u : 0u;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    scan_fused_tail<METRIC>(p, nq, qs, smem_raw, ctl, tid);
+  }
 }
 
 template <int METRIC, int LPR, bool SEG>
@@ -516,9 +626,13 @@ cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, u
   return launch_pdl(compact_eligible_kernel<false>, dim3(blocks), dim3(kCompactThreads), 0, st, iv, mask, list, count);
 }
 
+size_t scan_fused_tail_bytes(int grid, int K, int dpad) {
+  return 2 * (size_t)K * 8 + std::max<size_t>(2 * (size_t)grid * K * 8, (size_t)(kScanThreads / 32) * dpad * 4);
+}
+
 size_t scan_smem_bytes(int QT, int dpad, int K, int nstages, int stage_floats) {
   return (size_t)nstages * stage_floats * 4 + (size_t)QT * dpad * 4 + (size_t)QT * NW * K * 8 +
-         2 * kScanMaxStages * 8 + 16;
+         2 * kScanMaxStages * 8 + 4 * 8;  // barriers + the fused tail's control words
 }
 
 cudaError_t launch_scan(const ScanParams& p, int QT, int grid, cudaStream_t st) {

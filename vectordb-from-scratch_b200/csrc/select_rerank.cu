@@ -13,6 +13,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "exact.cuh"
 #include "kernels.h"
 
 namespace gfi {
@@ -21,17 +22,6 @@ namespace {
 
 constexpr int kSelThreads = 256;
 constexpr int kMaxKP = 1024;
-
-// One step of the reference's sequential sums (src/distance.rs:37-44,67-73): separately rounded
-// subtract / multiply / add, never contracted to FMA.
-template <int METRIC>
-__device__ __forceinline__ float exact_step(float acc, float a, float b) {
-  if (METRIC == kMetricL2) {
-    const float t = __fsub_rn(a, b);
-    return __fadd_rn(acc, __fmul_rn(t, t));
-  }
-  return __fadd_rn(acc, __fmul_rn(a, b));
-}
 
 // (valid candidate keys kept in shared memory: SelectParams::sel_cap, default kSelectStageKeys; else passes over
 // global memory)
@@ -273,28 +263,7 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
     const float qn = p.qnorm[qg];
     const float* qv = p.q32 + (size_t)qg * iv.dpad;
     auto finish_distance = [&](float acc, uint32_t slot) -> float {
-      float dist;
-      if (METRIC == kMetricL2) {
-        dist = __fsqrt_rn(acc);
-      } else if (METRIC == kMetricDot) {
-        dist = -acc;
-      } else {
-        const float xn = iv.norm[slot];
-        if (xn == 0.f || qn == 0.f) {
-          atomicOr(p.flags, kFlagZeroNorm);
-          dist = 0.f;
-        } else {
-          float sim = __fdiv_rn(acc, __fmul_rn(qn, xn));
-          if (sim < -1.0f) sim = -1.0f;
-          else if (sim > 1.0f) sim = 1.0f;
-          dist = __fsub_rn(1.0f, sim);
-        }
-      }
-      if (dist != dist) {
-        atomicOr(p.flags, kFlagNaN);
-        dist = 0.f;
-      }
-      return dist;
+      return exact_finish<METRIC>(acc, METRIC == kMetricCos ? iv.norm[slot] : 1.f, qn, p.flags);
     };
 
     if (p.warp_per_candidate) {
