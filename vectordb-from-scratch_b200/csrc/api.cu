@@ -106,12 +106,15 @@ struct Ctrl {
   uint32_t scan_done;   // CTAs of a fused-tail scan that have finished (ScanParams::done_ctr)
   uint32_t pad_[3];
 };
+static_assert(sizeof(Ctrl) == kCtrlWords * 4, "host result blocks reserve 64 bytes: Ctrl + the done word");
 
 struct SearchCtx {
   cudaStream_t stream = nullptr;
   DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, slice_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
       fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
   PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl, h_out;
+  bool zc_pending = false;   // the search enqueued last publishes its results in h_out itself (latency mode)
+  uint32_t zc_seq = 0;
   DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
   void* ctrl_dev = nullptr;  // control block of the search being enqueued (inside out_blk or `ctrl`)
   bool pending_status = false;  // device search issued, status not yet collected
@@ -208,6 +211,7 @@ struct gfi_index {
   int opt_hits = 0;        // 0 = auto
   int opt_scan_qt = 0;     // 0 = auto
   int opt_fused_tail = 1;  // small single-pass scans finish inside the scan kernel (experiments: 0 = separate K3)
+  int opt_zero_copy = 1;   // small host searches: pinned-host inputs/outputs, no copies, no stream sync (0 = off)
   int opt_grid = 0;        // 0 = sm_count
   int opt_tensor_min_rows = 8192;
   int opt_seed_rank = 8;
@@ -574,6 +578,13 @@ struct SearchArgs {
   float* d_out_dist;
   uint32_t* d_out_counts;
   int64_t kstride;
+  // latency mode (small host searches, see ScanParams::h_ctrl): pinned host views of ks and of the result block
+  const uint32_t* h_ks_in = nullptr;
+  uint32_t* h_ctrl = nullptr;
+  uint64_t* h_out_ids = nullptr;
+  float* h_out_dist = nullptr;
+  uint32_t* h_out_counts = nullptr;
+  uint32_t done_seq = 0;
   bool mask_by_slot = false;  // the mask is indexed by slot (device-evaluated filter), not by internal id
   int64_t mask_popcount = -1;  // eligible bits of a host mask when known (cost model), else -1
 };
@@ -654,6 +665,8 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   pq.d = (int)h->dim;
   pq.dpad = h->dpad;
   pq.dpad16 = h->dpad16;
+  pq.ks_in = a.h_ks_in;
+  pq.ks_out = a.h_ks_in ? const_cast<uint32_t*>(a.d_ks) : nullptr;
   CU_TRY(launch_prep_queries(pq, st));
   h->n_launch += tensor_ok ? 2 : 1;
 
@@ -792,6 +805,15 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
       sp.out_dist = a.d_out_dist;
       sp.out_counts = a.d_out_counts;
       sp.kstride = a.kstride;
+      if (a.h_ctrl) {
+        sp.h_ctrl = a.h_ctrl;
+        sp.d_ctrl = reinterpret_cast<const uint32_t*>(ctrl);
+        sp.h_out_ids = a.h_out_ids;
+        sp.h_out_dist = a.h_out_dist;
+        sp.h_out_counts = a.h_out_counts;
+        sp.done_seq = a.done_seq;
+        c->zc_pending = true;
+      }
     }
     prof_begin(h, c, 0, st);
     CU_TRY(launch_scan(sp, QT, scan_grid, st));
@@ -1360,15 +1382,27 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   char* blk = c->out_blk.as<char>();
   c->ctrl_dev = blk;
   if (mask || filter_json) CU_TRY(c->mask.ensure(mask_words * 8 + 8));
-  // queries already in pinned memory are copied straight from the caller's buffer
-  const void* q_src = queries;
-  if (!is_pinned_host(queries)) {
-    memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
-    q_src = c->h_q.p;
-  }
+  // Latency mode (small plain searches): the kernels read queries and ks straight from this context's pinned
+  // staging buffers over PCIe, and a fused-tail scan writes the results and a completion word back into pinned host
+  // memory, so the call issues no copy-engine operation and no stream synchronisation (each costs a few
+  // microseconds of engine hand-over, which is most of a 10k-row search).  Not with per-kernel event timing on.
+  const bool zero_copy = h->opt_zero_copy && !h->opt_profile && !mask && !filter_json && (size_t)q * dim * 4 <= 16384;
+  c->zc_pending = false;
+  const float* d_queries = c->q_in.as<float>();
   memcpy(c->h_ks.p, ks, (size_t)q * 4);
-  CU_TRY(cudaMemcpyAsync(c->q_in.p, q_src, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
-  CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
+  if (zero_copy) {
+    memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
+    d_queries = c->h_q.as<float>();  // cudaMallocHost memory: device-accessible under unified addressing
+  } else {
+    // queries already in pinned memory are copied straight from the caller's buffer
+    const void* q_src = queries;
+    if (!is_pinned_host(queries)) {
+      memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
+      q_src = c->h_q.p;
+    }
+    CU_TRY(cudaMemcpyAsync(c->q_in.p, q_src, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
+  }
   if (mask) CU_TRY(cudaMemcpyAsync(c->mask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, st));
   if (filter_json) {
     // the filter is evaluated on the device into a bitmask over slots: host metadata is never walked
@@ -1376,7 +1410,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     CU_TRY(launch_eval_filter(prog, h->meta_dptrs.as<const uint32_t*>(), h->n_slots, c->mask.as<uint64_t>(), st));
     ++h->n_launch;
   }
-  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), kmax,
+  SearchArgs a{d_queries, q, c->ks.as<uint32_t>(), kmax,
                (mask || filter_json) ? c->mask.as<uint64_t>() : nullptr, mask_bits,
                reinterpret_cast<uint64_t*>(blk + off_ids), reinterpret_cast<float*>(blk + off_dist),
                reinterpret_cast<uint32_t*>(blk + off_cnt), (int64_t)kout};
@@ -1389,12 +1423,40 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     for (size_t w = 0; w < full; w += 64, ++seen) pc += __builtin_popcountll(mask[w]);
     a.mask_popcount = seen ? (int64_t)((double)pc / (double)(seen * 64) * (double)mask_bits) : 0;
   }
+  if (zero_copy) {
+    char* hb0 = c->h_out.as<char>();
+    a.h_ks_in = c->h_ks.as<uint32_t>();
+    a.h_ctrl = reinterpret_cast<uint32_t*>(hb0);
+    a.h_out_counts = reinterpret_cast<uint32_t*>(hb0 + off_cnt);
+    a.h_out_dist = reinterpret_cast<float*>(hb0 + off_dist);
+    a.h_out_ids = reinterpret_cast<uint64_t*>(hb0 + off_ids);
+    a.done_seq = ++c->zc_seq ? c->zc_seq : ++c->zc_seq;  // never 0
+    reinterpret_cast<volatile uint32_t*>(hb0)[kCtrlDoneWord] = 0;
+  }
   rc = enqueue_search(h, c, a, st);
   c->ctrl_dev = nullptr;
   if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
-  CU_TRY(cudaMemcpyAsync(c->h_out.p, blk, blk_bytes, cudaMemcpyDeviceToHost, st));
-  const double t_enq = host_trace ? now_us() : 0.0;
-  CU_TRY(cudaStreamSynchronize(st));
+  bool published = false;
+  double t_enq = host_trace ? now_us() : 0.0;
+  if (c->zc_pending) {
+    // the scan's fused tail publishes the results itself: poll its completion word (bounded; a search that takes
+    // longer than that is not latency-bound, and the ordinary copy below returns the same block)
+    const volatile uint32_t* done = reinterpret_cast<const volatile uint32_t*>(c->h_out.p) + kCtrlDoneWord;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t it = 1;; ++it) {
+      if (*done == a.done_seq) { published = true; break; }
+      if ((it & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(2000)) break;
+#if defined(__x86_64__) || defined(__i386__)
+      __builtin_ia32_pause();
+#endif
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+  }
+  if (!published) {
+    CU_TRY(cudaMemcpyAsync(c->h_out.p, blk, blk_bytes, cudaMemcpyDeviceToHost, st));
+    if (host_trace) t_enq = now_us();
+    CU_TRY(cudaStreamSynchronize(st));
+  }
   const double t_sync = host_trace ? now_us() : 0.0;
   prof_collect(h, c);
   const char* hb = c->h_out.as<char>();
@@ -1893,6 +1955,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "hits") h->opt_hits = (int)value;
   else if (n == "scan_qt") h->opt_scan_qt = (int)value;
   else if (n == "fused_tail") h->opt_fused_tail = (int)value;
+  else if (n == "zero_copy") h->opt_zero_copy = (int)value;
   else if (n == "grid") h->opt_grid = (int)value;
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;

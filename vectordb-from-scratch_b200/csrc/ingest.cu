@@ -94,6 +94,7 @@ __global__ void prep_queries_kernel(const PrepQueriesParams p) {
   if (qi >= p.q) return;
   const float* src = p.q_in + (size_t)qi * p.d;
   float* dst = p.q32 + (size_t)qi * p.dpad;
+  if (p.ks_in && lane == 0) p.ks_out[qi] = p.ks_in[qi];
   float* mine = p.use_smem ? sq + (size_t)warp * p.dpad : nullptr;
   float m = 0.f;
   for (int c0 = 0; c0 < p.dpad; c0 += 32 * 8) {  // 8 independent loads in flight per lane

@@ -66,7 +66,14 @@ struct ScanParams {
   uint32_t* done_ctr;       // zeroed per call
   const uint32_t* ks;       // per-query k
   uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
+  // latency mode: the tail also stores the results, a copy of the call's control block and finally `done_seq`
+  // into PINNED HOST memory (same [kstride] layout), so the host neither copies nor synchronises: it polls the word
+  uint32_t* h_ctrl;         // host copy of the control block (kCtrlWords words) + the done word, or null
+  const uint32_t* d_ctrl;   // the device control block
+  uint64_t* h_out_ids; float* h_out_dist; uint32_t* h_out_counts;
+  uint32_t done_seq;
 };
+constexpr int kCtrlWords = 12, kCtrlDoneWord = 15;  // layout of the 64-byte control area of a host result block
 size_t scan_fused_tail_bytes(int grid, int K, int dpad);
 // eligible (live and unmasked) slots -> list[0..*count)
 cudaError_t launch_compact_eligible(const IndexView& iv, const MaskView& mask, uint32_t* list, uint32_t* count,
@@ -93,6 +100,9 @@ struct PrepQueriesParams {
   float* qmaxabs;      // [1] max |q| over the batch (for the common fp16 scale)
   int q, qpad, d, dpad, dpad16;
   int use_smem;        // set by launch_prep_queries
+  // latency mode (small host searches): q_in and ks_in are PINNED HOST memory read over PCIe by this kernel, which
+  // also forwards the per-query k to device memory -- no copy-engine operation precedes the search
+  const uint32_t* ks_in; uint32_t* ks_out;  // or null
 };
 cudaError_t launch_prep_queries(const PrepQueriesParams& p, cudaStream_t st);
 

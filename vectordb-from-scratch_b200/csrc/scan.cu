@@ -111,10 +111,19 @@ __device__ __noinline__ void scan_fused_tail(const ScanParams& p, int nq, const 
     if (tid == 0) { s_n = 0; s_m = 0; s_bound = kKeySentinel - 1; }
     __syncthreads();
     uint32_t nv = 0;
-    for (int i = tid; i < LK; i += NT) {
-      const uint64_t k64 = __ldcg(cand + i);  // written by the other CTAs: read at L2
-      keys[i] = k64;
-      nv += k64 != kKeySentinel;
+    for (int i0 = 0; i0 < LK; i0 += NT * 4) {  // four independent L2 round trips in flight per thread
+      uint64_t kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT + tid;
+        kk[u] = i < LK ? __ldcg(cand + i) : kKeySentinel;  // written by the other CTAs: read at L2
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * NT + tid;
+        if (i < LK) keys[i] = kk[u];
+        nv += kk[u] != kKeySentinel;
+      }
     }
     for (int o = 16; o > 0; o >>= 1) nv += __shfl_xor_sync(0xffffffffu, nv, o);
     if (lane == 0 && nv) atomicAdd(&s_n, nv);
@@ -174,10 +183,28 @@ __device__ __noinline__ void scan_fused_tail(const ScanParams& p, int nq, const 
       if (below < kq) {
         p.out_ids[(size_t)qg * p.kstride + below] = iv.ids[(uint32_t)(key & 0xffffffffu)];
         p.out_dist[(size_t)qg * p.kstride + below] = key_f32((uint32_t)(key >> 32));
+        if (p.h_ctrl) {
+          p.h_out_ids[(size_t)qg * p.kstride + below] = iv.ids[(uint32_t)(key & 0xffffffffu)];
+          p.h_out_dist[(size_t)qg * p.kstride + below] = key_f32((uint32_t)(key >> 32));
+        }
       }
     }
-    if (tid == 0) p.out_counts[qg] = kq;
+    if (tid == 0) {
+      p.out_counts[qg] = kq;
+      if (p.h_ctrl) p.h_out_counts[qg] = kq;
+    }
     __syncthreads();
+  }
+  if (p.h_ctrl) {
+    // latency mode: results are in host memory; publish the control block, then the word the host polls
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+      const volatile uint32_t* dc = p.d_ctrl;  // flags raised by the other CTAs precede their tickets
+      for (int w = 0; w < kCtrlWords; ++w) p.h_ctrl[w] = dc[w];
+      __threadfence_system();
+      *reinterpret_cast<volatile uint32_t*>(p.h_ctrl + kCtrlDoneWord) = p.done_seq;
+    }
   }
 }
 
