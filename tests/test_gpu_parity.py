@@ -250,6 +250,54 @@ def test_error_semantics():
     assert empty.search([1.0, 2.0], 3) == [] and empty.is_empty()
 
 
+@pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot"])
+def test_small_search_fused_tail_and_latency_mode_equal_the_separate_kernels(metric):
+    """Small plain searches finish inside the scan kernel (fused tail) and, from the host, without copies or a
+    stream synchronisation (latency mode).  Both must return what the separate select / rerank kernels and the
+    copying path return -- and the oracle's answer -- including k > n, per-query k and the error flags."""
+    n, d = 7000, 200
+    rows = oracle.gen_rows(71, 0, n, d, 1)
+    queries = oracle.gen_rows(72, 0, 4, d, 1)
+    ks = np.array([10, 1, 56, 33], dtype=np.uint32)
+    idx = build(metric, rows, flags=1)
+    for i in (0, 17, 6999):
+        idx.remove(i)
+    live = np.ones(n, dtype=bool)
+    live[[0, 17, 6999]] = False
+    ids = np.arange(n, dtype=np.uint64)
+    exp = oracle.search_batch(metric, rows[live], queries, ks, ids=ids[live], threads=4)
+    outs = []
+    for fused, zc in ((1, 1), (1, 0), (0, 1), (0, 0)):
+        idx.set_option("fused_tail", fused)
+        idx.set_option("zero_copy", zc)
+        for nq in (4, 1, 3):
+            got_ids, got_d, cnt = idx.search_arrays(queries[:nq], ks[:nq])
+            for i in range(nq):
+                assert cnt[i] == len(exp[i][0])
+                assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], exp[i][0], exp[i][1],
+                                    ctx=f"{metric} fused={fused} zc={zc} nq={nq} q{i}")
+        outs.append(idx.search_arrays(queries, ks))
+    for o in outs[1:]:
+        for a, b in zip(outs[0], o):
+            assert np.array_equal(a, b)
+    # k > n on a tiny index, and the flags raised inside the fused tail
+    idx.set_option("fused_tail", 1)
+    idx.set_option("zero_copy", 1)
+    tiny = build(metric, rows[:5], flags=1)
+    res = tiny.search(queries[0], 40)
+    e_ids, e_d = oracle.search_batch(metric, rows[:5], queries[:1], 40, threads=1)[0]
+    assert [i for i, _ in res] == [int(x) for x in e_ids]
+    assert np.array_equal(np.array([x for _, x in res], np.float32), e_d)
+    if metric == "cosine":
+        with pytest.raises(gfi.InvalidVector):
+            idx.search(np.zeros(d, np.float32), 5)
+    bad = queries[0].copy()
+    bad[3] = np.nan
+    with pytest.raises(gfi.NaNDistance):
+        idx.search(bad, 5)
+    assert idx.search(queries[1], 3)  # the handle is usable after an error
+
+
 # ---------------------------------------------------------------- filters
 @pytest.mark.parametrize("sel", [0.01, 0.5])
 def test_mask_pushdown_and_post_filter(sel):
