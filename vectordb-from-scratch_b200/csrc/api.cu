@@ -1053,6 +1053,19 @@ int32_t gfi_create(gfi_index** out, int32_t metric, int64_t dim, int32_t device,
   CU_TRY(h->counters.ensure(16));
   CU_TRY(cudaMemset(h->counters.p, 0, 16));
   *out = h.release();
+  // experiment aid for native probes that cannot call gfi_set_option: GFI_OPTS="name=value,name=value"
+  if (const char* env = getenv("GFI_OPTS")) {
+    std::string e(env);
+    size_t at = 0;
+    while (at < e.size()) {
+      size_t end = e.find(',', at);
+      if (end == std::string::npos) end = e.size();
+      const std::string kv = e.substr(at, end - at);
+      const size_t eq = kv.find('=');
+      if (eq != std::string::npos) gfi_set_option(*out, kv.substr(0, eq).c_str(), atoll(kv.c_str() + eq + 1));
+      at = end + 1;
+    }
+  }
   return GFI_OK;
 }
 
