@@ -235,9 +235,9 @@ struct gfi_index {
     int32_t rc = 0; std::string err; int64_t exp = 0, act = 0;
     bool done = false, lead = false;
     std::vector<CoReq*> batch;  // filled for the request promoted to leader
+    std::condition_variable cv;  // one per request: the leader wakes exactly the requests it finished and its successor
   };
   std::mutex co_mu;
-  std::condition_variable co_cv;
   bool co_busy = false;
   std::vector<CoReq*> co_pending;
   std::atomic<int64_t> n_co_batches{0}, n_co_requests{0};
@@ -1649,7 +1649,7 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
     std::unique_lock<std::mutex> lk(h->co_mu);
     if (h->co_busy) {
       h->co_pending.push_back(&me);
-      h->co_cv.wait(lk, [&] { return me.done || me.lead; });
+      me.cv.wait(lk, [&] { return me.done || me.lead; });
       if (me.done) {
         if (me.rc != GFI_OK) { tl_error = me.err; tl_expected = me.exp; tl_actual = me.act; }
         return me.rc;
@@ -1664,8 +1664,10 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   run_coalesced(h, batch);
   {
     std::lock_guard<std::mutex> lk(h->co_mu);
+    // (notified while the lock is held: a woken request cannot return -- and destroy its CoReq -- before the lock is
+    // released, and nobody else is woken: with one shared condition variable every hand-over woke all waiting clients)
     for (auto* r : batch)
-      if (r != &me) r->done = true;
+      if (r != &me) { r->done = true; r->cv.notify_one(); }
     if (h->co_pending.empty()) {
       h->co_busy = false;
     } else {
@@ -1676,9 +1678,9 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
       next->batch.assign(h->co_pending.begin(), h->co_pending.begin() + (long)take);
       h->co_pending.erase(h->co_pending.begin(), h->co_pending.begin() + (long)take);
       next->lead = true;
+      next->cv.notify_one();
     }
   }
-  h->co_cv.notify_all();
   if (me.rc != GFI_OK) { tl_error = me.err; tl_expected = me.exp; tl_actual = me.act; }
   return me.rc;
 }
