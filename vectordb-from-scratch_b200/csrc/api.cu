@@ -24,6 +24,7 @@
 #include <mutex>
 #include <shared_mutex>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -1459,6 +1460,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     for (uint32_t it = 1;; ++it) {
       if (*done == a.done_seq) { published = true; break; }
       if ((it & 1023u) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(2000)) break;
+      if (it >= 4096 && (it & 255u) == 0) std::this_thread::yield();  // more clients than cores: let them enqueue
 #if defined(__x86_64__) || defined(__i386__)
       __builtin_ia32_pause();
 #endif
