@@ -592,6 +592,64 @@ __global__ void seed_finalize_kernel(const SeedFinalizeParams p) {
   if (lane == 0) p.thresh[qi] = cur;
 }
 
+// The same with a whole block per query, for small batches: a single query's seed list is up to 64K scores
+// (10M rows, k = 10), which one warp walks in ~30 us.  Eight warps take strided shares, their per-lane lists are
+// merged lane-wise by warp 0, which then pops as above.
+__global__ void __launch_bounds__(256) seed_finalize_block_kernel(const SeedFinalizeParams p) {
+  griddep_wait();
+  if (p.skip && *p.skip) return;
+  __shared__ float s_sd[8][kSeedR][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int qi = blockIdx.x;
+  const float kInf = __int_as_float(0x7f800000);
+  const int64_t total = p.seed_tiles * 2 * kSeedR;
+  const float* s = p.seeds + (size_t)qi * total;
+  float sd[kSeedR];
+#pragma unroll
+  for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
+  auto insert = [&](float v) {
+    if (v < sd[kSeedR - 1]) {  // false for NaN
+      sd[kSeedR - 1] = v;
+#pragma unroll
+      for (int j = kSeedR - 1; j > 0; --j) {
+        const float lo = fminf(sd[j - 1], sd[j]), hi = fmaxf(sd[j - 1], sd[j]);
+        sd[j - 1] = lo;
+        sd[j] = hi;
+      }
+    }
+  };
+  for (int64_t i0 = (int64_t)warp * 256; i0 < total; i0 += 8 * 256) {
+    float vv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int64_t i = i0 + 32 * u + lane;
+      vv[u] = i < total ? __ldg(s + i) : kInf;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) insert(vv[u]);
+  }
+#pragma unroll
+  for (int j = 0; j < kSeedR; ++j) s_sd[warp][j][lane] = sd[j];
+  __syncthreads();
+  if (warp != 0) return;
+  for (int w = 1; w < 8; ++w)
+#pragma unroll
+    for (int j = 0; j < kSeedR; ++j) insert(s_sd[w][j][lane]);
+  float cur = kInf;
+  for (int r = 0; r < p.rank; ++r) {
+    float m = sd[0];
+    for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    cur = m;
+    const unsigned owners = __ballot_sync(0xffffffffu, sd[0] == m);
+    if (owners && lane == __ffs(owners) - 1) {  // pop this lane's head
+#pragma unroll
+      for (int j = 0; j < kSeedR - 1; ++j) sd[j] = sd[j + 1];
+      sd[kSeedR - 1] = kInf;
+    }
+  }
+  if (lane == 0) p.thresh[qi] = cur;
+}
+
 }  // namespace
 
 cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const void* tmap_q_host, int grid,
@@ -629,6 +687,8 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
 
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st) {
   if (p.q <= 0) return cudaSuccess;
+  if (p.q <= 64 && p.seed_tiles * 2 * kSeedR >= 4096)  // few queries with long seed lists: a block per query
+    return launch_pdl(seed_finalize_block_kernel, dim3(p.q), dim3(256), 0, st, p);
   const int blocks = (p.q * 32 + 255) / 256;
   return launch_pdl(seed_finalize_kernel, dim3(blocks), dim3(256), 0, st, p);
 }
