@@ -1,5 +1,6 @@
-// exact.cuh -- the reference's arithmetic, in ONE place: every distance that leaves the library is produced by
-// these two functions (K3 rerank, the fused tail of the scan kernel, K6 pair scoring use them).
+// exact.cuh -- the reference's arithmetic, in ONE place: every distance that leaves a search is produced by these
+// two functions (K3 rerank and the fused tail of the scan kernel; K6 pair scoring shares exact_step and keeps a
+// per-pair status instead of the call-wide flags).
 #pragma once
 #include "common.cuh"
 #include "kernels.h"

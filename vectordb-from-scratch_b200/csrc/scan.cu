@@ -16,7 +16,8 @@
 //     stage is processed, so no global-memory latency sits on a warp's per-row critical path;
 //   * a row touches the per-warp sorted list only when it beats the list's current K-th key.
 // The scores computed here only rank candidates; the K survivors per CTA are re-scored with the
-// reference's exact arithmetic in select_rerank.cu.
+// reference's exact arithmetic in select_rerank.cu -- or, for small single-pass searches, by this
+// kernel's own last CTA (scan_fused_tail below), which then also emits the results.
 #include <algorithm>
 
 #include "common.cuh"
