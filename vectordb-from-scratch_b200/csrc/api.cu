@@ -697,7 +697,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     R = nseg == 1 ? 16 * std::max(1, std::min(4, kTargetStageBytes / (16 * h->dpad * 4))) : 16;
   }
   const int stage_floats = R * (nseg == 1 ? h->dpad : segf);
-  // filtered or heavily tombstoned scans gather only the eligible rows (one bulk copy per row)
+  // filtered or heavily tombstoned scans gather only the eligible rows (one bulk copy per run of adjacent eligible rows)
   const bool gather = a.d_mask != nullptr || h->n_live * 10 < h->n_slots * 9;
   // queries per pass: as many as shared memory allows next to a ring of at least 3 stages
   int QT = 4, nstages = 0;

@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) scan_topk_kernel(const __grid
   __syncthreads();
 
   // gather mode (filtered / tombstoned scans): rows are taken from a compacted list of eligible slots,
-  // one bulk copy per row, so ineligible rows cost no bandwidth at all
+  // one bulk copy per run of adjacent slots, so ineligible rows cost no bandwidth at all
   const uint32_t* glist = p.gather_list;
   const uint32_t n = glist ? *p.gather_count : (uint32_t)iv.n_slots;
   if (glist && p.elig_out && blockIdx.x == 0 && tid == 0) *p.elig_out = n + 1u;
