@@ -1,0 +1,116 @@
+"""Round-2 regression tests for the host runtime of libgfi (ADVICE r1 / VERDICT r1 items), through the C ABI."""
+import numpy as np
+import pytest
+
+import oracle
+import vectordb_from_scratch_b200 as gfi
+from vectordb_from_scratch_b200 import DistanceMetric as DM
+from helpers import assert_topk_matches
+
+pytestmark = pytest.mark.gpu
+
+
+def test_rows_added_after_a_metadata_sync_read_as_no_metadata():
+    """gfi_add / gfi_add_generated after the last metadata sync grew the slot array but not the
+    device columns; a filtered search then read past them.  Rows without metadata must behave like the reference's
+    `metadata.get(id) = None` rows: eq/exists false, ne true (storage.rs:62-70)."""
+    n0, n1, d, k = 3000, 5000, 24, 8
+    rows = oracle.gen_rows(41, 0, n0 + n1, d, 1)
+    idx = gfi.GpuFlatIndex(DM.Euclidean)
+    idx.add_batch(np.arange(n0, dtype=np.uint64), rows[:n0])
+    for i in range(n0):
+        idx.set_metadata(i, {"color": "red" if i % 2 else "blue"})
+    q = oracle.gen_rows(42, 0, 2, d, 1)
+    ids, dist, cnt = idx.search_filtered(q, k, {"op": "eq", "field": "color", "value": "red"})  # syncs the columns
+    assert all(int(i) % 2 == 1 for i in ids[0, :cnt[0]])
+    # plain adds and generated rows: no gfi_set_metadata call for them
+    idx.add_batch(np.arange(n0, n0 + 1000, dtype=np.uint64), rows[n0:n0 + 1000])
+    idx.add_generated(41, n0 + 1000, n1 - 1000, 1, n0 + 1000)
+    has_md = np.arange(n0 + n1) < n0
+    red = has_md & (np.arange(n0 + n1) % 2 == 1)
+    cases = [({"op": "eq", "field": "color", "value": "red"}, red),
+             ({"op": "ne", "field": "color", "value": "red"}, ~red),
+             ({"op": "exists", "field": "color"}, has_md),
+             ({"op": "and", "filters": [{"op": "ne", "field": "color", "value": "blue"},
+                                        {"op": "ne", "field": "color", "value": "red"}]}, ~has_md)]
+    for flt, elig in cases:
+        ids, dist, cnt = idx.search_filtered(q, k, flt)
+        exp = oracle.search_batch("euclidean", rows, q, k, eligible=elig, threads=4)
+        for i, (eids, ed) in enumerate(exp):
+            assert cnt[i] == len(eids), (flt, cnt[i], len(eids))
+            assert_topk_matches(ids[i, :cnt[i]], dist[i, :cnt[i]], eids, ed, ctx=str(flt))
+
+
+def test_an_emptied_index_takes_a_new_dimension():
+    """latch dim 3, remove every row, add dim-5 rows, search with a dim-5 query: FlatIndex::search
+    returns those rows (it has no dimension of its own, flat_index.rs:38-41,52-65)."""
+    idx = gfi.GpuFlatIndex(DM.Euclidean)
+    idx.add(0, [1.0, 2.0, 3.0])
+    idx.add(1, [0.0, 0.0, 1.0])
+    assert idx.search([1.0, 2.0, 3.0], 1)[0] == (0, 0.0)
+    idx.remove(0)
+    idx.remove(1)
+    assert idx.len() == 0
+    rows = oracle.gen_rows(7, 0, 300, 5, 0)
+    idx.add_batch(np.arange(10, 310, dtype=np.uint64), rows)
+    assert idx.dim() == 5 and idx.len() == 300
+    got = idx.search(rows[17], 3)
+    exp_ids, exp_d = oracle.search_batch("euclidean", rows, rows[17:18], 3, ids=np.arange(10, 310, dtype=np.uint64))[0]
+    assert [g[0] for g in got] == list(exp_ids) and got[0] == (27, 0.0)
+    assert np.array_equal(np.float32([g[1] for g in got]), exp_d)
+    assert np.array_equal(idx.get_vector(27), rows[17]) and idx.get_vector(0) is None
+    # rows of a second dimension recorded while others were live, which then disappear: loud, not an empty Ok
+    idx2 = gfi.GpuFlatIndex(DM.Euclidean)
+    idx2.add(0, [1.0, 2.0])
+    idx2.add(1, [1.0, 2.0, 3.0])
+    idx2.remove(0)
+    with pytest.raises(gfi.IndexError_):
+        idx2.search([1.0, 2.0, 3.0], 1)
+    idx2.add(1, [1.0, 2.0, 3.0])  # re-added now that nothing else is stored: the index takes its dimension
+    assert idx2.search([1.0, 2.0, 3.0], 1)[0] == (1, 0.0) and idx2.len() == 1
+
+
+def test_len_counts_a_staged_overwrite_once():
+    """FlatIndex::len after add(id) of an existing id stays the same (HashMap::insert)."""
+    idx = gfi.GpuFlatIndex(DM.DotProduct)
+    idx.add(5, [1.0, 0.0])
+    idx.add(6, [0.0, 1.0])
+    idx.flush()
+    idx.add(5, [2.0, 0.0])      # staged overwrite of a flushed id
+    idx.add(9, [3.0, 3.0])      # staged new id
+    assert idx.len() == 3
+    assert idx.search([1.0, 0.0], 1)[0] == (9, -3.0)
+    assert idx.len() == 3
+
+
+def test_device_search_flags_are_sticky_until_collected():
+    """several gfi_search_device calls before one gfi_search_status: an error raised by ANY of them is
+    reported (the control block used to be cleared by every call, so only the last search's flags survived)."""
+    torch = pytest.importorskip("torch")
+    n, d, k = 20000, 64, 5
+    idx = gfi.GpuFlatIndex(DM.Cosine, dim=d)
+    idx.add_generated(3, 0, n, 1, 0)
+    dev = torch.device("cuda", 0)
+    good = torch.from_numpy(oracle.gen_rows(4, 0, 2, d, 1)).to(dev)
+    bad = good.clone()
+    bad[1] = 0.0  # zero-norm query: InvalidVector
+    ks = torch.full((2,), k, dtype=torch.int32, device=dev)
+    oi = torch.zeros((2, k), dtype=torch.int64, device=dev)
+    od = torch.zeros((2, k), dtype=torch.float32, device=dev)
+    oc = torch.zeros((2,), dtype=torch.int32, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    idx.search_device(bad.data_ptr(), 2, ks.data_ptr(), k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), k,
+                      stream=s1.cuda_stream)
+    # a second search on ANOTHER stream is ordered behind the first (shared workspace) and must not clear its error
+    idx.search_device(good.data_ptr(), 2, ks.data_ptr(), k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), k,
+                      stream=s2.cuda_stream)
+    with pytest.raises(gfi.InvalidVector):
+        idx.search_status()
+    idx.search_device(good.data_ptr(), 2, ks.data_ptr(), k, oi.data_ptr(), od.data_ptr(), oc.data_ptr(), k,
+                      stream=s2.cuda_stream)
+    idx.search_status()  # collected and clean again
+    rows = oracle.gen_rows(3, 0, n, d, 1)
+    exp = oracle.search_batch("cosine", rows, good.cpu().numpy(), k, threads=4)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(oi[i].cpu().numpy().astype(np.uint64), od[i].cpu().numpy(), eids, ed)

@@ -119,6 +119,8 @@ struct SearchCtx {
   DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
   void* ctrl_dev = nullptr;  // control block of the search being enqueued (inside out_blk or `ctrl`)
   bool pending_status = false;  // device search issued, status not yet collected
+  cudaStream_t last_stream = nullptr;  // stream of the uncollected device search(es)
+  cudaEvent_t order_ev = nullptr;      // orders a device search on a new stream behind the uncollected ones
   int64_t auto_tensor_q = 0;     // queries of the search being enqueued that took the tensor path by the cost model
   // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
   struct EvPair { cudaEvent_t a, b; int kind; };
@@ -133,6 +135,8 @@ struct SearchCtx {
     for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
     evs.clear();
     ev_used = 0;
+    if (order_ev) cudaEventDestroy(order_ev);
+    order_ev = nullptr;
     if (stream) cudaStreamDestroy(stream);
     stream = nullptr;
   }
@@ -199,6 +203,7 @@ struct gfi_index {
   std::vector<DevBuf> meta_dcols;
   DevBuf meta_dptrs;
   bool meta_dirty = false;
+  int64_t meta_synced_slots = 0;  // slots the device columns cover (rows beyond read as "no metadata")
   std::unordered_map<uint64_t, std::vector<std::pair<int, uint32_t>>> meta_pending;
 
   // staging (pinned)
@@ -234,7 +239,7 @@ struct gfi_index {
     const float* queries; int64_t q, dim; const uint32_t* ks;
     uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
     int32_t rc = 0; std::string err; int64_t exp = 0, act = 0;
-    bool done = false, lead = false;
+    bool done = false, lead = false, answered = false;
     std::vector<CoReq*> batch;  // filled for the request promoted to leader
     std::condition_variable cv;  // one per request: the leader wakes exactly the requests it finished and its successor
   };
@@ -482,6 +487,7 @@ int32_t flush_locked(gfi_index* h) {
     if ((rc = ingest_slots(h, slot0, n, false, 0, 0, 0)) != GFI_OK) return rc;
     CU_TRY(cudaStreamSynchronize(h->ingest_stream));
     h->st_n = 0;
+    if (!h->meta_values.empty()) h->meta_dirty = true;  // the per-field columns must grow with the slot array
     if ((rc = read_counters(h)) != GFI_OK) return rc;
   }
   if ((rc = upload_live(h)) != GFI_OK) return rc;
@@ -588,6 +594,7 @@ struct SearchArgs {
   uint32_t done_seq = 0;
   bool mask_by_slot = false;  // the mask is indexed by slot (device-evaluated filter), not by internal id
   int64_t mask_popcount = -1;  // eligible bits of a host mask when known (cost model), else -1
+  bool keep_flags = false;     // an earlier search of this context has not been collected yet: its error flags stay
 };
 
 // Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
@@ -651,7 +658,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   CU_TRY(c->sel_keys.ensure((size_t)q * 1024 * 8));
   CU_TRY(c->sel_info.ensure((size_t)q * sizeof(SelInfo)));
   if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
-  if (first_chunk) CU_TRY(cudaMemsetAsync(c->ctrl_dev, 0, sizeof(Ctrl), st));
+  if (first_chunk) {
+    // (the flags word is the first of the block; it is sticky across uncollected device searches)
+    const size_t skip = a.keep_flags ? sizeof(uint32_t) : 0;
+    CU_TRY(cudaMemsetAsync(static_cast<char*>(c->ctrl_dev) + skip, 0, sizeof(Ctrl) - skip, st));
+  }
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(c->ctrl_dev);
 
   PrepQueriesParams pq{};
@@ -1012,7 +1023,15 @@ int32_t precheck(gfi_index* h, int64_t qdim, bool* empty) {
     tl_actual = h->dim;
     return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
   }
-  if (h->n_live == 0) *empty = true;  // only odd rows of the right dimension... cannot happen, be safe
+  if (h->n_live == 0) {
+    // Rows of a second dimension were added while rows of the latched dimension were live (they are recorded, not
+    // stored), and the latter have all been removed since: FlatIndex::search would now return the former.  That
+    // state cannot be served from the GPU copy -- say so instead of answering with an empty Ok.
+    if (!h->odd_dim_rows.empty())
+      return fail(GFI_ERR_INDEX, "rows whose dimension differs from the index dimension are not stored on the GPU; "
+                                 "re-add them now that the index holds no other rows");
+    *empty = true;
+  }
   return GFI_OK;
 }
 
@@ -1090,8 +1109,15 @@ int32_t gfi_destroy(gfi_index* h) {
 int64_t gfi_len(const gfi_index* h) {
   if (!h) return 0;
   std::shared_lock<std::shared_mutex> g(h->mu);
-  // staged rows that overwrite existing ids are resolved at flush; count them pessimistically unique
-  return h->n_live + h->st_n + (int64_t)h->odd_dim_rows.size();
+  // staged rows that overwrite an id already stored replace it at flush (HashMap::insert): count them once
+  int64_t staged_new = 0;
+  const uint64_t* sid = h->st_ids.as<uint64_t>();
+  for (int64_t i = 0; i < h->st_n; ++i) {
+    uint32_t slot;
+    if (!(h->any_id && sid[i] <= h->max_id_seen && lookup_slot(h, sid[i], &slot)) && !h->odd_dim_rows.count(sid[i]))
+      ++staged_new;
+  }
+  return h->n_live + staged_new + (int64_t)h->odd_dim_rows.size();
 }
 int32_t gfi_metric(const gfi_index* h) { return h ? h->metric : -1; }
 int64_t gfi_dim(const gfi_index* h) { return h ? h->dim : 0; }
@@ -1109,6 +1135,42 @@ static int32_t add_rows_locked(gfi_index* h, const uint64_t* ids, const float* r
   if (h->dim == 0 && n > 0) {
     if (dim <= 0) return fail(GFI_ERR_INDEX, "zero-dimensional vectors are not supported");
     latch_dim(h, dim);
+  }
+  bool odd_covered = true;  // every recorded odd-dimension row is re-added by this very call
+  if (dim != h->dim && !h->odd_dim_rows.empty()) {
+    std::unordered_map<uint64_t, bool> incoming;
+    for (int64_t i = 0; i < n; ++i) incoming[ids[i]] = true;
+    for (auto& kv : h->odd_dim_rows) odd_covered = odd_covered && incoming.count(kv.first);
+  }
+  if (dim != h->dim && n > 0 && dim > 0 && h->n_live == 0 && odd_covered) {
+    // nothing is stored any more (every row was removed): the index takes the new dimension, as an empty FlatIndex
+    // would (it has no dimension of its own)
+    int32_t rc = flush_locked(h);
+    if (rc != GFI_OK) return rc;
+    if (h->n_live == 0) {
+      if ((rc = set_device(h)) != GFI_OK) return rc;
+      CU_TRY(cudaDeviceSynchronize());  // no search may still be reading the old arrays
+      for (DevBuf* b : {&h->x32, &h->x16, &h->ids, &h->norm, &h->sumsq, &h->coef, &h->live, &h->rowflags}) b->release();
+      h->cap = h->n_slots = 0;
+      h->runs.clear();
+      h->h_live.clear();
+      h->live_dirty_lo = h->live_dirty_hi = -1;
+      h->ids_identity = true;
+      h->needs_reorder = false;
+      h->any_id = false;
+      h->max_id_seen = 0;
+      h->st_rows.release();
+      h->st_ids.release();
+      h->st_cap = 0;
+      for (auto& col : h->meta_cols) col.clear();
+      h->meta_synced_slots = 0;
+      if (!h->meta_values.empty()) h->meta_dirty = true;
+      ++h->layout_gen;
+      CU_TRY(cudaMemset(h->counters.p, 0, 16));
+      h->zero_rows_ever = h->unsafe_rows_ever = 0;
+      h->xnorm_max = 0.f;
+      latch_dim(h, dim);
+    }
   }
   if (dim != h->dim) {
     // FlatIndex::add never checks dimensions (flat_index.rs:38-41); remember the row so that searches
@@ -1243,6 +1305,7 @@ int32_t gfi_add_generated(gfi_index* h, uint32_t seed, uint64_t first_row, int64
   register_ids(h, nullptr, first_id, n, slot0);
   if ((rc = ingest_slots(h, slot0, n, true, seed, first_row, kind)) != GFI_OK) return rc;
   CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+  if (!h->meta_values.empty()) h->meta_dirty = true;  // rows without metadata still need (absent) column entries
   if ((rc = read_counters(h)) != GFI_OK) return rc;
   return upload_live(h);
 }
@@ -1321,20 +1384,23 @@ static int32_t sync_metadata_locked(gfi_index* h) {
   if (nf) CU_TRY(cudaMemcpyAsync(h->meta_dptrs.p, ptrs.data(), nf * sizeof(void*), cudaMemcpyHostToDevice, h->ingest_stream));
   CU_TRY(cudaStreamSynchronize(h->ingest_stream));
   h->meta_dirty = false;
+  h->meta_synced_slots = h->n_slots;
   return GFI_OK;
 }
 
-static int32_t ensure_flushed(gfi_index* h) {
+static int32_t ensure_flushed(gfi_index* h, bool with_metadata = false) {
   bool need;
   {
     std::shared_lock<std::shared_mutex> g(h->mu);
-    need = h->st_n > 0 || h->live_dirty_lo >= 0 || h->needs_reorder;
+    need = h->st_n > 0 || h->live_dirty_lo >= 0 || h->needs_reorder || (with_metadata && h->meta_dirty);
   }
   if (!need) return GFI_OK;
   std::unique_lock<std::shared_mutex> g(h->mu);
   int32_t rc = flush_locked(h);
   if (rc != GFI_OK) return rc;
-  if (h->needs_reorder) return compact_locked(h);
+  if (h->needs_reorder && (rc = compact_locked(h)) != GFI_OK) return rc;
+  // (after a compaction, which moves rows and re-marks the columns dirty, never before)
+  if (with_metadata) return sync_metadata_locked(h);
   return GFI_OK;
 }
 
@@ -1344,13 +1410,15 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (q < 0 || (q > 0 && (!queries || !ks || !out_counts))) return fail(GFI_ERR_INDEX, "bad arguments");
   if (q == 0) return GFI_OK;
-  int32_t rc = ensure_flushed(h);
-  if (rc != GFI_OK) return rc;
-  if (filter_json && h->meta_dirty) {
-    std::unique_lock<std::shared_mutex> gu(h->mu);
-    if ((rc = sync_metadata_locked(h)) != GFI_OK) return rc;
+  int32_t rc;
+  std::shared_lock<std::shared_mutex> g(h->mu, std::defer_lock);
+  for (;;) {
+    if ((rc = ensure_flushed(h, filter_json != nullptr)) != GFI_OK) return rc;
+    g.lock();
+    // a writer may have slipped in between the two locks; a filtered search needs columns that match the layout
+    if (!(filter_json && h->meta_dirty)) break;
+    g.unlock();
   }
-  std::shared_lock<std::shared_mutex> g(h->mu);
   ++h->n_search;
   h->n_queries += q;
   bool empty;
@@ -1378,7 +1446,11 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   const double t_begin = host_trace ? now_us() : 0.0;
   SearchCtx* c = acquire_ctx(h);
   if (!c) return fail(GFI_ERR_INDEX, "cannot create a CUDA stream");
-  struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
+  // (a context goes back to the pool only with an idle stream: every early error return below drains it first)
+  struct Releaser {
+    gfi_index* h; SearchCtx* c; bool in_flight;
+    ~Releaser() { if (in_flight) cudaStreamSynchronize(c->stream); release_ctx(h, c); }
+  } rel{h, c, false};
   cudaStream_t st = c->stream;
   const uint32_t kout = std::min<uint32_t>(kmax, (uint32_t)std::min<int64_t>(kstride, 1 << 20));
   if (filter_json) { mask = nullptr; mask_bits = h->n_slots; }
@@ -1404,6 +1476,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   c->zc_pending = false;
   const float* d_queries = c->q_in.as<float>();
   memcpy(c->h_ks.p, ks, (size_t)q * 4);
+  rel.in_flight = true;
   if (zero_copy) {
     memcpy(c->h_q.p, queries, (size_t)q * dim * 4);
     d_queries = c->h_q.as<float>();  // cudaMallocHost memory: device-accessible under unified addressing
@@ -1421,7 +1494,8 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   if (filter_json) {
     // the filter is evaluated on the device into a bitmask over slots: host metadata is never walked
     CU_TRY(cudaMemsetAsync(c->mask.p, 0, mask_words * 8 + 8, st));
-    CU_TRY(launch_eval_filter(prog, h->meta_dptrs.as<const uint32_t*>(), h->n_slots, c->mask.as<uint64_t>(), st));
+    CU_TRY(launch_eval_filter(prog, h->meta_dptrs.as<const uint32_t*>(), h->meta_synced_slots, h->n_slots,
+                                 c->mask.as<uint64_t>(), st));
     ++h->n_launch;
   }
   SearchArgs a{d_queries, q, c->ks.as<uint32_t>(), kmax,
@@ -1472,6 +1546,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     if (host_trace) t_enq = now_us();
     CU_TRY(cudaStreamSynchronize(st));
   }
+  rel.in_flight = false;
   const double t_sync = host_trace ? now_us() : 0.0;
   prof_collect(h, c);
   const char* hb = c->h_out.as<char>();
@@ -1585,6 +1660,7 @@ static void run_coalesced(gfi_index* h, std::vector<gfi_index::CoReq*>& batch) {
     r->rc = search_impl(h, r->queries, r->q, r->dim, r->ks, nullptr, 0, nullptr, r->out_ids, r->out_dist,
                         r->out_counts, r->kstride);
     if (r->rc != GFI_OK) { r->err = tl_error; r->exp = tl_expected; r->act = tl_actual; }
+    r->answered = true;
   };
   bool combine = batch.size() > 1;
   int64_t total = 0;
@@ -1618,6 +1694,7 @@ static void run_coalesced(gfi_index* h, std::vector<gfi_index::CoReq*>& batch) {
           memcpy(r->out_dist + i * r->kstride, dist.data() + (size_t)at * kmax, (size_t)c * 4);
         }
         r->rc = GFI_OK;
+        r->answered = true;
       }
       ++h->n_co_batches;
       h->n_co_requests += (int64_t)batch.size();
@@ -1639,8 +1716,11 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   // masked searches, large batches and malformed calls take the direct path
   // (indexes below 32 MB are launch-latency-bound: independent calls on separate streams overlap on the GPU and
   // beat a serialised batch -- measured 68-75k vs 53k q/s at 10k x 128 -- so only large ones are coalesced)
-  bool plain = h && h->opt_coalesce && !mask && q > 0 && q <= 256 && queries && ks && out_counts && out_ids && out_dist &&
-               h->n_slots * (int64_t)h->dpad * 4 >= (32ll << 20);
+  bool plain = h && !mask && q > 0 && q <= 256 && queries && ks && out_counts && out_ids && out_dist;
+  if (plain) {
+    std::shared_lock<std::shared_mutex> g(h->mu);  // (writers mutate these under the unique lock)
+    plain = h->opt_coalesce && h->n_slots * (int64_t)h->dpad * 4 >= (32ll << 20);
+  }
   if (plain)
     for (int64_t i = 0; i < q; ++i)
       if ((int64_t)ks[i] > kstride) { plain = false; break; }
@@ -1663,7 +1743,14 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   }
   // leader: run my batch, then hand the baton to the first queued request (with everything queued so far)
   std::vector<gfi_index::CoReq*> batch = std::move(me.batch);
-  run_coalesced(h, batch);
+  try {
+    run_coalesced(h, batch);
+  } catch (...) {
+    // nothing may escape with co_busy set (every later plain search would wait forever): whatever was not answered
+    // fails with an index error, and the baton is handed over below as usual
+    for (auto* r : batch)
+      if (r->rc == GFI_OK && !r->answered) { r->rc = GFI_ERR_INDEX; r->err = "search failed (out of memory?)"; }
+  }
   {
     std::lock_guard<std::mutex> lk(h->co_mu);
     // (notified while the lock is held: a woken request cannot return -- and destroy its CoReq -- before the lock is
@@ -1749,22 +1836,29 @@ int32_t gfi_search_device(gfi_index* h, const float* d_queries, int64_t q, const
   }
   SearchCtx* c = tl_dev_ctx;
   cudaStream_t st = stream ? (cudaStream_t)stream : c->stream;
+  // The context's workspace and control block are shared by every search issued before the next
+  // gfi_search_status: they are stream-ordered as long as the stream stays the same; a search on ANOTHER stream is
+  // ordered behind the uncollected ones with an event, and the error flags are sticky until collected.
+  if (c->pending_status && c->last_stream != st) {
+    if (!c->order_ev) CU_TRY(cudaEventCreateWithFlags(&c->order_ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventRecord(c->order_ev, c->last_stream));
+    CU_TRY(cudaStreamWaitEvent(st, c->order_ev, 0));
+  }
+  const bool had_pending = c->pending_status;
+  c->last_stream = st;
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
   if (h->n_live == 0 || kmax == 0) {
     CU_TRY(cudaMemsetAsync(d_out_counts, 0, (size_t)q * 4, st));
+    if (!had_pending) CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
     c->pending_status = true;
-    CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
-    CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
     return GFI_OK;
   }
   SearchArgs a{d_queries, q, d_ks, kmax, d_mask, mask_bits, d_out_ids, d_out_dist, d_out_counts, kstride};
-  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  a.keep_flags = had_pending;
   c->ctrl_dev = c->ctrl.p;
   rc = enqueue_search(h, c, a, st);
   c->ctrl_dev = nullptr;
   c->pending_status = true;
-  // remember which stream to synchronise when the status is collected
-  c->h_ctrl.ensure(sizeof(Ctrl) + sizeof(cudaStream_t));
-  memcpy(c->h_ctrl.as<char>() + sizeof(Ctrl), &st, sizeof(cudaStream_t));
   return rc;
 }
 
@@ -1777,13 +1871,13 @@ int32_t gfi_search_status(gfi_index* h) {
   struct Releaser { gfi_index* h; SearchCtx* c; ~Releaser() { release_ctx(h, c); } } rel{h, c};
   int32_t rc;
   if ((rc = set_device(h)) != GFI_OK) return rc;
-  cudaStream_t st = c->stream;
-  if (c->h_ctrl.bytes >= sizeof(Ctrl) + sizeof(cudaStream_t))
-    memcpy(&st, c->h_ctrl.as<char>() + sizeof(Ctrl), sizeof(cudaStream_t));
-  CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl) + sizeof(cudaStream_t)));
+  cudaStream_t st = c->last_stream ? c->last_stream : c->stream;
+  c->pending_status = false;
+  c->last_stream = nullptr;
+  if (!c->ctrl.p) return GFI_OK;
+  CU_TRY(c->h_ctrl.ensure(sizeof(Ctrl)));
   CU_TRY(cudaMemcpyAsync(c->h_ctrl.p, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDeviceToHost, st));
   CU_TRY(cudaStreamSynchronize(st));
-  c->pending_status = false;
   prof_collect(h, c);
   const Ctrl* hc = c->h_ctrl.as<Ctrl>();
   h->n_fallback_q += hc->uncertified;
@@ -2063,7 +2157,7 @@ int32_t compact_locked(gfi_index* h) {
       if ((size_t)perm[(size_t)j] < col.size()) nc[(size_t)j] = col[perm[(size_t)j]];
     col.swap(nc);
   }
-  if (!h->meta_cols.empty()) h->meta_dirty = true;
+  if (!h->meta_cols.empty()) { h->meta_dirty = true; h->meta_synced_slots = 0; }
   h->h_live.swap(nh_live);
   h->runs.swap(nruns);
   h->ids_identity = identity;

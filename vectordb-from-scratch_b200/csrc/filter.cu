@@ -20,8 +20,8 @@ namespace gfi {
 
 namespace {
 
-__global__ void eval_filter_kernel(const FilterProgram prog, const uint32_t* const* cols, int64_t n_slots,
-                                   uint64_t* mask_words) {
+__global__ void eval_filter_kernel(const FilterProgram prog, const uint32_t* const* cols, int64_t cols_len,
+                                   int64_t n_slots, uint64_t* mask_words) {
   griddep_wait();
   // one thread per slot; the 64 slots of a mask word are assembled with two ballots
   const int lane = threadIdx.x & 31;
@@ -36,7 +36,7 @@ __global__ void eval_filter_kernel(const FilterProgram prog, const uint32_t* con
       for (int i = 0; i < prog.n; ++i) {
         const FilterOp op = prog.ops[i];
         if (op.kind <= kFilterExists) {
-          const uint32_t code = op.field >= 0 ? cols[op.field][s] : 0u;
+          const uint32_t code = (op.field >= 0 && s < cols_len) ? cols[op.field][s] : 0u;  // beyond the synced columns: absent
           bool v;
           if (op.kind == kFilterEq) v = code != 0u && code == op.code;
           else if (op.kind == kFilterNe) v = !(code != 0u && code == op.code);
@@ -179,11 +179,11 @@ bool compile_filter(const char* json, const std::map<std::string, int>& fields,
   return true;
 }
 
-cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const* d_cols, int64_t n_slots,
-                               uint64_t* mask_words, cudaStream_t st) {
+cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const* d_cols, int64_t cols_len,
+                               int64_t n_slots, uint64_t* mask_words, cudaStream_t st) {
   if (n_slots <= 0) return cudaSuccess;
   const int blocks = (int)std::min<int64_t>((n_slots + 255) / 256, 148 * 8);
-  return launch_pdl(eval_filter_kernel, dim3(blocks), dim3(256), 0, st, prog, d_cols, n_slots, mask_words);
+  return launch_pdl(eval_filter_kernel, dim3(blocks), dim3(256), 0, st, prog, d_cols, cols_len, n_slots, mask_words);
 }
 
 }  // namespace gfi

@@ -225,8 +225,9 @@ constexpr int kFilterEq = 0, kFilterNe = 1, kFilterExists = 2, kFilterAnd = 3, k
 constexpr int kFilterMaxOps = 64, kFilterMaxDepth = 24;
 struct FilterOp { int kind; int field; uint32_t code; };  // And/Or: code = number of children
 struct FilterProgram { int n; FilterOp ops[kFilterMaxOps]; };  // postfix
-cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const* d_cols, int64_t n_slots,
-                               uint64_t* mask_words, cudaStream_t st);
+// cols_len = slots covered by the synced columns; slots beyond it read as "field absent" (code 0)
+cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const* d_cols, int64_t cols_len,
+                               int64_t n_slots, uint64_t* mask_words, cudaStream_t st);
 
 // misc
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st);

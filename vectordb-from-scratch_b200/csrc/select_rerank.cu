@@ -426,7 +426,9 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
         } else {
           const float qs = p.qsumsq[qg];
           const float xs = p.xnorm_max * p.xnorm_max;
-          float d2 = a_s + qs - 2.f * e_dot - 4.7683716e-07f * (xs + qs);
+          // a_s uses the PRECOMPUTED sequential sums sum x^2 and sum q^2, each off by up to gamma relatively
+          // (ADVICE r1), plus the epilogue's own fp32 rounding (2^-22 of the magnitudes involved)
+          float d2 = a_s + qs - 2.f * e_dot - (gamma + 2.3841858e-07f) * (xs + qs);
           d2 = fmaxf(d2, 0.f);
           lb = sqrtf(d2) * (1.f - gamma) - 1e-30f;
         }
