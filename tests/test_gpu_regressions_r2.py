@@ -114,3 +114,48 @@ def test_device_search_flags_are_sticky_until_collected():
     exp = oracle.search_batch("cosine", rows, good.cpu().numpy(), k, threads=4)
     for i, (eids, ed) in enumerate(exp):
         assert_topk_matches(oi[i].cpu().numpy().astype(np.uint64), od[i].cpu().numpy(), eids, ed)
+
+
+# ---------------------------------------------------------------- short-K row-tile-stationary tcgen05 kernel
+SHORT_K_CASES = [  # metric, n, d, kind, q, k, mask?
+    ("euclidean", 60000, 128, 0, 520, 10, False),   # C5 scaled down: 5 query tiles (last one partial), 2 k-chunks
+    ("cosine", 40000, 128, 1, 512, 10, False),      # raw epilogue
+    ("dot", 33000, 100, 1, 640, 20, False),         # d not a multiple of 16: partial second chunk (TMA zero fill)
+    ("euclidean", 50000, 64, 0, 512, 10, False),    # one k-chunk
+    ("cosine", 30011, 72, 0, 600, 5, True),         # mask -> coefficient epilogue for cosine; n not a tile multiple
+    ("euclidean", 300, 96, 1, 512, 10, False),      # fewer row tiles than CTAs (most CTAs idle)
+]
+
+
+@pytest.mark.parametrize("case", SHORT_K_CASES, ids=lambda c: "%s_n%d_d%d_q%d_k%d" % (c[0], c[1], c[2], c[4], c[5]))
+def test_short_k_row_stationary_kernel_matches_oracle_and_the_k_ring_kernel(case):
+    metric, n, d, kind, q, k, masked = case
+    M = {"euclidean": DM.Euclidean, "cosine": DM.Cosine, "dot": DM.DotProduct}
+    rows = oracle.gen_rows(500 + d, 0, n, d, kind)
+    queries = oracle.gen_rows(600 + d, 0, q, d, kind)
+    idx = gfi.GpuFlatIndex(M[metric])
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    idx.set_option("tensor_min_rows", 256)
+    for i in range(5, n, 97):
+        idx.remove(i)
+    elig = np.ones(n, dtype=bool)
+    elig[5::97] = False
+    mask = None
+    if masked:
+        mask = (np.arange(n) * 2654435761 >> 4) % 3 != 0
+        elig &= mask
+    res = {}
+    for sk in (1, 0):
+        idx.set_option("short_k", sk)
+        s0 = idx.stats()
+        res[sk] = idx.search_arrays(queries, k, mask=mask)
+        s1 = idx.stats()
+        assert s1["tensor_queries"] - s0["tensor_queries"] == q, (sk, s0, s1)
+        assert s1["fallback_queries"] - s0["fallback_queries"] <= 2, (sk, s0, s1)
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(a, b)
+    got_ids, got_d, cnt = res[1]
+    exp = oracle.search_batch(metric, rows, queries[:48], k, eligible=elig, threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert cnt[i] == len(eids)
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"{case} q{i}")

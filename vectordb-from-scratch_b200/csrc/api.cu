@@ -223,6 +223,8 @@ struct gfi_index {
   int opt_seed_rank = 8;
   int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
                              // gain -- the pass is power-limited either way -- so off by default
+  int opt_short_k = 1;       // dpad16 <= 128: row-tile-stationary main pass (0 = the k-ring kernel, for A/B timing)
+  int opt_short_k_min_tiles = 4;  // ... for batches of at least this many 128-query tiles
   int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
   std::atomic<int64_t> last_mask_pop{-1};     // population of the last device-resident mask searched (route predictor)
   std::atomic<bool> auto_tensor_off{false};   // set when such searches keep falling back (uncertifiable data)
@@ -853,6 +855,10 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
                                : std::min(1024, pow2_at_least(std::max<int>(64, 4 * (int)a.kmax)));
   const int hits = h->opt_hits > 0 ? h->opt_hits : 8 * KP;
   int main_grid = (int)std::min<int64_t>(grid_sm, ((h->n_slots + 255) / 256) * (qpad / 128));
+  // rows of at most 128 fp16 columns and a batch of several query tiles: the row-tile-stationary main pass
+  // (gemm_topk.cu, namespace sk) -- a CTA owns whole row tiles and meets every query tile for each of them
+  const bool short_k = h->opt_short_k && !h->opt_pair && h->dpad16 <= 128 && qpad / 128 >= h->opt_short_k_min_tiles;
+  if (short_k) main_grid = (int)std::min<int64_t>(grid_sm, (h->n_slots + 255) / 256);
   // CTA pairs (tcgen05 cta_group::2) when the batch has an even number of 128-query tiles: each SM then takes in
   // a third less data per k-step through its L2 port, which is what bounds the single-CTA kernel
   const bool pair = h->opt_pair && ((qpad / 128) % 2 == 0) && main_grid >= 2;
@@ -931,6 +937,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   // cosine without a caller mask: raw-accumulator epilogue (rows are stored pre-normalised, one coefficient)
   gp.seed_mode = (h->metric == kMetricCos && mv.bits == nullptr && h->opt_raw_epilogue) ? 3 : 0;
   gp.pair = pair ? 1 : 0;
+  gp.short_k = short_k ? 1 : 0;
   prof_begin(h, c, 1, st);
   CU_TRY(launch_gemm_topk(gp, pair ? &tmx_half : &tmx, &tmq, main_grid, st));
   prof_end(h, c, st);
@@ -2071,6 +2078,8 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "seed_rank") h->opt_seed_rank = (int)value;
   else if (n == "raw_epilogue") h->opt_raw_epilogue = (int)value;
   else if (n == "pair") h->opt_pair = (int)value;
+  else if (n == "short_k") h->opt_short_k = (int)value;
+  else if (n == "short_k_min_tiles") h->opt_short_k_min_tiles = (int)value;
   else if (n == "tensor_auto") { h->opt_tensor_auto = (int)value; h->auto_tensor_off = false; h->auto_q = 0; h->auto_fb = 0; }
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "coalesce") h->opt_coalesce = (int)value;

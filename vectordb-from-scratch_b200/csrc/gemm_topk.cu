@@ -88,6 +88,118 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
+// Main-pass filter of one accumulator half (128 columns) for the calling thread's query: 32 columns at a time
+// with two TMEM loads in flight.
+//  MODE 0: score = acc * a[row] + b[row] (coefficients as broadcast 128-bit shared loads), 3-input MIN
+//          trees, ONE compare per 32 values against the query's threshold.
+//  MODE 3 (cosine, rows stored pre-normalised: score = acc * c_q with one per-batch constant): compare raw
+//          accumulators with thr / c_q -- no coefficients, 3-input MAX trees; tombstoned / out-of-range
+//          rows are weeded out in the rare path.
+// Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in a block, the warp
+// re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane appends
+// its own survivors to the candidate slice private to this (query, unit, half): plain stores, no atomics.
+// Shared by the k-ring kernel and the short-K row-stationary kernel.
+template <int MODE>
+__device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
+                                                const float thr, const float c_q, const int qidx, const int64_t n0,
+                                                const int half, const int64_t unit, unsigned short* hitcnt) {
+  const IndexView& iv = p.iv;
+  const float thr_raw = MODE == 3 ? __fdiv_rn(thr, c_q) : 0.f;  // exact: c_q is a (negative) power of two
+  auto process = [&](const uint32_t (&r)[32], const int c0) {
+    float m8[4];
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      float v0 = __uint_as_float(r[8 * g8]), v1 = __uint_as_float(r[8 * g8 + 1]);
+      float v2 = __uint_as_float(r[8 * g8 + 2]), v3 = __uint_as_float(r[8 * g8 + 3]);
+      float v4 = __uint_as_float(r[8 * g8 + 4]), v5 = __uint_as_float(r[8 * g8 + 5]);
+      float v6 = __uint_as_float(r[8 * g8 + 6]), v7 = __uint_as_float(r[8 * g8 + 7]);
+      if (MODE == 3) {
+        m8[g8] = fmax3(fmax3(v0, v1, v2), fmax3(v3, v4, v5), fmaxf(v6, v7));
+      } else {
+        const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+        const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+        v0 = fmaf(v0, k0.x, k0.y); v1 = fmaf(v1, k0.z, k0.w);
+        v2 = fmaf(v2, k1.x, k1.y); v3 = fmaf(v3, k1.z, k1.w);
+        v4 = fmaf(v4, k2.x, k2.y); v5 = fmaf(v5, k2.z, k2.w);
+        v6 = fmaf(v6, k3.x, k3.y); v7 = fmaf(v7, k3.z, k3.w);
+        // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the rare path)
+        m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
+      }
+    }
+    const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
+    const bool hit_any = MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
+    if (__any_sync(0xffffffffu, hit_any && qidx < p.q) && !(p.debug & 8)) {
+#pragma unroll 1
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
+        const bool mine = (MODE == 3 ? !(mg <= thr_raw) : !(mg >= thr)) && qidx < p.q;
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        uint32_t v[8];
+        tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
+        const int64_t slot0 = n0 + half * (BN / 2) + c0 + 8 * g8;  // multiple of 8: one word of live bits
+        uint32_t lv = 0xffu;
+        float4 k0, k1, k2, k3;
+        if (MODE == 3) {
+          lv = 0;
+          if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
+        } else {
+          k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+          k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+        }
+        tmem_ld_wait();
+        if (mine) {
+          float s8[8];
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) s8[jj] = __uint_as_float(v[jj]);
+          if (MODE == 3) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+              const bool ok = !(s8[jj] <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots;
+              s8[jj] = ok ? s8[jj] * c_q : __int_as_float(0x7f800000);  // +inf never beats the threshold
+            }
+          } else {
+            s8[0] = fmaf(s8[0], k0.x, k0.y); s8[1] = fmaf(s8[1], k0.z, k0.w);
+            s8[2] = fmaf(s8[2], k1.x, k1.y); s8[3] = fmaf(s8[3], k1.z, k1.w);
+            s8[4] = fmaf(s8[4], k2.x, k2.y); s8[5] = fmaf(s8[5], k2.z, k2.w);
+            s8[6] = fmaf(s8[6], k3.x, k3.y); s8[7] = fmaf(s8[7], k3.z, k3.w);
+          }
+          unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
+          uint32_t cnt = *hc;
+          uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap;
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float score = s8[jj];
+            if (!(score >= thr)) {
+              if (score != score) {
+                atomicOr(p.flags, kFlagNaN);
+              } else {
+                if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(slot0 + jj));
+                ++cnt;  // beyond the capacity only counted: select_kernel sees the overflow and falls back
+              }
+            }
+          }
+          *hc = (unsigned short)min(cnt, 65535u);
+        }
+      }
+    }
+  };
+  if (!(p.debug & 4)) {
+    uint32_t ra[32], rb[32];
+    tmem_ld_32x32b_x32(taddr, ra);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(taddr + 32, rb);
+    process(ra, 0);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(taddr + 64, ra);
+    process(rb, 32);
+    tmem_ld_wait();
+    tmem_ld_32x32b_x32(taddr + 96, rb);
+    process(ra, 64);
+    tmem_ld_wait();
+    process(rb, 96);
+  }
+}
+
 // item -> (row tile, query tile).  The query tile is rotated by the row-tile index so that every
 // CTA meets every query tile: a query's candidates then spread evenly over all CTAs' slices.
 template <int MODE, int CG>
@@ -340,109 +452,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
       if (MODE == 0 || MODE == 3) {
-        // Main-pass filter, 32 columns at a time with two TMEM loads in flight.
-        //  MODE 0: score = acc * a[row] + b[row] (coefficients as broadcast 128-bit shared loads), 3-input MIN
-        //          trees, ONE compare per 32 values against the query's threshold.
-        //  MODE 3 (cosine, rows stored pre-normalised: score = acc * c_q with one per-batch constant): compare raw
-        //          accumulators with thr / c_q -- no coefficients, 3-input MAX trees; tombstoned / out-of-range
-        //          rows are weeded out in the rare path.
-        // Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in a block, the warp
-        // re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane appends
-        // its own survivors to the candidate slice private to this (query, unit, half): plain stores, no atomics.
-        const float thr_raw = MODE == 3 ? __fdiv_rn(thr, c_q) : 0.f;  // exact: c_q is a (negative) power of two
-        auto process = [&](const uint32_t (&r)[32], const int c0) {
-          float m8[4];
-#pragma unroll
-          for (int g8 = 0; g8 < 4; ++g8) {
-            float v0 = __uint_as_float(r[8 * g8]), v1 = __uint_as_float(r[8 * g8 + 1]);
-            float v2 = __uint_as_float(r[8 * g8 + 2]), v3 = __uint_as_float(r[8 * g8 + 3]);
-            float v4 = __uint_as_float(r[8 * g8 + 4]), v5 = __uint_as_float(r[8 * g8 + 5]);
-            float v6 = __uint_as_float(r[8 * g8 + 6]), v7 = __uint_as_float(r[8 * g8 + 7]);
-            if (MODE == 3) {
-              m8[g8] = fmax3(fmax3(v0, v1, v2), fmax3(v3, v4, v5), fmaxf(v6, v7));
-            } else {
-              const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
-              const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
-              v0 = fmaf(v0, k0.x, k0.y); v1 = fmaf(v1, k0.z, k0.w);
-              v2 = fmaf(v2, k1.x, k1.y); v3 = fmaf(v3, k1.z, k1.w);
-              v4 = fmaf(v4, k2.x, k2.y); v5 = fmaf(v5, k2.z, k2.w);
-              v6 = fmaf(v6, k3.x, k3.y); v7 = fmaf(v7, k3.z, k3.w);
-              // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the rare path)
-              m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
-            }
-          }
-          const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
-          const bool hit_any = MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
-          if (__any_sync(0xffffffffu, hit_any && qidx < p.q) && !(p.debug & 8)) {
-#pragma unroll 1
-            for (int g8 = 0; g8 < 4; ++g8) {
-              const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
-              const bool mine = (MODE == 3 ? !(mg <= thr_raw) : !(mg >= thr)) && qidx < p.q;
-              if (!__any_sync(0xffffffffu, mine)) continue;
-              uint32_t v[8];
-              tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
-              const int64_t slot0 = n0 + half * (BN / 2) + c0 + 8 * g8;  // multiple of 8: one word of live bits
-              uint32_t lv = 0xffu;
-              float4 k0, k1, k2, k3;
-              if (MODE == 3) {
-                lv = 0;
-                if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
-              } else {
-                k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
-                k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
-              }
-              tmem_ld_wait();
-              if (mine) {
-                float s8[8];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) s8[jj] = __uint_as_float(v[jj]);
-                if (MODE == 3) {
-#pragma unroll
-                  for (int jj = 0; jj < 8; ++jj) {
-                    const bool ok = !(s8[jj] <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots;
-                    s8[jj] = ok ? s8[jj] * c_q : __int_as_float(0x7f800000);  // +inf never beats the threshold
-                  }
-                } else {
-                  s8[0] = fmaf(s8[0], k0.x, k0.y); s8[1] = fmaf(s8[1], k0.z, k0.w);
-                  s8[2] = fmaf(s8[2], k1.x, k1.y); s8[3] = fmaf(s8[3], k1.z, k1.w);
-                  s8[4] = fmaf(s8[4], k2.x, k2.y); s8[5] = fmaf(s8[5], k2.z, k2.w);
-                  s8[6] = fmaf(s8[6], k3.x, k3.y); s8[7] = fmaf(s8[7], k3.z, k3.w);
-                }
-                unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
-                uint32_t cnt = *hc;
-                uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap;
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj) {
-                  const float score = s8[jj];
-                  if (!(score >= thr)) {
-                    if (score != score) {
-                      atomicOr(p.flags, kFlagNaN);
-                    } else {
-                      if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(slot0 + jj));
-                      ++cnt;  // beyond the capacity only counted: select_kernel sees the overflow and falls back
-                    }
-                  }
-                }
-                *hc = (unsigned short)min(cnt, 65535u);
-              }
-            }
-          }
-        };
-        if (!(p.debug & 4)) {
-          uint32_t ra[32], rb[32];
-          tmem_ld_32x32b_x32(taddr, ra);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 32, rb);
-          process(ra, 0);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 64, ra);
-          process(rb, 32);
-          tmem_ld_wait();
-          tmem_ld_32x32b_x32(taddr + 96, rb);
-          process(ra, 64);
-          tmem_ld_wait();
-          process(rb, 96);
-        }
+        epi_filter_half<MODE>(p, taddr, cs_addr, thr, c_q, qidx, n0, half, unit, hitcnt);
       } else {
         // seed pass / debug dump: one 32-column block at a time
 #pragma unroll 1
@@ -529,6 +539,275 @@ gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant_
   griddep_wait();
   if (p.skip && *p.skip) return;  // device-side route: the scan answers this batch
   gemm_topk_body<MODE, 1>(tmx, tmq, p);
+}
+
+// =====================================================================================================
+// Short-K, ROW-TILE-STATIONARY instance (dpad16 <= 128, i.e. the whole K extent fits ONE shared-memory stage).
+//
+// Why a second main-pass kernel: at d = 128 an item of the k-ring kernel above is only 8 MMAs (1024 clk) but
+//   * 3 tcgen05.commits of ~430 clk each (one per 64-column k-step + the accumulator hand-over): the fixed
+//     hand-shake per item was as large as the math (DESIGN.md, round-1 in-kernel clocks);
+//   * 96 KB of operands through the L2->SM port (a 32 KB query block AND a 64 KB row block per item), although
+//     consecutive items of a CTA could share either.
+// Here a CTA keeps ONE 256-row tile of the database (<= 64 KB) in shared memory and streams every 128-query
+// block of the batch past it (A ring of kNA stages, <= 32 KB each): the row tile is read from L2 once per
+// num_m_tiles items (34 KB of operand traffic per item instead of 96), and an item costs exactly ONE
+// tcgen05.commit on a barrier `done[s]` that both the producer (A stage s is free) and the epilogue
+// (accumulator s & 1 is complete) wait on.  The per-row coefficients (MODE 0) are staged once per row tile
+// instead of once per item.  Epilogue, TMEM layout, candidate slices and certification are unchanged.
+namespace sk {
+constexpr int kNA = 4;                                  // A-ring stages (items of prefetch)
+constexpr int kAStageBytes = 2 * kABytes;               // 128 queries x 128 fp16 (two SWIZZLE_128B chunks)
+constexpr int kBChunkBytes = BN * BK * 2;               // 256 rows x 64 fp16 = 32 KB
+constexpr size_t kOffB = 0;
+constexpr size_t kOffA = kOffB + 2 * (size_t)kBChunkBytes;
+constexpr size_t kOffCoef = kOffA + (size_t)kNA * kAStageBytes;
+constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
+constexpr size_t kOffCnt = kOffBar + 24 * 8 + 16;
+constexpr size_t kSmemUsed = kOffCnt + 2 * 2 * kGemmMaxQueries;
+constexpr size_t kSmemBytes = kSmemUsed + 1024;
+static_assert(kSmemBytes <= 232448, "shared memory budget");
+}  // namespace sk
+
+// waits like mbar_wait; with `diag` the cycles spent waiting are added to `acc` (in-kernel diagnostics, debug bit 5)
+__device__ __forceinline__ void mbar_wait_d(uint64_t* bar, uint32_t parity, bool diag, long long& acc) {
+  if (!diag) { mbar_wait(bar, parity); return; }
+  const long long t0 = clock64();
+  mbar_wait(bar, parity);
+  acc += clock64() - t0;
+}
+
+template <int MODE>
+__device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const CUtensorMap& tmq, const GemmParams& p) {
+  static_assert(MODE == 0 || MODE == 3, "main-pass modes only");
+  constexpr int kNA = sk::kNA;
+  constexpr uint32_t kIdesc = Geo<1>::kIdesc;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                                         ~(uintptr_t)1023);
+  unsigned char* sB = smem + sk::kOffB;
+  unsigned char* sA = smem + sk::kOffA;
+  float2* sCoef = reinterpret_cast<float2*>(smem + sk::kOffCoef);
+  uint64_t* afull = reinterpret_cast<uint64_t*>(smem + sk::kOffBar);  // TMA -> MMA: A stage loaded
+  uint64_t* done = afull + kNA;    // MMA -> producer + epilogue: the item's MMAs have completed (ONE commit per item)
+  uint64_t* bfull = done + kNA;    // TMA -> MMA: row tile loaded
+  uint64_t* tempty = bfull + 1;    // epilogue -> MMA: accumulator drained            [2]
+  uint64_t* cfull = tempty + 2;    // stager -> epilogue: coefficients of a row tile  [2]
+  uint64_t* cempty = cfull + 2;    // epilogue -> stager                              [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty + 2);
+  unsigned short* hitcnt = reinterpret_cast<unsigned short*>(smem + sk::kOffCnt);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const IndexView& iv = p.iv;
+  const int KS = (iv.dpad16 + BK - 1) / BK;         // 64-column chunks: 1 or 2
+  const int nk16 = (iv.dpad16 + 15) / 16;           // K = 16 MMA steps per item (<= 8)
+  const int64_t unit = blockIdx.x, nunits = gridDim.x;
+  const int M = p.num_m_tiles;
+  // this CTA's row tiles: unit, unit + nunits, ...
+  const int64_t ntiles = unit < p.num_n_tiles ? (p.num_n_tiles - unit + nunits - 1) / nunits : 0;
+  const int64_t total = ntiles * M;                 // items of this CTA
+  const bool diag = (p.debug & 32) && blockIdx.x == 0;
+  long long w_a = 0, w_b = 0, w_c = 0;              // per-role wait cycles (diag)
+
+  if (tid == 0) {
+    for (int s = 0; s < kNA; ++s) {
+      mbar_init(&afull[s], 1);
+      mbar_init(&done[s], 1);
+    }
+    mbar_init(bfull, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tempty[s], kEpiWarps);
+      mbar_init(&cfull[s], 2);
+      mbar_init(&cempty[s], kEpiWarps);
+    }
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 2 * kGemmMaxQueries; i += kGemmThreads) hitcnt[i] = 0;
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmx);
+    tma_prefetch_desc(&tmq);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  long long dbg_c0 = 0, dbg_t0 = 0;
+  if (diag && tid == 0) {
+    dbg_c0 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
+  }
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    // In-order stream of loads, each issued as soon as its precondition holds: A(it) needs the MMAs of item it - kNA
+    // (its stage) to have completed, B(j) those of the last item of row tile j - 1 (the single row-tile buffer).
+    auto load_b = [&](int64_t j) {
+      if (lane == 0) {
+        const int n_row0 = (int)((unit + j * nunits) * BN);
+        if (p.debug & 2) { mbar_arrive(bfull); return; }
+        mbar_arrive_expect_tx(bfull, (uint32_t)KS * sk::kBChunkBytes);
+        for (int kc = 0; kc < KS; ++kc) tma_load_2d(sB + (size_t)kc * sk::kBChunkBytes, &tmx, kc * BK, n_row0, bfull);
+      }
+    };
+    int64_t next_b = 1;
+    if (total > 0) load_b(0);
+    int m = 0;
+    for (int64_t it = 0; it < total; ++it) {
+      const int s = (int)(it & (kNA - 1));
+      const uint32_t u = (uint32_t)(it / kNA);
+      if (it >= kNA) mbar_wait_d(&done[s], (u - 1u) & 1u, diag, w_a);
+      if (lane == 0) {
+        if ((p.debug & 1) && it >= kNA) {
+          mbar_arrive(&afull[s]);
+        } else {
+          mbar_arrive_expect_tx(&afull[s], (uint32_t)KS * kABytes);
+          for (int kc = 0; kc < KS; ++kc)
+            tma_load_2d(sA + (size_t)s * sk::kAStageBytes + (size_t)kc * kABytes, &tmq, kc * BK, m * BM, &afull[s]);
+        }
+      }
+      if (++m == M) m = 0;
+      // the wait just passed covers B(next_b)'s precondition when item next_b*M - 1 is not younger than it - kNA
+      if (next_b < ntiles && it - kNA >= next_b * M - 1) load_b(next_b++);
+      __syncwarp();
+    }
+    while (next_b < ntiles) {  // (fewer query tiles than ring stages: the triggers above lie beyond the last item)
+      const int64_t il = next_b * M - 1;
+      mbar_wait_d(&done[il & (kNA - 1)], (uint32_t)(il / kNA) & 1u, diag, w_b);
+      load_b(next_b++);
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    const uint32_t a_lo_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t b_lo_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t desc_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);  // SBO | version 1 | SWIZZLE_128B
+    const uint32_t done0 = smem_u32(done);
+    int m = 0;
+    uint32_t j = 0;
+    for (int64_t it = 0; it < total; ++it) {
+      const int s = (int)(it & (kNA - 1));
+      const uint32_t u = (uint32_t)(it / kNA);
+      const uint32_t as = (uint32_t)it & 1u, aph = (uint32_t)(it >> 1) & 1u;
+      if (m == 0) mbar_wait_d(bfull, j & 1u, diag, w_b);
+      mbar_wait_d(&tempty[as], aph ^ 1u, diag, w_c);
+      mbar_wait_d(&afull[s], u & 1u, diag, w_a);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      const uint32_t a_lo = a_lo_base + (uint32_t)s * (sk::kAStageBytes >> 4);
+      if (!(p.debug & 16)) {
+#pragma unroll 1
+        for (int k = 0; k < nk16; ++k) {
+          // chunk k >> 2 (16 / 32 KB further), K step k & 3 (32 bytes further)
+          const uint32_t ao = (uint32_t)(k >> 2) * (kABytes >> 4) + (uint32_t)(k & 3) * 2u;
+          const uint32_t bo = (uint32_t)(k >> 2) * (sk::kBChunkBytes >> 4) + (uint32_t)(k & 3) * 2u;
+          umma_f16_elect(d_tmem, a_lo + ao, b_lo_base + bo, desc_hi, kIdesc, k != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit_elect(done0 + s * 8);
+      if (++m == M) { m = 0; ++j; }
+    }
+  } else if ((warp == 2 || warp == 3) && MODE != 3) {
+    // ------------------------------ coefficient stager: once per ROW TILE ------------------------------
+    constexpr int RPL = BN / 64;
+    const int r0 = (warp - 2) * (BN / 2);
+    const float inv_sq = pow2_scale_inv(*p.qmaxabs);
+    const float kInf = __int_as_float(0x7f800000);
+    const bool has_mask = p.mask.bits != nullptr;
+    const bool by_slot = has_mask && iv.ids_identity;
+    for (int64_t j = 0; j < ntiles; ++j) {
+      const uint32_t cb = (uint32_t)j & 1u, cph = (uint32_t)(j >> 1) & 1u;
+      const int64_t n0 = (unit + j * nunits) * BN;
+      float2 cv[RPL];
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        const int64_t slot = n0 + r0 + lane + 32 * i;
+        cv[i] = make_float2(0.f, kInf);
+        if (slot < iv.n_slots) {
+          bool elig = (__ldg(iv.live + (slot >> 5)) >> (slot & 31)) & 1u;
+          if (elig && has_mask) {
+            const uint64_t id = by_slot ? (uint64_t)slot : iv.ids[slot];
+            elig = (id < (uint64_t)p.mask.nbits) && ((__ldg(p.mask.bits + (id >> 6)) >> (id & 63)) & 1ull);
+          }
+          if (elig) {
+            const float2 c = __ldg(iv.coef + slot);
+            cv[i] = make_float2(c.x * inv_sq, c.y);
+          }
+        }
+      }
+      mbar_wait(&cempty[cb], cph ^ 1u);
+      float2* cs = sCoef + cb * BN;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) cs[r0 + lane + 32 * i] = cv[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&cfull[cb]);
+    }
+  } else if (warp >= kEpiWarp0) {
+    // ------------------------------ epilogue: thread == (query, column half) ------------------------------
+    const int quarter = warp & 3;
+    const int half = (warp - kEpiWarp0) >> 2;
+    const int mrow = quarter * 32 + lane;
+    const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
+    int m = 0;
+    int64_t j = 0;
+    for (int64_t it = 0; it < total; ++it) {
+      const int s = (int)(it & (kNA - 1));
+      const uint32_t u = (uint32_t)(it / kNA);
+      const uint32_t as = (uint32_t)it & 1u;
+      const uint32_t cb = (uint32_t)j & 1u;
+      const int64_t n0 = (unit + j * nunits) * BN;
+      const int qidx = m * BM + mrow;
+      float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
+      if (qidx < p.q) thr = p.thresh[qidx];
+      if (MODE != 3 && m == 0) mbar_wait_d(&cfull[cb], (uint32_t)(j >> 1) & 1u, diag, w_c);
+      mbar_wait_d(&done[s], u & 1u, diag, w_a);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
+      const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
+      epi_filter_half<MODE>(p, taddr, cs_addr, thr, c_q, qidx, n0, half, unit, hitcnt);
+      tc_fence_before();
+      __syncwarp();
+      const bool last_m = m == M - 1;
+      if (lane == 0) {
+        mbar_arrive(&tempty[as]);
+        if (MODE != 3 && last_m) mbar_arrive(&cempty[cb]);
+      }
+      if (last_m) { m = 0; ++j; } else ++m;
+    }
+  }
+
+  if (diag && (tid == 0 || tid == 32 || tid == kEpiWarp0 * 32))
+    printf("[gemm_topk_sk] role %d items %lld waits: A/done %lld, B %lld, tmem/coef %lld clk\n", warp, (long long)total,
+           w_a, w_b, w_c);
+  tc_fence_before();
+  __syncthreads();
+  for (int i = tid; i < 2 * p.q; i += kGemmThreads) {
+    const int hf = i >= p.q ? 1 : 0, qi = i - hf * p.q;
+    p.slice_cnt[(size_t)(unit * 2 + hf) * p.q + qi] = hitcnt[hf * kGemmMaxQueries + qi];
+  }
+  if (diag && tid == 0) {
+    long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    const long long c1 = clock64();
+    printf("[gemm_topk_sk] cycles %lld ns %lld -> %.1f MHz, %.0f clk/item\n", c1 - dbg_c0, t1 - dbg_t0,
+           1e3 * (double)(c1 - dbg_c0) / (double)(t1 - dbg_t0), total ? (double)(c1 - dbg_c0) / (double)total : 0.0);
+  }
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_topk_sk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
+                    const GemmParams p) {
+  griddep_wait();
+  if (p.skip && *p.skip) return;
+  gemm_topk_sk_body<MODE>(tmx, tmq, p);
 }
 
 // CTA-pair instance: clusters of two CTAs (the two SMs of a TPC), tcgen05.mma.cta_group::2.
@@ -670,6 +949,8 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk::kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk::kSmemBytes);
     if (e != cudaSuccess) return e;
     attr_set[dev & 15] = true;
   }
@@ -677,6 +958,11 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   const CUtensorMap* tq = reinterpret_cast<const CUtensorMap*>(tmap_q_host);
   const size_t sm1 = Geo<1>::kSmemBytes, sm2 = Geo<2>::kSmemBytes;
   const dim3 g(grid), b(kGemmThreads);
+  if (p.short_k) {
+    if (pair || p.iv.dpad16 > 2 * BK || (p.seed_mode != 0 && p.seed_mode != 3)) return cudaErrorInvalidValue;
+    if (p.seed_mode == 0) return launch_pdl(gemm_topk_sk_kernel<0>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
+    return launch_pdl(gemm_topk_sk_kernel<3>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
+  }
   if (pair && p.seed_mode == 0) return launch_pdl(gemm_topk_pair_kernel<0>, g, b, sm2, st, *tx, *tq, p);
   if (pair) return launch_pdl(gemm_topk_pair_kernel<3>, g, b, sm2, st, *tx, *tq, p);
   if (p.seed_mode == 0) return launch_pdl(gemm_topk_kernel<0>, g, b, sm1, st, *tx, *tq, p);

@@ -183,6 +183,8 @@ struct GemmParams {
   uint32_t* flags;
   const uint32_t* skip; // device word or null: non-zero = the device-side route chose the scan, exit at once
   int debug;            // timing experiments only (see gemm_topk.cu)
+  int short_k;          // 1: short-K row-tile-stationary main pass (dpad16 <= 128; gemm_topk.cu, namespace sk): the
+                        // grid's CTA b owns row tiles b, b + grid, ... and meets every query tile for each of them
   int pair;             // 1: CTA-pair kernel (cta_group::2); needs an even grid and an even number of query tiles;
                         // the row tensor map then has a 128-row box and slices are per PAIR: (pair*2+half)
 };
