@@ -62,6 +62,26 @@ int32_t gfi_create(gfi_index **out, int32_t metric, int64_t dim, int32_t device,
 int32_t gfi_destroy(gfi_index *h);
 
 /*
+ * The same index sharded row-wise over several GPUs of one box, in ONE process -- what the reference server needs:
+ * it owns a single `RwLock<VectorStore<I>>` (src/server/mod.rs:13-16, src/main.rs:152-198), so `GpuFlatIndex: Index`
+ * must reach all GPUs from behind one handle.  devices[0] is the root GPU (it merges).  Every entry point of this
+ * header accepts the handle; differences:
+ *   - rows are routed by internal id in blocks: shard = (id / block) % n_devices, block = 65536 ids, or
+ *     ceil(n_rows / n_devices) after gfi_reserve(h, n_rows) on an empty index (contiguous id ranges);
+ *   - a search copies the query block once into pinned memory, every shard's worker thread enqueues the ordinary
+ *     single-GPU pipeline on its own GPU, and each shard's finalize kernel stores its k candidates straight into
+ *     the root GPU's gather block over NVLink (peer stores: no collective, no staging copy); the root merges the
+ *     per-shard lists by (distance, id) with one kernel and returns one result block;
+ *   - gfi_search_device takes queries/results in the ROOT GPU's memory and double-buffers the gather block, so the
+ *     exchange + merge of one batch overlaps the next batch's main pass;
+ *   - gfi_debug_tensor_scores is single-GPU only.
+ * A device may be listed more than once (several shards on one GPU: used by the single-GPU tests).
+ * All listed GPUs must be able to access the root GPU's memory (NVLink / NVSwitch peers).
+ */
+int32_t gfi_create_sharded(gfi_index **out, int32_t metric, int64_t dim, const int32_t *devices, int32_t n_devices,
+                           uint32_t flags);
+
+/*
  * Index::add, reference src/index.rs:13 / src/flat_index.rs:38-41, for n rows at
  * once (n = 1 from Index::add; large n for bulk load).  An existing id is
  * overwritten.  Rows are staged in pinned host memory and reach the GPU at the
@@ -206,6 +226,10 @@ typedef struct gfi_stats {
   int64_t tensor_kernel_ns, tensor_kernel_count; /* K2 flat_gemm_topk main-pass launches */
   /* group commit of concurrent plain gfi_search calls (option "coalesce", default on) */
   int64_t coalesced_batches, coalesced_requests; /* combined searches run, calls they served */
+  /* sharded handles (gfi_create_sharded); shards = 1 otherwise.  With "profile"=1: CUDA-event time on the root GPU
+   * from the moment the last shard's candidates have arrived to the end of the merge kernel, summed. */
+  int64_t shards;
+  int64_t merge_ns, merge_count;
 } gfi_stats;
 int32_t gfi_get_stats(gfi_index *h, gfi_stats *out);
 

@@ -28,124 +28,22 @@
 #include <unordered_map>
 #include <vector>
 
-#include "../../include/gfi.h"
-#include "kernels.h"
+#include "host.h"
 
 using namespace gfi;
 
-namespace {
-
+namespace gfi {
 thread_local std::string tl_error;
 thread_local int64_t tl_expected = 0, tl_actual = 0;
-thread_local bool tl_mask_by_slot = false;  // search_impl: the host mask passed in is indexed by slot (big-k passes)
-
 int32_t fail(int32_t code, const std::string& msg) {
   tl_error = msg;
   return code;
 }
+}  // namespace gfi
 
-#define CU_TRY(expr)                                                                             \
-  do {                                                                                           \
-    cudaError_t e__ = (expr);                                                                    \
-    if (e__ != cudaSuccess)                                                                      \
-      return fail(GFI_ERR_INDEX, std::string(#expr) + ": " + cudaGetErrorString(e__));           \
-  } while (0)
+namespace {
 
-struct DevBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t ensure(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-    size_t want = need + need / 4 + 256;
-    cudaError_t e = cudaMalloc(&p, want);
-    if (e != cudaSuccess) { e = cudaMalloc(&p, need); want = need; }
-    if (e == cudaSuccess) bytes = want;
-    return e;
-  }
-  void release() {
-    if (p) cudaFree(p);
-    p = nullptr;
-    bytes = 0;
-  }
-  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-struct PinBuf {
-  void* p = nullptr;
-  size_t bytes = 0;
-  cudaError_t ensure(size_t need) {
-    if (need <= bytes) return cudaSuccess;
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    bytes = 0;
-    cudaError_t e = cudaMallocHost(&p, need + need / 4 + 256);
-    if (e == cudaSuccess) bytes = need + need / 4 + 256;
-    return e;
-  }
-  void release() {
-    if (p) cudaFreeHost(p);
-    p = nullptr;
-    bytes = 0;
-  }
-  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
-};
-
-// control block of one search call (device memory, zeroed per call)
-struct Ctrl {
-  uint32_t flags;
-  uint32_t fb_count;
-  uint32_t uncertified;
-  uint32_t qmaxabs_bits;
-  // device-side route of a small batch with a device-resident mask (kernels.h, RouteParams)
-  uint32_t skip_tensor;
-  uint32_t tensor_nq;
-  uint32_t routed_scan;
-  uint32_t elig_count;  // population of the mask + 1 when a gather scan or the route kernel saw it, else 0
-  uint32_t scan_done;   // CTAs of a fused-tail scan that have finished (ScanParams::done_ctr)
-  uint32_t pad_[3];
-};
-static_assert(sizeof(Ctrl) == kCtrlWords * 4, "host result blocks reserve 64 bytes: Ctrl + the done word");
-
-struct SearchCtx {
-  cudaStream_t stream = nullptr;
-  DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, slice_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
-      fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
-  PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl, h_out;
-  bool zc_pending = false;   // the search enqueued last publishes its results in h_out itself (latency mode)
-  uint32_t zc_seq = 0;
-  DevBuf out_blk;            // [Ctrl | counts | dist | ids] of a host search: one D2H copy brings it all back
-  void* ctrl_dev = nullptr;  // control block of the search being enqueued (inside out_blk or `ctrl`)
-  bool pending_status = false;  // device search issued, status not yet collected
-  cudaStream_t last_stream = nullptr;  // stream of the uncollected device search(es)
-  cudaEvent_t order_ev = nullptr;      // orders a device search on a new stream behind the uncollected ones
-  int64_t auto_tensor_q = 0;     // queries of the search being enqueued that took the tensor path by the cost model
-  // CUDA-event pairs around the dominant kernel of each enqueued search (option "profile")
-  struct EvPair { cudaEvent_t a, b; int kind; };
-  std::vector<EvPair> evs;
-  size_t ev_used = 0;
-  void release() {
-    for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &slice_cnt, &cand_fb, &cand_fb_cnt,
-                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
-      b->release();
-    for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl, &h_out}) b->release();
-    out_blk.release();
-    for (auto& e : evs) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
-    evs.clear();
-    ev_used = 0;
-    if (order_ev) cudaEventDestroy(order_ev);
-    order_ev = nullptr;
-    if (stream) cudaStreamDestroy(stream);
-    stream = nullptr;
-  }
-};
-
-struct Run {  // ids[slot0 + i] == id0 + i for i < n
-  uint32_t slot0;
-  uint32_t n;
-};
+thread_local bool tl_mask_by_slot = false;  // search_impl: the host mask passed in is indexed by slot (big-k passes)
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -166,111 +64,6 @@ EncodeTiledFn get_encode_fn() {
 
 }  // namespace
 
-struct gfi_index {
-  int metric = 0;
-  int64_t dim = 0;
-  int dpad = 0, dpad16 = 0;
-  int device = 0;
-  uint32_t flags = 0;
-  int sm_count = 148;
-
-  mutable std::shared_mutex mu;  // writers: add/remove/flush/compact; readers: search
-  std::mutex pool_mu;
-  std::vector<std::unique_ptr<SearchCtx>> pool;
-
-  // device storage
-  int64_t cap = 0, n_slots = 0, n_live = 0;
-  DevBuf x32, x16, ids, norm, sumsq, coef, live, rowflags, counters;
-  cudaStream_t ingest_stream = nullptr;
-  bool use_x16 = true;
-  int64_t zero_rows_ever = 0, unsafe_rows_ever = 0;
-  float xnorm_max = 0.f;
-
-  // host bookkeeping
-  std::map<uint64_t, Run> runs;          // id0 -> run (disjoint id ranges)
-  std::vector<uint32_t> h_live;          // host mirror of the live bitmap
-  int64_t live_dirty_lo = -1, live_dirty_hi = -1;
-  bool ids_identity = true;
-  bool needs_reorder = false;
-  uint64_t max_id_seen = 0;
-  bool any_id = false;
-  std::unordered_map<uint64_t, int64_t> odd_dim_rows;  // id -> dim of rows whose dim != index dim
-
-  // metadata (device-side filter evaluation): dictionary-encoded u32 column per field, code 0 = absent
-  std::map<std::string, int> meta_fields;
-  std::vector<std::map<std::string, uint32_t>> meta_values;
-  std::vector<std::vector<uint32_t>> meta_cols;  // host mirror, one entry per slot
-  std::vector<DevBuf> meta_dcols;
-  DevBuf meta_dptrs;
-  bool meta_dirty = false;
-  int64_t meta_synced_slots = 0;  // slots the device columns cover (rows beyond read as "no metadata")
-  std::unordered_map<uint64_t, std::vector<std::pair<int, uint32_t>>> meta_pending;
-
-  // staging (pinned)
-  PinBuf st_rows, st_ids;
-  int64_t st_n = 0, st_cap = 0;
-
-  // stats / options
-  std::atomic<int64_t> n_search{0}, n_queries{0}, n_scan_q{0}, n_tensor_q{0}, n_fallback_q{0}, n_launch{0};
-  int opt_tensor_min_q = 16;
-  int opt_kp = 0;          // 0 = auto
-  int opt_hits = 0;        // 0 = auto
-  int opt_scan_qt = 0;     // 0 = auto
-  int opt_fused_tail = 1;  // small single-pass scans finish inside the scan kernel (experiments: 0 = separate K3)
-  int opt_zero_copy = 1;   // small host searches: pinned-host inputs/outputs, no copies, no stream sync (0 = off)
-  int opt_grid = 0;        // 0 = sm_count
-  int opt_tensor_min_rows = 8192;
-  int opt_seed_rank = 8;
-  int opt_pair = 0;          // 1: CTA-pair (cta_group::2) kernel for even query-tile counts.  Measured on B200: no
-                             // gain -- the pass is power-limited either way -- so off by default
-  int opt_short_k = 1;       // dpad16 <= 128: row-tile-stationary main pass (0 = the k-ring kernel, for A/B timing)
-  int opt_short_k_min_tiles = 4;  // ... for batches of at least this many 128-query tiles
-  int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
-  std::atomic<int64_t> last_mask_pop{-1};     // population of the last device-resident mask searched (route predictor)
-  std::atomic<bool> auto_tensor_off{false};   // set when such searches keep falling back (uncertifiable data)
-  std::atomic<int64_t> auto_q{0}, auto_fb{0};
-  int opt_raw_epilogue = 1;  // 0: force the per-row-coefficient epilogue for cosine (A/B timing, tests)
-  std::atomic<uint64_t> layout_gen{0};  // bumped whenever rows change slots (compaction)
-  int opt_profile = 0;
-  // Group commit of concurrent plain searches (micro-batching of concurrent Index::search
-  // calls).  While one batch runs, arriving calls queue up; the next leader takes everything queued as ONE batch
-  // (one scan pass serves up to 4 queries, >= 16 go to the tensor path).  A call that finds the index idle runs at
-  // once, alone: no timers, no added latency.
-  int opt_coalesce = 1;
-  struct CoReq {
-    const float* queries; int64_t q, dim; const uint32_t* ks;
-    uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
-    int32_t rc = 0; std::string err; int64_t exp = 0, act = 0;
-    bool done = false, lead = false, answered = false;
-    std::vector<CoReq*> batch;  // filled for the request promoted to leader
-    std::condition_variable cv;  // one per request: the leader wakes exactly the requests it finished and its successor
-  };
-  std::mutex co_mu;
-  bool co_busy = false;
-  std::vector<CoReq*> co_pending;
-  std::atomic<int64_t> n_co_batches{0}, n_co_requests{0};
-  int opt_gemm_debug = 0;
-  int opt_scan_stages = 0;
-  std::atomic<int64_t> prof_ns[2] = {{0}, {0}}, prof_cnt[2] = {{0}, {0}};
-
-  IndexView view() const {
-    IndexView v;
-    v.x32 = x32.as<float>();
-    v.x16 = use_x16 ? x16.as<__half>() : nullptr;
-    v.ids = ids.as<uint64_t>();
-    v.norm = norm.as<float>();
-    v.sumsq = sumsq.as<float>();
-    v.coef = use_x16 ? coef.as<float2>() : nullptr;
-    v.live = live.as<uint32_t>();
-    v.n_slots = n_slots;
-    v.d = (int)dim;
-    v.dpad = dpad;
-    v.dpad16 = dpad16;
-    v.metric = metric;
-    v.ids_identity = ids_identity ? 1 : 0;
-    return v;
-  }
-};
 
 namespace {
 
@@ -506,7 +299,9 @@ SearchCtx* acquire_ctx(gfi_index* h) {
     return c;
   }
   SearchCtx* c = new SearchCtx();
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // (the stream belongs to the index's GPU whatever device the calling thread has current)
+  if (cudaSetDevice(h->device) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return nullptr;
   }
@@ -1047,7 +842,7 @@ int32_t precheck(gfi_index* h, int64_t qdim, bool* empty) {
 // ======================================= C ABI =======================================
 extern "C" {
 
-int32_t gfi_version(void) { return 100; }
+int32_t gfi_version(void) { return 101; }
 
 const char* gfi_last_error(void) { return tl_error.c_str(); }
 
@@ -1096,8 +891,14 @@ int32_t gfi_create(gfi_index** out, int32_t metric, int64_t dim, int32_t device,
   return GFI_OK;
 }
 
+int32_t gfi_create_sharded(gfi_index** out, int32_t metric, int64_t dim, const int32_t* devices, int32_t n_devices,
+                           uint32_t flags) {
+  return sharded_create(out, metric, dim, devices, n_devices, flags);
+}
+
 int32_t gfi_destroy(gfi_index* h) {
   if (!h) return GFI_OK;
+  if (h->shards) { sharded_destroy(h); return GFI_OK; }
   cudaSetDevice(h->device);
   cudaDeviceSynchronize();
   for (auto& c : h->pool) c->release();
@@ -1115,6 +916,7 @@ int32_t gfi_destroy(gfi_index* h) {
 
 int64_t gfi_len(const gfi_index* h) {
   if (!h) return 0;
+  if (h->shards) return sharded_len(h);
   std::shared_lock<std::shared_mutex> g(h->mu);
   // staged rows that overwrite an id already stored replace it at flush (HashMap::insert): count them once
   int64_t staged_new = 0;
@@ -1127,10 +929,11 @@ int64_t gfi_len(const gfi_index* h) {
   return h->n_live + staged_new + (int64_t)h->odd_dim_rows.size();
 }
 int32_t gfi_metric(const gfi_index* h) { return h ? h->metric : -1; }
-int64_t gfi_dim(const gfi_index* h) { return h ? h->dim : 0; }
+int64_t gfi_dim(const gfi_index* h) { return !h ? 0 : h->shards ? sharded_dim(h) : h->dim; }
 
 int32_t gfi_reserve(gfi_index* h, int64_t n_rows) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_reserve(h, n_rows);
   std::unique_lock<std::shared_mutex> g(h->mu);
   if (h->dim == 0) return fail(GFI_ERR_INDEX, "reserve before the dimension is known");
   int32_t rc;
@@ -1246,6 +1049,7 @@ static int32_t add_rows_locked(gfi_index* h, const uint64_t* ids, const float* r
 int32_t gfi_add(gfi_index* h, const uint64_t* ids, const float* rows, int64_t n, int64_t dim) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (n < 0 || (n > 0 && (!ids || (!rows && dim > 0)))) return fail(GFI_ERR_INDEX, "bad arguments");
+  if (h->shards) return sharded_add(h, ids, rows, n, dim);
   std::unique_lock<std::shared_mutex> g(h->mu);
   return add_rows_locked(h, ids, rows, n, dim);
 }
@@ -1261,9 +1065,11 @@ int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int
   const uint32_t dim = (uint32_t)hdr[0] | ((uint32_t)hdr[1] << 8) | ((uint32_t)hdr[2] << 16) | ((uint32_t)hdr[3] << 24);
   const uint32_t count = (uint32_t)hdr[4] | ((uint32_t)hdr[5] << 8) | ((uint32_t)hdr[6] << 16) | ((uint32_t)hdr[7] << 24);
   if (dim == 0) return fail(GFI_ERR_INDEX, "flat file has dimension 0");
-  std::unique_lock<std::shared_mutex> g(h->mu);
-  if (h->dim != 0 && (int64_t)dim != h->dim) {
-    tl_expected = h->dim;
+  std::unique_lock<std::shared_mutex> g(h->mu, std::defer_lock);
+  if (!h->shards) g.lock();  // (a sharded index locks per chunk inside sharded_add)
+  const int64_t have_dim = h->shards ? sharded_dim(h) : h->dim;
+  if (have_dim != 0 && (int64_t)dim != have_dim) {
+    tl_expected = have_dim;
     tl_actual = dim;
     return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
   }
@@ -1276,7 +1082,8 @@ int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int
     if (fread(buf.data(), 4, (size_t)take * dim, f) != (size_t)take * dim)
       return fail(GFI_ERR_INDEX, "flat file is shorter than its header says");
     for (int64_t i = 0; i < take; ++i) ids[(size_t)i] = first_id + (uint64_t)(done + i);
-    int32_t rc = add_rows_locked(h, ids.data(), buf.data(), take, dim);
+    int32_t rc = h->shards ? sharded_add(h, ids.data(), buf.data(), take, dim)
+                           : add_rows_locked(h, ids.data(), buf.data(), take, dim);
     if (rc != GFI_OK) return rc;
     done += take;
     if (out_rows) *out_rows = done;
@@ -1288,6 +1095,7 @@ int32_t gfi_add_generated(gfi_index* h, uint32_t seed, uint64_t first_row, int64
                           uint64_t first_id) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (n <= 0) return GFI_OK;
+  if (h->shards) return sharded_add_generated(h, seed, first_row, n, kind, first_id);
   std::unique_lock<std::shared_mutex> g(h->mu);
   if (h->dim == 0) return fail(GFI_ERR_INDEX, "gfi_add_generated needs an index created with a dimension");
   int32_t rc;
@@ -1319,6 +1127,7 @@ int32_t gfi_add_generated(gfi_index* h, uint32_t seed, uint64_t first_row, int64
 
 int32_t gfi_remove(gfi_index* h, uint64_t id) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_remove(h, id);
   std::unique_lock<std::shared_mutex> g(h->mu);
   if (h->odd_dim_rows.erase(id)) return GFI_OK;
   if (h->st_n > 0) {
@@ -1331,6 +1140,7 @@ int32_t gfi_remove(gfi_index* h, uint64_t id) {
 
 int32_t gfi_flush(gfi_index* h) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_flush(h, false);
   std::unique_lock<std::shared_mutex> g(h->mu);
   int32_t rc = flush_locked(h);
   if (rc != GFI_OK) return rc;
@@ -1340,6 +1150,7 @@ int32_t gfi_flush(gfi_index* h) {
 
 int32_t gfi_compact(gfi_index* h) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_flush(h, true);
   std::unique_lock<std::shared_mutex> g(h->mu);
   int32_t rc = flush_locked(h);
   if (rc != GFI_OK) return rc;
@@ -1348,6 +1159,7 @@ int32_t gfi_compact(gfi_index* h) {
 
 int32_t gfi_get_vector(gfi_index* h, uint64_t id, float* out, int64_t cap, int64_t* out_dim) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_get_vector(h, id, out, cap, out_dim);
   std::unique_lock<std::shared_mutex> g(h->mu);
   int32_t rc = flush_locked(h);
   if (rc != GFI_OK) return rc;
@@ -1417,6 +1229,8 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (q < 0 || (q > 0 && (!queries || !ks || !out_counts))) return fail(GFI_ERR_INDEX, "bad arguments");
   if (q == 0) return GFI_OK;
+  if (h->shards)  // one index over several GPUs: fan out, exchange over NVLink, merge (sharded.cu)
+    return sharded_search(h, queries, q, dim, ks, mask, mask_bits, filter_json, out_ids, out_dist, out_counts, kstride);
   int32_t rc;
   std::shared_lock<std::shared_mutex> g(h->mu, std::defer_lock);
   for (;;) {
@@ -1581,6 +1395,104 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
   return GFI_OK;
 }
 
+}  // extern "C"
+
+// ---- hooks for sharded.cu (namespace gfi, declared in host.h) ----
+namespace gfi {
+
+SearchCtx* host_acquire_ctx(gfi_index* h) { return acquire_ctx(h); }
+void host_release_ctx(gfi_index* h, SearchCtx* c) { release_ctx(h, c); }
+int32_t host_flags_to_status(uint32_t flags) { return flags_to_status(flags); }
+int32_t host_ensure_flushed(gfi_index* h, bool with_metadata) { return ensure_flushed(h, with_metadata); }
+bool host_needs_flush(gfi_index* h, bool with_metadata) {
+  std::shared_lock<std::shared_mutex> g(h->mu);
+  return h->st_n > 0 || h->live_dirty_lo >= 0 || h->needs_reorder || (with_metadata && h->meta_dirty);
+}
+int64_t host_row_bytes(const gfi_index* h) {
+  if (h->shards) return sharded_row_bytes(h);
+  std::shared_lock<std::shared_mutex> g(h->mu);  // (writers mutate these under the unique lock)
+  return h->n_slots * (int64_t)h->dpad * 4;
+}
+
+void shard_account(gfi_index* h, SearchCtx* c, const Ctrl& hc) {
+  prof_collect(h, c);
+  h->n_fallback_q += hc.uncertified;
+  h->n_tensor_q -= hc.routed_scan;
+  h->n_scan_q += hc.routed_scan;
+  if (hc.elig_count) h->last_mask_pop = (int64_t)hc.elig_count - 1;
+  if (c->auto_tensor_q > 0) {
+    const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc.uncertified);
+    if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;
+  }
+}
+
+// The shard-local half of a sharded search: same pipeline as search_impl, but the inputs come from pinned host
+// memory shared by all shards (or from the root GPU), and the results go to wherever the caller points -- for a
+// shard on another GPU that is peer memory of the root GPU, written by the finalize kernels themselves.
+int32_t shard_enqueue(gfi_index* h, SearchCtx* c, const ShardSearch& s) {
+  int32_t rc;
+  std::shared_lock<std::shared_mutex> g(h->mu);  // (the sharded handle's own lock keeps writers away until the end)
+  ++h->n_search;
+  h->n_queries += s.q;
+  bool empty;
+  if ((rc = precheck(h, s.dim, &empty)) != GFI_OK) return rc;
+  FilterProgram prog{};
+  if (s.filter_json) {
+    std::string err;
+    if (!compile_filter(s.filter_json, h->meta_fields, h->meta_values, &prog, &err))
+      return fail(GFI_ERR_INDEX, "bad filter: " + err);
+    for (int i = 0; i < prog.n; ++i)
+      if (prog.ops[i].field >= (int)h->meta_dcols.size()) prog.ops[i].field = -1;
+  }
+  if ((rc = set_device(h)) != GFI_OK) return rc;
+  cudaStream_t st = c->stream;
+  if (s.wait_a) CU_TRY(cudaStreamWaitEvent(st, s.wait_a, 0));
+  if (s.wait_b) CU_TRY(cudaStreamWaitEvent(st, s.wait_b, 0));
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  auto finish = [&]() -> int32_t {
+    CU_TRY(cudaMemcpyAsync(s.out_ctrl, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDefault, st));
+    if (s.done) CU_TRY(cudaEventRecord(s.done, st));
+    return GFI_OK;
+  };
+  if (empty || s.kmax == 0) {
+    CU_TRY(cudaMemsetAsync(s.out_counts, 0, (size_t)s.q * 4, st));
+    if (!s.keep_flags) CU_TRY(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Ctrl), st));
+    return finish();
+  }
+  const int64_t q = s.q, dim = s.dim;
+  const bool masked = s.mask != nullptr || s.filter_json != nullptr;
+  const int64_t mask_bits = s.filter_json ? h->n_slots : s.mask_bits;
+  const size_t mask_words = masked ? (size_t)((mask_bits + 63) / 64) : 0;
+  CU_TRY(c->q_in.ensure((size_t)q * dim * 4));
+  CU_TRY(c->ks.ensure((size_t)q * 4));
+  if (masked) CU_TRY(c->mask.ensure(mask_words * 8 + 8));
+  // cudaMemcpyDefault: pinned host memory or the root GPU's memory alike (unified addressing)
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, s.queries, (size_t)q * dim * 4, cudaMemcpyDefault, st));
+  CU_TRY(cudaMemcpyAsync(c->ks.p, s.ks, (size_t)q * 4, cudaMemcpyDefault, st));
+  if (s.mask) CU_TRY(cudaMemcpyAsync(c->mask.p, s.mask, mask_words * 8, cudaMemcpyDefault, st));
+  if (s.filter_json) {
+    CU_TRY(cudaMemsetAsync(c->mask.p, 0, mask_words * 8 + 8, st));
+    CU_TRY(launch_eval_filter(prog, h->meta_dptrs.as<const uint32_t*>(), h->meta_synced_slots, h->n_slots,
+                              c->mask.as<uint64_t>(), st));
+    ++h->n_launch;
+  }
+  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), s.kmax, masked ? c->mask.as<uint64_t>() : nullptr,
+               mask_bits, s.out_ids, s.out_dist, s.out_counts, s.kstride};
+  a.mask_by_slot = s.filter_json != nullptr;
+  if (s.mask && s.mask_density >= 0.0) a.mask_popcount = (int64_t)(s.mask_density * (double)h->n_slots);
+  a.keep_flags = s.keep_flags;
+  c->zc_pending = false;
+  c->ctrl_dev = c->ctrl.p;
+  rc = enqueue_search(h, c, a, st);
+  c->ctrl_dev = nullptr;
+  if (rc != GFI_OK) { cudaStreamSynchronize(st); return rc; }
+  return finish();
+}
+
+}  // namespace gfi
+
+extern "C" {
+
 // k beyond the kernels' list capacity (FlatIndex::search accepts any k, src/flat_index.rs:63).  Queries with
 // k <= kMaxListK run as one ordinary batch; each larger one is answered in passes of kMaxListK results: a pass is an
 // exact search over the rows not returned yet (slot-indexed eligibility mask), so the concatenation of the passes
@@ -1718,15 +1630,16 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
   if (h && !mask && q > 0 && ks) {
     bool bigk = false;
     for (int64_t i = 0; i < q; ++i) bigk = bigk || ks[i] > kMaxListK;
-    if (bigk) return search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride);
+    if (bigk)
+      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride)
+                       : search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride);
   }
   // masked searches, large batches and malformed calls take the direct path
   // (indexes below 32 MB are launch-latency-bound: independent calls on separate streams overlap on the GPU and
   // beat a serialised batch -- measured 68-75k vs 53k q/s at 10k x 128 -- so only large ones are coalesced)
   bool plain = h && !mask && q > 0 && q <= 256 && queries && ks && out_counts && out_ids && out_dist;
   if (plain) {
-    std::shared_lock<std::shared_mutex> g(h->mu);  // (writers mutate these under the unique lock)
-    plain = h->opt_coalesce && h->n_slots * (int64_t)h->dpad * 4 >= (32ll << 20);
+    plain = h->opt_coalesce && host_row_bytes(h) >= (32ll << 20);
   }
   if (plain)
     for (int64_t i = 0; i < q; ++i)
@@ -1791,6 +1704,7 @@ int32_t gfi_search_filtered(gfi_index* h, const float* queries, int64_t q, int64
 int32_t gfi_set_metadata(gfi_index* h, uint64_t id, int32_t n_fields, const char* const* keys,
                          const char* const* values) {
   if (!h || n_fields < 0 || (n_fields > 0 && (!keys || !values))) return fail(GFI_ERR_INDEX, "bad arguments");
+  if (h->shards) return sharded_set_metadata(h, id, n_fields, keys, values);
   std::unique_lock<std::shared_mutex> g(h->mu);
   std::vector<std::pair<int, uint32_t>> enc;
   enc.reserve((size_t)n_fields);
@@ -1828,6 +1742,9 @@ int32_t gfi_search_device(gfi_index* h, const float* d_queries, int64_t q, const
                           uint32_t* d_out_counts, int64_t kstride, void* stream) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (q <= 0) return GFI_OK;
+  if (h->shards)
+    return sharded_search_device(h, d_queries, q, d_ks, kmax, d_mask, mask_bits, d_out_ids, d_out_dist, d_out_counts,
+                                 kstride, stream);
   int32_t rc = ensure_flushed(h);
   if (rc != GFI_OK) return rc;
   std::shared_lock<std::shared_mutex> g(h->mu);
@@ -1871,6 +1788,7 @@ int32_t gfi_search_device(gfi_index* h, const float* d_queries, int64_t q, const
 
 int32_t gfi_search_status(gfi_index* h) {
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
+  if (h->shards) return sharded_search_status(h);
   SearchCtx* c = tl_dev_ctx;
   if (!c || tl_dev_owner != h) return GFI_OK;
   tl_dev_ctx = nullptr;
@@ -1921,6 +1839,7 @@ int32_t gfi_distances(gfi_index* h, const float* queries, int64_t q, int64_t dim
   if (!h) return fail(GFI_ERR_INDEX, "null handle");
   if (q < 0 || m < 0 || (q > 0 && m > 0 && (!queries || !cand_ids || !out_dist))) return fail(GFI_ERR_INDEX, "bad arguments");
   if (q == 0 || m == 0) return GFI_OK;
+  if (h->shards) return sharded_distances(h, queries, q, dim, cand_ids, m, out_dist, out_status);
   int32_t rc = ensure_flushed(h);
   if (rc != GFI_OK) return rc;
   std::shared_lock<std::shared_mutex> g(h->mu);
@@ -1990,6 +1909,7 @@ int32_t gfi_distances(gfi_index* h, const float* queries, int64_t q, int64_t dim
 
 int32_t gfi_debug_tensor_scores(gfi_index* h, const float* queries, int64_t q, float* out, int64_t out_stride) {
   if (!h || !queries || !out || q <= 0) return fail(GFI_ERR_INDEX, "bad arguments");
+  if (h->shards) return fail(GFI_ERR_INDEX, "gfi_debug_tensor_scores: single-GPU handles only");
   int32_t rc = ensure_flushed(h);
   if (rc != GFI_OK) return rc;
   std::shared_lock<std::shared_mutex> g(h->mu);
@@ -2043,6 +1963,9 @@ int32_t gfi_debug_tensor_scores(gfi_index* h, const float* queries, int64_t q, f
 
 int32_t gfi_get_stats(gfi_index* h, gfi_stats* out) {
   if (!h || !out) return fail(GFI_ERR_INDEX, "null argument");
+  memset(out, 0, sizeof(*out));
+  out->shards = 1;
+  if (h->shards) return sharded_get_stats(h, out);
   std::shared_lock<std::shared_mutex> g(h->mu);
   out->n_slots = h->n_slots;
   out->n_live = h->n_live;
@@ -2065,6 +1988,7 @@ int32_t gfi_get_stats(gfi_index* h, gfi_stats* out) {
 
 int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   if (!h || !name) return fail(GFI_ERR_INDEX, "null argument");
+  if (h->shards) return sharded_set_option(h, name, value);
   std::unique_lock<std::shared_mutex> g(h->mu);
   const std::string n(name);
   if (n == "tensor_min_q") h->opt_tensor_min_q = (int)value;

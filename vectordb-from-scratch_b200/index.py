@@ -46,10 +46,16 @@ def pack_mask(bits):
 class GpuFlatIndex:
     """Drop-in for FlatIndex behind `trait Index`.  All compute runs in libgfi.so on a B200."""
 
-    def __init__(self, metric=DistanceMetric.Euclidean, dim=0, device=0, flags=0):
+    def __init__(self, metric=DistanceMetric.Euclidean, dim=0, device=0, flags=0, devices=None):
+        """`devices`: a list of GPU ordinals -> ONE index sharded row-wise over them inside libgfi
+        (gfi_create_sharded; devices[0] merges).  Every method below works on such a handle unchanged."""
         self._L = native.lib()
         self._h = ctypes.c_void_p()
-        rc = self._L.gfi_create(ctypes.byref(self._h), int(metric), int(dim), int(device), int(flags))
+        if devices is not None:
+            devs = (ctypes.c_int32 * len(devices))(*[int(x) for x in devices])
+            rc = self._L.gfi_create_sharded(ctypes.byref(self._h), int(metric), int(dim), devs, len(devices), int(flags))
+        else:
+            rc = self._L.gfi_create(ctypes.byref(self._h), int(metric), int(dim), int(device), int(flags))
         if rc:
             self._h = None
             _raise(self._L, rc)

@@ -39,7 +39,8 @@ class GfiStats(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int64) for n in (
         "n_slots", "n_live", "searches", "queries", "scan_queries", "tensor_queries", "fallback_queries",
         "kernel_launches", "bytes_fp32", "bytes_fp16", "scan_kernel_ns", "scan_kernel_count",
-        "tensor_kernel_ns", "tensor_kernel_count", "coalesced_batches", "coalesced_requests")]
+        "tensor_kernel_ns", "tensor_kernel_count", "coalesced_batches", "coalesced_requests", "shards", "merge_ns",
+        "merge_count")]
 
 
 def lib():
@@ -59,6 +60,7 @@ def lib():
         "gfi_last_error": (c.c_char_p, []),
         "gfi_last_mismatch": (None, [c.POINTER(i64), c.POINTER(i64)]),
         "gfi_create": (i32, [c.POINTER(vp), i32, i64, i32, u32]),
+        "gfi_create_sharded": (i32, [c.POINTER(vp), i32, i64, c.POINTER(i32), i32, u32]),
         "gfi_destroy": (i32, [vp]),
         "gfi_add": (i32, [vp, vp, vp, i64, i64]),
         "gfi_add_generated": (i32, [vp, u32, u64, i64, i32, u64]),
