@@ -154,6 +154,14 @@ int32_t gfi_search(gfi_index *h, const float *queries, int64_t q, int64_t dim, c
  */
 int32_t gfi_set_metadata(gfi_index *h, uint64_t id, int32_t n_fields, const char *const *keys,
                          const char *const *values);
+
+/*
+ * Bulk form for ONE field over many rows: field `key` of ids[i] becomes values[codes[i]] (codes[i] = UINT32_MAX:
+ * the field is absent); the other fields of those ids are left as they are.  This loads the reference's
+ * `metadata: HashMap<usize, Metadata>` (src/storage.rs:90) at ingest speed instead of one call per row.
+ */
+int32_t gfi_set_metadata_column(gfi_index *h, const char *key, const uint64_t *ids, int64_t n,
+                                const char *const *values, int32_t n_values, const uint32_t *codes);
 int32_t gfi_search_filtered(gfi_index *h, const float *queries, int64_t q, int64_t dim, const uint32_t *ks,
                             const char *filter_json, uint64_t *out_ids, float *out_dist, uint32_t *out_counts,
                             int64_t kstride);

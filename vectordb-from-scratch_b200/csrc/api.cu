@@ -1734,6 +1734,59 @@ int32_t gfi_set_metadata(gfi_index* h, uint64_t id, int32_t n_fields, const char
   return GFI_OK;
 }
 
+// Bulk form for ONE field over many rows (loading the reference's `HashMap<usize, Metadata>`, src/storage.rs:90,
+// at ingest speed instead of one call per row).  Stored rows are written straight into the field's column; ids that
+// are not stored yet go through the pending map like gfi_set_metadata's.
+int32_t gfi_set_metadata_column(gfi_index* h, const char* key, const uint64_t* ids, int64_t n,
+                                const char* const* values, int32_t n_values, const uint32_t* codes) {
+  if (!h || !key || n < 0 || n_values < 0 || (n > 0 && (!ids || !codes)) || (n_values > 0 && !values))
+    return fail(GFI_ERR_INDEX, "bad arguments");
+  if (h->shards) return sharded_set_metadata_column(h, key, ids, n, values, n_values, codes);
+  std::unique_lock<std::shared_mutex> g(h->mu);
+  int32_t rc = flush_locked(h);
+  if (rc != GFI_OK) return rc;
+  if (h->needs_reorder && (rc = compact_locked(h)) != GFI_OK) return rc;
+  int f;
+  auto it = h->meta_fields.find(key);
+  if (it == h->meta_fields.end()) {
+    f = (int)h->meta_values.size();
+    h->meta_fields[key] = f;
+    h->meta_values.emplace_back();
+  } else {
+    f = it->second;
+  }
+  auto& dict = h->meta_values[(size_t)f];
+  std::vector<uint32_t> code_of((size_t)n_values);
+  for (int32_t v = 0; v < n_values; ++v) {
+    auto vt = dict.find(values[v]);
+    if (vt == dict.end()) {
+      code_of[(size_t)v] = (uint32_t)dict.size() + 1u;
+      dict[values[v]] = code_of[(size_t)v];
+    } else {
+      code_of[(size_t)v] = vt->second;
+    }
+  }
+  h->meta_cols.resize(h->meta_values.size());
+  for (auto& c : h->meta_cols) c.resize((size_t)h->n_slots, 0u);
+  auto& col = h->meta_cols[(size_t)f];
+  for (int64_t i = 0; i < n; ++i) {
+    if (codes[i] != UINT32_MAX && codes[i] >= (uint32_t)n_values) return fail(GFI_ERR_INDEX, "metadata code out of range");
+    const uint32_t code = codes[i] == UINT32_MAX ? 0u : code_of[codes[i]];
+    uint32_t slot;
+    if (lookup_slot(h, ids[i], &slot)) {
+      col[slot] = code;
+    } else if (code) {  // not stored yet: merged into whatever is pending for the id
+      auto& pend = h->meta_pending[ids[i]];
+      bool found = false;
+      for (auto& fv : pend)
+        if (fv.first == f) { fv.second = code; found = true; }
+      if (!found) pend.emplace_back(f, code);
+    }
+  }
+  h->meta_dirty = true;
+  return GFI_OK;
+}
+
 static thread_local SearchCtx* tl_dev_ctx = nullptr;
 static thread_local gfi_index* tl_dev_owner = nullptr;
 

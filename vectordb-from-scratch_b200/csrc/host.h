@@ -191,6 +191,8 @@ int32_t sharded_search_device(gfi_index* h, const float* d_queries, int64_t q, c
 int32_t sharded_search_status(gfi_index* h);
 int32_t sharded_set_metadata(gfi_index* h, uint64_t id, int32_t n_fields, const char* const* keys,
                              const char* const* values);
+int32_t sharded_set_metadata_column(gfi_index* h, const char* key, const uint64_t* ids, int64_t n,
+                                    const char* const* values, int32_t n_values, const uint32_t* codes);
 int32_t sharded_distances(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint64_t* cand_ids,
                           int64_t m, float* out_dist, uint8_t* out_status);
 int32_t sharded_get_stats(gfi_index* h, gfi_stats* out);

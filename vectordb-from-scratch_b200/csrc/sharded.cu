@@ -563,6 +563,31 @@ int32_t sharded_set_metadata(gfi_index* H, uint64_t id, int32_t n_fields, const 
   return gfi_set_metadata(H->shards->sub[(size_t)H->shards->shard_of(id)], id, n_fields, keys, values);
 }
 
+int32_t sharded_set_metadata_column(gfi_index* H, const char* key, const uint64_t* ids, int64_t n,
+                                    const char* const* values, int32_t n_values, const uint32_t* codes) {
+  ShardSet* S = H->shards;
+  std::unique_lock<std::shared_mutex> lk(H->mu);
+  struct Piece { int64_t at, len; };
+  std::vector<std::vector<Piece>> pieces((size_t)S->G);
+  for (int64_t i = 0; i < n;) {
+    const int g = S->shard_of(ids[i]);
+    int64_t j = i + 1;
+    while (j < n && S->shard_of(ids[j]) == g) ++j;
+    pieces[(size_t)g].push_back({i, j - i});
+    i = j;
+  }
+  // every shard learns the field and the dictionary (same codes everywhere is not required: filters compile per shard)
+  return S->on_shards(S->all(), [&](int g) -> int32_t {
+    if (pieces[(size_t)g].empty())
+      return gfi_set_metadata_column(S->sub[(size_t)g], key, nullptr, 0, values, n_values, nullptr);
+    for (const Piece& p : pieces[(size_t)g]) {
+      int32_t rc = gfi_set_metadata_column(S->sub[(size_t)g], key, ids + p.at, p.len, values, n_values, codes + p.at);
+      if (rc != GFI_OK) return rc;
+    }
+    return GFI_OK;
+  });
+}
+
 int32_t sharded_search(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
                        const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
                        float* out_dist, uint32_t* out_counts, int64_t kstride) {

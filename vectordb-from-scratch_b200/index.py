@@ -193,6 +193,15 @@ class GpuFlatIndex:
         vals = (ctypes.c_char_p * max(n, 1))(*[v.encode() for _, v in items])
         self._chk(self._L.gfi_set_metadata(self._h, int(id), n, keys, vals))
 
+    def set_metadata_column(self, key, ids, values, codes):
+        """Bulk form: field `key` of ids[i] = values[codes[i]] (code 0xFFFFFFFF: absent); other fields untouched."""
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        codes = np.ascontiguousarray(codes, dtype=np.uint32)
+        assert ids.shape == codes.shape
+        vals = (ctypes.c_char_p * max(len(values), 1))(*[v.encode() for v in values])
+        self._chk(self._L.gfi_set_metadata_column(self._h, key.encode(), ids.ctypes.data if ids.size else None,
+                                                  ids.size, vals, len(values), codes.ctypes.data if codes.size else None))
+
     def search_filtered(self, queries, ks, filter_json):
         """FlatIndex::search over the rows matching a MetadataFilter (the reference's JSON form,
         src/storage.rs:44-58), with the filter evaluated on the GPU.  Array form like search_arrays."""

@@ -76,6 +76,7 @@ def lib():
         "gfi_search": (i32, [vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, i64]),
         "gfi_search_filtered": (i32, [vp, vp, i64, i64, vp, c.c_char_p, vp, vp, vp, i64]),
         "gfi_set_metadata": (i32, [vp, u64, i32, c.POINTER(c.c_char_p), c.POINTER(c.c_char_p)]),
+        "gfi_set_metadata_column": (i32, [vp, c.c_char_p, vp, i64, c.POINTER(c.c_char_p), i32, vp]),
         "gfi_search_device": (i32, [vp, vp, i64, vp, u32, vp, i64, vp, vp, vp, i64, vp]),
         "gfi_search_status": (i32, [vp]),
         "gfi_merge_topk_device": (i32, [vp, vp, vp, i32, i64, i64, vp, vp, vp, vp, i64, vp]),
