@@ -40,6 +40,10 @@ typedef struct gfi_index gfi_index;
 #define GFI_ERR_INVALID_VECTOR 2     /* VectorDbError::InvalidVector (cosine with a zero-norm query or row) */
 #define GFI_ERR_INDEX 3              /* VectorDbError::IndexError(String): CUDA failure, bad argument, ... */
 #define GFI_ERR_NAN 4                /* a distance is NaN: the reference panics (flat_index.rs:62); we report */
+#define GFI_ERR_UNPROVEN 5           /* gfi_search_status only: a device-resident search met more near-ties of the
+                                        k-th distance than the kernels' candidate lists hold and could not PROVE its
+                                        answer exact; re-run those queries through gfi_search, which proves them by
+                                        paging (host searches never return this code) */
 
 /* DistanceMetric, reference src/distance.rs:9-16 */
 #define GFI_METRIC_EUCLIDEAN 0
@@ -238,6 +242,8 @@ typedef struct gfi_stats {
    * from the moment the last shard's candidates have arrived to the end of the merge kernel, summed. */
   int64_t shards;
   int64_t merge_ns, merge_count;
+  /* host searches whose fp32-scan answer the device could not certify and that were proven exact by paging */
+  int64_t paged_queries;
 } gfi_stats;
 int32_t gfi_get_stats(gfi_index *h, gfi_stats *out);
 

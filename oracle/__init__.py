@@ -5,5 +5,5 @@ legs may import this package.  See flat_oracle.c for what it restates and why.
 """
 from .oracle import (  # noqa: F401
     METRICS, OracleError, build, distance, norm, flat_search, search_post_filter,
-    search_batch, gen_rows, max_threads,
+    search_batch, search_generated, gen_rows, max_threads,
 )

@@ -277,6 +277,104 @@ void orc_gen_rows(uint32_t seed, uint64_t first_row, int64_t n, int64_t d, int k
       out[r * d + c] = orc_gen_elem(seed, first_row + (uint64_t)r, (uint32_t)c, kind);
 }
 
+/*
+ * FlatIndex::search over GENERATED rows, rows-parallel: the checker for full-size configurations (10M x 768 does
+ * not fit a test process as an array, and one query over it takes 14 s on one core).  Row r is
+ * orc_gen_elem(seed, first_row + r, *, kind) with id first_id + r, produced on the fly; every thread walks a
+ * contiguous range of rows, scores ALL q queries against each row it generates (same sequential arithmetic as
+ * orc_distance) and keeps, per query, its k best by (distance, id); the per-thread lists are then merged by the
+ * same order.  The k smallest of a set under a total order do not depend on how the set was partitioned, so the
+ * result equals score-all + sort + truncate(k) (flat_index.rs:52-65) with the stated tie rule.
+ *   eligible: optional bitmask over rows (bit r of word r/64).  Output kmax-strided like orc_search_batch.
+ */
+int orc_search_generated(int metric, uint32_t seed, uint64_t first_row, uint64_t first_id, int64_t n, int64_t d,
+                         int kind, const uint64_t *eligible, const float *queries, int64_t q, const int64_t *ks,
+                         int64_t kmax, uint64_t *out_ids, float *out_dist, int64_t *out_counts, int threads) {
+  if (threads < 1) threads = 1;
+  int rc_all = ORC_OK;
+  orc_pair *best = (orc_pair *)malloc(sizeof(orc_pair) * (size_t)threads * (size_t)q * (size_t)kmax);
+  int64_t *have = (int64_t *)calloc((size_t)threads * (size_t)q, sizeof(int64_t));
+  float *qnorm = (float *)malloc(sizeof(float) * (size_t)(q > 0 ? q : 1));
+  for (int64_t i = 0; i < q; ++i) qnorm[i] = orc_norm(queries + i * d, d);
+#ifdef _OPENMP
+#pragma omp parallel num_threads(threads)
+#endif
+  {
+#ifdef _OPENMP
+    const int t = omp_get_thread_num(), nt = omp_get_num_threads();
+#else
+    const int t = 0, nt = 1;
+#endif
+    float *row = (float *)malloc(sizeof(float) * (size_t)d);
+    const int64_t lo = n * t / nt, hi = n * (t + 1) / nt;
+    int rc = ORC_OK;
+    for (int64_t r = lo; r < hi && rc == ORC_OK; ++r) {
+      if (eligible && !((eligible[r >> 6] >> (r & 63)) & 1ull)) continue;
+      for (int64_t c = 0; c < d; ++c) row[c] = orc_gen_elem(seed, first_row + (uint64_t)r, (uint32_t)c, kind);
+      const float xn = metric == ORC_COSINE ? orc_norm(row, d) : 1.0f;
+      for (int64_t i = 0; i < q; ++i) {
+        const float *qv = queries + i * d;
+        float dist;
+        if (metric == ORC_EUCLIDEAN) {
+          dist = orc_euclidean(qv, row, d);
+        } else if (metric == ORC_DOT) {
+          dist = -orc_dot(qv, row, d);
+        } else {
+          if (qnorm[i] == 0.0f || xn == 0.0f) { rc = ORC_INVALID_VECTOR; break; }
+          float sim = orc_dot(qv, row, d) / (qnorm[i] * xn);
+          if (sim < -1.0f) sim = -1.0f;
+          else if (sim > 1.0f) sim = 1.0f;
+          dist = 1.0f - sim;
+        }
+        if (dist != dist) { rc = ORC_NAN; break; }
+        const int64_t k = ks[i];
+        if (k <= 0) continue;
+        orc_pair *lst = best + ((size_t)t * (size_t)q + (size_t)i) * (size_t)kmax;
+        int64_t *m = have + (size_t)t * (size_t)q + (size_t)i;
+        orc_pair cand;
+        cand.dist = dist;
+        cand.id = first_id + (uint64_t)r;
+        if (*m == k && pair_cmp(&cand, &lst[k - 1]) >= 0) continue;
+        int64_t pos = *m < k ? (*m)++ : k - 1; /* insertion into the ascending list */
+        while (pos > 0 && pair_cmp(&cand, &lst[pos - 1]) < 0) {
+          lst[pos] = lst[pos - 1];
+          --pos;
+        }
+        lst[pos] = cand;
+      }
+    }
+    free(row);
+    if (rc != ORC_OK) {
+#ifdef _OPENMP
+#pragma omp critical
+#endif
+      rc_all = rc;
+    }
+  }
+  if (rc_all == ORC_OK) {
+    orc_pair *all = (orc_pair *)malloc(sizeof(orc_pair) * (size_t)threads * (size_t)(kmax > 0 ? kmax : 1));
+    for (int64_t i = 0; i < q; ++i) {
+      int64_t m = 0;
+      for (int t = 0; t < threads; ++t) {
+        const orc_pair *lst = best + ((size_t)t * (size_t)q + (size_t)i) * (size_t)kmax;
+        for (int64_t j = 0; j < have[(size_t)t * (size_t)q + (size_t)i]; ++j) all[m++] = lst[j];
+      }
+      qsort(all, (size_t)m, sizeof(orc_pair), pair_cmp);
+      const int64_t take = ks[i] < m ? ks[i] : m;
+      for (int64_t j = 0; j < take; ++j) {
+        out_ids[i * kmax + j] = all[j].id;
+        out_dist[i * kmax + j] = all[j].dist;
+      }
+      out_counts[i] = take;
+    }
+    free(all);
+  }
+  free(best);
+  free(have);
+  free(qnorm);
+  return rc_all;
+}
+
 int orc_max_threads(void) {
 #ifdef _OPENMP
   return omp_get_max_threads();

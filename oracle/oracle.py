@@ -46,6 +46,10 @@ def _load():
         lib.orc_search_batch.argtypes = [ctypes.c_int, f32p, u64p, ctypes.c_int64, ctypes.c_int64, u64p,
                                          f32p, ctypes.c_int64, ctypes.c_int64, i64p, ctypes.c_int64,
                                          u64p, f32p, i64p, ctypes.c_int]
+        lib.orc_search_generated.restype = ctypes.c_int
+        lib.orc_search_generated.argtypes = [ctypes.c_int, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint64,
+                                             ctypes.c_int64, ctypes.c_int64, ctypes.c_int, u64p, f32p,
+                                             ctypes.c_int64, i64p, ctypes.c_int64, u64p, f32p, i64p, ctypes.c_int]
         lib.orc_gen_rows.restype = None
         lib.orc_gen_rows.argtypes = [ctypes.c_uint32, ctypes.c_uint64, ctypes.c_int64, ctypes.c_int64,
                                      ctypes.c_int, f32p]
@@ -137,6 +141,33 @@ def search_batch(metric, rows, queries, ks, ids=None, eligible=None, threads=1):
                                   _p(el, ctypes.c_uint64), _p(queries, ctypes.c_float), q, dq,
                                   _p(ks, ctypes.c_int64), kmax, _p(out_ids, ctypes.c_uint64),
                                   _p(out_d, ctypes.c_float), _p(cnt, ctypes.c_int64), int(threads))
+    if rc:
+        raise OracleError(rc)
+    return [(out_ids[i, :cnt[i]].copy(), out_d[i, :cnt[i]].copy()) for i in range(q)]
+
+
+def search_generated(metric, seed, first_row, n, d, kind, queries, ks, eligible=None, first_id=0, threads=None):
+    """FlatIndex::search over rows gen_rows(seed, first_row, n, d, kind) produced on the fly (ids first_id + r),
+    rows-parallel: the full-size checker.  Returns list of (ids, dist) per query."""
+    queries = _rows(queries)
+    q = queries.shape[0]
+    assert queries.shape[1] == d
+    ks = np.ascontiguousarray(np.broadcast_to(np.asarray(ks, dtype=np.int64), (q,)))
+    kmax = max(int(ks.max()) if q else 0, 1)
+    el = None if eligible is None else pack_mask(eligible)
+    out_ids = np.zeros((q, kmax), dtype=np.uint64)
+    out_d = np.zeros((q, kmax), dtype=np.float32)
+    cnt = np.zeros(q, dtype=np.int64)
+    if threads is None:
+        import os
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    rc = _load().orc_search_generated(_metric(metric), seed, first_row, first_id, n, d, kind,
+                                      _p(el, ctypes.c_uint64), _p(queries, ctypes.c_float), q,
+                                      _p(ks, ctypes.c_int64), kmax, _p(out_ids, ctypes.c_uint64),
+                                      _p(out_d, ctypes.c_float), _p(cnt, ctypes.c_int64), int(threads))
     if rc:
         raise OracleError(rc)
     return [(out_ids[i, :cnt[i]].copy(), out_d[i, :cnt[i]].copy()) for i in range(q)]

@@ -20,6 +20,60 @@ def test_library_exports_every_declared_symbol():
     assert gfi.lib().gfi_version() >= 100
 
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def build_c_client():
+    """gcc -Wall -Werror against include/gfi.h, linked against libgfi.so (no compute call happens at build time)."""
+    import subprocess
+    src = os.path.join(ROOT, "tests", "c_client", "abi_client.c")
+    exe = os.path.join(ROOT, "tests", "c_client", "abi_client")
+    lib_dir = os.path.dirname(gfi.lib_path())
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), src, "-L", lib_dir,
+                           "-lgfi", f"-Wl,-rpath,{lib_dir}", "-lm", "-o", exe])
+    return exe
+
+
+def test_c_client_compiles_and_links_against_the_header():
+    assert os.path.exists(build_c_client())
+
+
+def _c_arg_counts():
+    """function name -> number of parameters, from include/gfi.h"""
+    import re
+    text = open(os.path.join(ROOT, "include", "gfi.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(gfi_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def test_rust_sys_crate_declares_every_header_symbol():
+    """rust/gpu-flat-index-sys/src/lib.rs is not compiled here (no cargo): keep it in step with the header --
+    same function set, same number of arguments, gfi_stats with the header's fields in the header's order."""
+    import re
+    rs = open(os.path.join(ROOT, "rust", "gpu-flat-index-sys", "src", "lib.rs")).read()
+    decl = {}
+    for m in re.finditer(r"pub fn (gfi_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S):
+        args = m.group(2).strip()
+        decl[m.group(1)] = 0 if not args else len([a for a in args.split(",") if a.strip()])
+    c = _c_arg_counts()
+    assert set(c) == set(gfi.DECLARED_SYMBOLS)
+    assert decl == c, {k: (decl.get(k), c.get(k)) for k in set(decl) | set(c) if decl.get(k) != c.get(k)}
+    from vectordb_from_scratch_b200 import native
+    fields = re.findall(r"pub (\w+): i64", rs)
+    assert fields == [n for n, _ in native.GfiStats._fields_]
+    hdr = open(os.path.join(ROOT, "include", "gfi.h")).read()
+    hdr_stats = hdr[hdr.index("typedef struct gfi_stats"):hdr.index("} gfi_stats;")]
+    hdr_stats = re.sub(r"/\*.*?\*/", "", hdr_stats, flags=re.S)
+    hdr_fields = [f.strip() for line in re.findall(r"int64_t ([^;]+);", hdr_stats) for f in line.split(",")]
+    assert hdr_fields == fields
+    for code in re.findall(r"#define (GFI_[A-Z_]+) (\d+)", hdr):
+        assert re.search(rf"pub const {code[0]}: [iu]32 = {code[1]};", rs), code
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():

@@ -648,9 +648,8 @@ def test_device_side_route_of_small_batches_with_a_device_mask():
 
 # ---------------------------------------------------------------- full-size checks (BASELINE.json configs)
 def test_full_size_c2_cosine_batch_against_oracle_subset():
-    """C2: 1M x 768 cosine, batch 1024, k = 10.  The whole batch runs on the tcgen05 path; the oracle
-    (about 1 s per query on a host core) checks a subset of the queries bit for bit, and
-    size-independent properties are checked for all of them."""
+    """C2: 1M x 768 cosine, batch 1024, k = 10.  The whole batch runs on the tcgen05 path; the oracle checks 32 of
+    the queries at full size, and size-independent properties are checked for all of them."""
     n, d, q, k = 1_000_000, 768, 1024, 10
     idx = gfi.GpuFlatIndex(DM.Cosine, dim=d)
     idx.reserve(n)
@@ -667,11 +666,11 @@ def test_full_size_c2_cosine_batch_against_oracle_subset():
     idx.set_option("tensor_min_q", 1 << 30)
     ids_s, dist_s, _ = idx.search_arrays(queries[:8], k)
     assert np.array_equal(ids_s, ids[:8]) and np.array_equal(dist_s, dist[:8])
-    # bit-exact oracle parity on 4 queries at full size
-    rows = oracle.gen_rows(3, 0, n, d, 1)
-    exp = oracle.search_batch("cosine", rows, queries[:4], k, threads=4)
-    for i, (eids, ed) in enumerate(exp):
-        assert_topk_matches(ids[i], dist[i], eids, ed, ctx=f"C2 full q{i}")
+    # oracle parity on 32 queries at full size (rows-parallel oracle over the generated rows)
+    pick = np.arange(0, q, q // 32)[:32]
+    exp = oracle.search_generated("cosine", 3, 0, n, d, 1, queries[pick], k)
+    for j, (eids, ed) in zip(pick, exp):
+        assert_topk_matches(ids[j], dist[j], eids, ed, ctx=f"C2 full q{j}")
 
 
 # ---------------------------------------------------------------- concurrency (B2: &self searches under RwLock::read)
@@ -778,8 +777,8 @@ def test_bulk_ingest_from_reference_flat_file(tmp_path):
 # ---------------------------------------------------------------- more full-size checks (BASELINE.json configs)
 def test_full_size_c5_shard_l2_batch4096_against_oracle_subset():
     """C5 shard: 12.5M x 128 Euclidean, batch 4096, k = 10 (one GPU's share of the 100M index).  The
-    whole batch runs on the tcgen05 path; 4 queries are checked bit for bit against the oracle at
-    full size, 16 against the independent exact-scan path, all for sortedness / idempotence."""
+    whole batch runs on the tcgen05 path; 32 queries are checked against the oracle at full size, 16 against
+    the independent exact-scan path, all for sortedness / idempotence."""
     n, d, q, k = 12_500_000, 128, 4096, 10
     idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
     idx.reserve(n)
@@ -792,10 +791,10 @@ def test_full_size_c5_shard_l2_batch4096_against_oracle_subset():
     idx.set_option("tensor_min_q", 1 << 30)
     ids_s, dist_s, _ = idx.search_arrays(queries[:16], k)
     assert np.array_equal(ids_s, ids[:16]) and np.array_equal(dist_s, dist[:16])
-    rows = oracle.gen_rows(7, 0, n, d, 0)
-    exp = oracle.search_batch("euclidean", rows, queries[:4], k, threads=4)
-    for i, (eids, ed) in enumerate(exp):
-        assert_topk_matches(ids[i], dist[i], eids, ed, ctx=f"C5 full q{i}")
+    pick = np.arange(0, q, q // 32)[:32]
+    exp = oracle.search_generated("euclidean", 7, 0, n, d, 0, queries[pick], k)
+    for j, (eids, ed) in zip(pick, exp):
+        assert_topk_matches(ids[j], dist[j], eids, ed, ctx=f"C5 full q{j}")
 
 
 def test_full_size_c3_c4_properties():
@@ -845,6 +844,67 @@ def test_full_size_c3_c4_properties():
     s_ids, s_d, s_c = idx.search_arrays(qs[:2], k)        # forced onto the fp32 scan path (C3a as specified)
     assert idx.stats()["scan_queries"] == 2
     assert np.array_equal(s_ids, t_ids[:2]) and np.array_equal(s_d, t_d[:2])
+
+
+def test_full_size_c3_dot_k100_against_the_oracle():
+    """C3a / C3b at full size against the ORACLE: 10M x 768 dot, k = 100, bench.py's own seeds.
+    Eight queries of the batch-64 answer (tcgen05 path, 16 384-key select staging), the same eight as single queries
+    through the cost-model route, and two on the fp32 scan (tensor_auto = 0)."""
+    n, d, k = 10_000_000, 768, 100
+    idx = gfi.GpuFlatIndex(DM.DotProduct, dim=d)
+    idx.reserve(n)
+    idx.add_generated(5, 0, n, 1, 0)
+    qs = oracle.gen_rows(6, 0, 64, d, 1)
+    t_ids, t_d, t_c = idx.search_arrays(qs, k)
+    assert idx.stats()["tensor_queries"] == 64 and np.all(t_c == k)
+    pick = np.arange(0, 64, 8)
+    exp = oracle.search_generated("dot", 5, 0, n, d, 1, qs[pick], k)
+    for j, (eids, ed) in zip(pick, exp):
+        assert_topk_matches(t_ids[j], t_d[j], eids, ed, ctx=f"C3b q{j}")
+    for j, (eids, ed) in zip(pick, exp):  # C3a: one query per call
+        a_ids, a_d, a_c = idx.search_arrays(qs[j:j + 1], k)
+        assert_topk_matches(a_ids[0], a_d[0], eids, ed, ctx=f"C3a routed q{j}")
+    assert idx.stats()["scan_queries"] == 0
+    idx.set_option("tensor_auto", 0)
+    for j, (eids, ed) in list(zip(pick, exp))[:2]:
+        s_ids, s_d, s_c = idx.search_arrays(qs[j:j + 1], k)
+        assert_topk_matches(s_ids[0], s_d[0], eids, ed, ctx=f"C3a scan q{j}")
+    st = idx.stats()
+    assert st["scan_queries"] == 2 and st["fallback_queries"] <= 2 and st["paged_queries"] == 0, st
+
+
+@pytest.mark.parametrize("pct", [1, 50])
+def test_full_size_c4_filtered_against_the_oracle(pct):
+    """C4 at full size against the ORACLE over the eligible rows: 10M x 384 Euclidean, eq filter at 1 % / 50 %,
+    k = 10, eight queries, through all three reference-facing forms: the eligibility bitmask (filter push-down), the
+    device-evaluated metadata filter (gfi_search_filtered over a resident column), and the reference's own
+    post-filter (search 3k unfiltered, keep the matching hits: storage.rs:249-290)."""
+    import bench
+    n, d, k = 10_000_000, 384, 10
+    idx = gfi.GpuFlatIndex(DM.Euclidean, dim=d)
+    idx.reserve(n)
+    idx.add_generated(6, 0, n, 0, 0)
+    elig = bench.eligible_rows(0, n, pct)
+    qs = oracle.gen_rows(7, 0, 8, d, 0)
+    exp = oracle.search_generated("euclidean", 6, 0, n, d, 0, qs, k, eligible=elig)
+    m_ids, m_d, m_c = idx.search_arrays(qs, k, mask=elig)              # 8 queries in one call
+    for i, (eids, ed) in enumerate(exp):
+        assert m_c[i] == k
+        assert_topk_matches(m_ids[i], m_d[i], eids, ed, ctx=f"C4 {pct}% mask q{i}")
+    idx.set_metadata_column("tag", np.arange(n, dtype=np.uint64), ["hit", "miss"], np.where(elig, 0, 1).astype(np.uint32))
+    flt = {"op": "eq", "field": "tag", "value": "hit"}
+    for i, (eids, ed) in enumerate(exp):                               # single queries, as the bench issues them
+        f_ids, f_d, f_c = idx.search_filtered(qs[i:i + 1], k, flt)
+        assert f_c[0] == k
+        assert_topk_matches(f_ids[0], f_d[0], eids, ed, ctx=f"C4 {pct}% filter q{i}")
+    # reference semantics: unfiltered top-3k, then the filter (may return fewer than k; at 1 % usually none)
+    full = oracle.search_generated("euclidean", 6, 0, n, d, 0, qs[:4], 3 * k)
+    u_ids, u_d, u_c = idx.search_arrays(qs[:4], 3 * k)
+    for i, (eids, ed) in enumerate(full):
+        assert_topk_matches(u_ids[i], u_d[i], eids, ed, ctx=f"C4 unfiltered 3k q{i}")
+        keep_g = elig[u_ids[i].astype(np.int64)]
+        keep_o = elig[eids.astype(np.int64)]
+        assert np.array_equal(u_ids[i][keep_g][:k], eids[keep_o][:k])
 
 
 def test_full_size_cost_model_route_switches_off_on_uncertifiable_data():

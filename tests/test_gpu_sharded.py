@@ -195,21 +195,22 @@ def test_sharded_device_resident_searches_double_buffer_and_keep_flags(layout):
     idx.add_batch(np.arange(n, dtype=np.uint64), rows)
     dev = torch.device("cuda", devs[0])
     torch.cuda.set_device(dev)
-    ts = torch.cuda.Stream(device=dev)
+    tss = [torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)]
     outs = []
-    with torch.cuda.stream(ts):
-        dks = torch.full((q,), k, dtype=torch.int32, device=dev)
-        for it in range(5):
-            queries = oracle.gen_rows(110 + it, 0, q, d, 1)
-            dq = torch.from_numpy(queries).to(dev)
+    dks = torch.full((q,), k, dtype=torch.int32, device=dev)
+    torch.cuda.synchronize(dev)
+    for it in range(7):  # batches alternate between two caller streams: merge of one overlaps the next main pass
+        ts = tss[it % 2]
+        queries = oracle.gen_rows(110 + it, 0, q, d, 1)
+        with torch.cuda.stream(ts):
+            dq = torch.from_numpy(queries).to(dev, non_blocking=False)
             o_ids = torch.zeros((q, k), dtype=torch.int64, device=dev)
             o_d = torch.zeros((q, k), dtype=torch.float32, device=dev)
             o_c = torch.zeros((q,), dtype=torch.int32, device=dev)
-            ts.synchronize()
-            idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, o_ids.data_ptr(), o_d.data_ptr(), o_c.data_ptr(), k,
-                              stream=ts.cuda_stream)
-            outs.append((queries, dq, o_ids, o_d, o_c))
-        idx.search_status()
+        idx.search_device(dq.data_ptr(), q, dks.data_ptr(), k, o_ids.data_ptr(), o_d.data_ptr(), o_c.data_ptr(), k,
+                          stream=ts.cuda_stream)
+        outs.append((queries, dq, o_ids, o_d, o_c))
+    idx.search_status()
     torch.cuda.synchronize(dev)
     for queries, _, o_ids, o_d, o_c in outs:
         exp = oracle.search_batch("dot", rows, queries, k, threads=8)

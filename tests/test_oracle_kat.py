@@ -140,3 +140,23 @@ def test_frozen_golden_cases():
         res = oracle.search_batch(metric, rows, queries, k)
         assert np.array_equal(np.stack([r[0] for r in res]), z[name + "/ids"])
         assert np.array_equal(np.stack([r[1] for r in res]), z[name + "/dist"])
+
+
+def test_generated_rows_parallel_mode_equals_the_array_mode():
+    """oracle.search_generated (rows produced on the fly, rows-parallel, per-thread top-k + merge) is the full-size
+    checker; it must equal the array mode, which the reference's own KATs pin above."""
+    for metric, kind in (("euclidean", 0), ("cosine", 1), ("dot", 1)):
+        n, d, q = 6000, 40, 5
+        rows = oracle.gen_rows(11, 100, n, d, kind)
+        qs = oracle.gen_rows(12, 0, q, d, kind)
+        elig = (np.arange(n) * 7 % 5) != 0
+        ks = [10, 1, 0, 100, 7]
+        a = oracle.search_batch(metric, rows, qs, ks, ids=np.arange(n, dtype=np.uint64) + 5000, eligible=elig, threads=2)
+        for threads in (1, 3):
+            b = oracle.search_generated(metric, 11, 100, n, d, kind, qs, ks, eligible=elig, first_id=5000, threads=threads)
+            for (ai, ad), (bi, bd) in zip(a, b):
+                assert np.array_equal(ai, bi) and np.array_equal(ad, bd)
+    # duplicates: ties resolve by lower id whatever the partition
+    rows = np.tile(oracle.gen_rows(13, 0, 1, 16, 0), (50, 1))
+    a = oracle.search_batch("euclidean", rows, rows[:1], 7)[0]
+    assert list(a[0]) == list(range(7))

@@ -8,7 +8,7 @@ tests read like the reference's own tests.  There is no CPU fallback anywhere: i
 works without a GPU (so symbols can be checked), every compute call needs a B200.
 """
 from .errors import (  # noqa: F401
-    VectorDbError, DimensionMismatch, InvalidVector, IndexError_, VectorNotFound, NaNDistance,
+    VectorDbError, DimensionMismatch, InvalidVector, IndexError_, VectorNotFound, NaNDistance, Unproven,
 )
 from .native import lib, lib_path, build_native, DECLARED_SYMBOLS  # noqa: F401
 from .index import GpuFlatIndex, DistanceMetric  # noqa: F401

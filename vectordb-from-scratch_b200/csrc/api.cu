@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "host.h"
+#include "exact.cuh"  // scan_lower_bound (host side of the scan-path certification)
 
 using namespace gfi;
 
@@ -392,7 +393,53 @@ struct SearchArgs {
   bool mask_by_slot = false;  // the mask is indexed by slot (device-evaluated filter), not by internal id
   int64_t mask_popcount = -1;  // eligible bits of a host mask when known (cost model), else -1
   bool keep_flags = false;     // an earlier search of this context has not been collected yet: its error flags stay
+  int64_t q_base = 0, q_total = 0;  // chunked batches: index of this chunk's first query, queries of the whole call
 };
+
+// Ring / list geometry of the scan kernel for per-query lists of K keys and a batch of q queries.
+struct ScanGeom { int R, segf, nseg, lpr, stage_floats, QT, nstages; };
+int32_t scan_geometry(const gfi_index* h, int K, int q, ScanGeom* g) {
+  // A stage is one contiguous bulk copy of whole rows whenever rows fit (<= 4 KB): rows <= 1 KB use 8 lanes per
+  // row (64 rows per round of the 16 consumer warps), longer rows one warp per row (16 rows per round); rows
+  // beyond 4 KB are cut into 4 KB column segments.
+  int R, segf, nseg, lpr;
+  const int kTargetStageBytes = 48 * 1024;
+  if (h->dpad <= 256) {
+    lpr = 8;
+    segf = h->dpad;
+    nseg = 1;
+    R = 64 * std::max(1, std::min(4, kTargetStageBytes / (64 * h->dpad * 4)));
+  } else if (h->dpad <= 512) {
+    lpr = 16;  // two rows per warp at a time: halves the per-row reduction/bookkeeping cost of mid-size rows
+    segf = h->dpad;
+    nseg = 1;
+    R = 32 * std::max(1, std::min(4, kTargetStageBytes / (32 * h->dpad * 4)));
+  } else {
+    lpr = 32;
+    segf = std::min(h->dpad, 1024);
+    nseg = (h->dpad + segf - 1) / segf;
+    R = nseg == 1 ? 16 * std::max(1, std::min(4, kTargetStageBytes / (16 * h->dpad * 4))) : 16;
+  }
+  const int stage_floats = R * (nseg == 1 ? h->dpad : segf);
+  // queries per pass: as many as shared memory allows next to a ring of at least 3 stages
+  int QT = 4, nstages = 0;
+  for (;; QT >>= 1) {
+    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
+    const size_t budget = 227 * 1024;
+    nstages = fixed < budget ? (int)std::min<size_t>(kScanMaxStages, (budget - fixed) / ((size_t)stage_floats * 4)) : 0;
+    if (nstages >= 3 || QT == 1) break;
+  }
+  if (nstages < 2) return fail(GFI_ERR_INDEX, "k and dimension too large for the scan kernel's shared memory");
+  if (h->opt_scan_qt > 0) QT = std::min(QT, pow2_at_least(h->opt_scan_qt));
+  while (QT > 1 && QT / 2 >= q) QT >>= 1;  // (also on the tensor path: its fallback never has more than q queries)
+  {
+    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
+    nstages = (int)std::min<size_t>(kScanMaxStages, (227 * 1024 - fixed) / ((size_t)stage_floats * 4));
+    if (h->opt_scan_stages > 0) nstages = std::max(2, std::min(nstages, h->opt_scan_stages));
+  }
+  *g = ScanGeom{R, segf, nseg, lpr, stage_floats, QT, nstages};
+  return GFI_OK;
+}
 
 // Enqueues the whole device pipeline of one search batch on `st`.  No host synchronisation.
 int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStream_t st, bool first_chunk, bool last_chunk) {
@@ -452,12 +499,13 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     c->ctrl_dev = c->ctrl.p;
   }
   CU_TRY(c->fb_list.ensure((size_t)q * 4));
+  CU_TRY(c->up_list.ensure((size_t)std::max<int64_t>(a.q_total, q) * 4));
   CU_TRY(c->sel_keys.ensure((size_t)q * 1024 * 8));
   CU_TRY(c->sel_info.ensure((size_t)q * sizeof(SelInfo)));
   if (tensor_ok) CU_TRY(c->q16.ensure((size_t)qpad * h->dpad16 * 2));
   if (first_chunk) {
     // (the flags word is the first of the block; it is sticky across uncollected device searches)
-    const size_t skip = a.keep_flags ? sizeof(uint32_t) : 0;
+    const size_t skip = a.keep_flags ? 2 * sizeof(uint32_t) : 0;  // flags, unproven
     CU_TRY(cudaMemsetAsync(static_cast<char*>(c->ctrl_dev) + skip, 0, sizeof(Ctrl) - skip, st));
   }
   Ctrl* ctrl = reinterpret_cast<Ctrl*>(c->ctrl_dev);
@@ -483,46 +531,15 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const int K = std::min(1024, pow2_at_least(std::max<int>(32, (int)a.kmax + 8)));
   if ((int)a.kmax > K) return fail(GFI_ERR_INDEX, "k too large: the scan path supports k <= 1024");
   if (h->dpad > 16384) return fail(GFI_ERR_INDEX, "dimension too large (max 16384)");
-  // Ring geometry.  A stage is one contiguous bulk copy of whole rows whenever rows fit (<= 4 KB):
-  // rows <= 1 KB use 8 lanes per row (64 rows per round of the 16 consumer warps), longer rows one
-  // warp per row (16 rows per round); rows beyond 4 KB are cut into 4 KB column segments.
-  int R, segf, nseg, lpr;
-  const int kTargetStageBytes = 48 * 1024;
-  if (h->dpad <= 256) {
-    lpr = 8;
-    segf = h->dpad;
-    nseg = 1;
-    R = 64 * std::max(1, std::min(4, kTargetStageBytes / (64 * h->dpad * 4)));
-  } else if (h->dpad <= 512) {
-    lpr = 16;  // two rows per warp at a time: halves the per-row reduction/bookkeeping cost of mid-size rows
-    segf = h->dpad;
-    nseg = 1;
-    R = 32 * std::max(1, std::min(4, kTargetStageBytes / (32 * h->dpad * 4)));
-  } else {
-    lpr = 32;
-    segf = std::min(h->dpad, 1024);
-    nseg = (h->dpad + segf - 1) / segf;
-    R = nseg == 1 ? 16 * std::max(1, std::min(4, kTargetStageBytes / (16 * h->dpad * 4))) : 16;
+  ScanGeom geo;
+  {
+    int32_t grc = scan_geometry(h, K, q, &geo);
+    if (grc != GFI_OK) return grc;
   }
-  const int stage_floats = R * (nseg == 1 ? h->dpad : segf);
+  const int R = geo.R, segf = geo.segf, nseg = geo.nseg, lpr = geo.lpr, stage_floats = geo.stage_floats;
+  const int QT = geo.QT, nstages = geo.nstages;
   // filtered or heavily tombstoned scans gather only the eligible rows (one bulk copy per run of adjacent eligible rows)
   const bool gather = a.d_mask != nullptr || h->n_live * 10 < h->n_slots * 9;
-  // queries per pass: as many as shared memory allows next to a ring of at least 3 stages
-  int QT = 4, nstages = 0;
-  for (;; QT >>= 1) {
-    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
-    const size_t budget = 227 * 1024;
-    nstages = fixed < budget ? (int)std::min<size_t>(kScanMaxStages, (budget - fixed) / ((size_t)stage_floats * 4)) : 0;
-    if (nstages >= 3 || QT == 1) break;
-  }
-  if (nstages < 2) return fail(GFI_ERR_INDEX, "k and dimension too large for the scan kernel's shared memory");
-  if (h->opt_scan_qt > 0) QT = std::min(QT, pow2_at_least(h->opt_scan_qt));
-  while (QT > 1 && QT / 2 >= q) QT >>= 1;  // (also on the tensor path: its fallback never has more than q queries)
-  {
-    const size_t fixed = (size_t)QT * h->dpad * 4 + (size_t)QT * kScanConsumerWarps * K * 8 + 1024;
-    nstages = (int)std::min<size_t>(kScanMaxStages, (227 * 1024 - fixed) / ((size_t)stage_floats * 4));
-    if (h->opt_scan_stages > 0) nstages = std::max(2, std::min(nstages, h->opt_scan_stages));
-  }
   const int64_t nblocks = (h->n_slots + R - 1) / R;
   if (gather) {
     CU_TRY(c->gather.ensure(((size_t)h->n_slots + 8) * 4));
@@ -569,6 +586,13 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     sp.lanes_per_row = lpr;
     sp.nstages = nstages;
     sp.stage_floats = stage_floats;
+    if (h->opt_scan_certify) {
+      sp.up_count = &ctrl->unproven;
+      sp.up_list = c->up_list.as<uint32_t>();
+      sp.up_base = (uint32_t)a.q_base;
+      sp.up_cap = (uint32_t)std::max<int64_t>(a.q_total, q);
+      sp.xnorm_max = h->xnorm_max;
+    }
   };
   auto fill_select = [&](SelectParams& s, DevBuf& cand, DevBuf& cnt, int64_t stride, int KP) {
     s.iv = iv;
@@ -593,6 +617,10 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     s.kstride = a.kstride;
     s.flags = &ctrl->flags;
     s.uncertified = &ctrl->uncertified;
+    s.up_count = &ctrl->unproven;
+    s.up_list = c->up_list.as<uint32_t>();
+    s.up_base = (uint32_t)a.q_base;
+    s.up_cap = (uint32_t)std::max<int64_t>(a.q_total, q);
   };
 
   if (!tensor_ok) {
@@ -637,7 +665,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
     s.qlist = nullptr;
     s.nq_dev = nullptr;
     s.nq = q;
-    s.certify = 0;
+    s.certify = h->opt_scan_certify ? 2 : 0;
     s.list_len = K;
     CU_TRY(launch_select_rerank(s, std::min(q, grid_sm * 8), st));
     h->n_launch += 3;
@@ -767,7 +795,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s2.qlist = c->fb_list.as<uint32_t>();
   s2.nq_dev = &ctrl->fb_count;
   s2.nq = 0;
-  s2.certify = 0;
+  s2.certify = h->opt_scan_certify ? 2 : 0;
   s2.list_len = K;
   CU_TRY(launch_select_rerank(s2, std::min(q, grid_sm * 2), st));
   if (!last_chunk) CU_TRY(cudaMemsetAsync(&ctrl->fb_count, 0, 4, st));  // the next chunk starts an empty fallback list
@@ -782,6 +810,8 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
   if (a.q <= lim) return enqueue_chunk(h, c, a, st, true, true);
   for (int64_t q0 = 0; q0 < a.q; q0 += lim) {
     SearchArgs s = a;
+    s.q_base = q0;
+    s.q_total = a.q;
     s.q = std::min(lim, a.q - q0);
     s.d_queries = a.d_queries + q0 * h->dim;
     s.d_ks = a.d_ks + q0;
@@ -792,6 +822,146 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
     if (rc != GFI_OK) return rc;
   }
   return GFI_OK;
+}
+
+// Host-driven proof of ONE query whose scan-path answer the device could not certify (exact.cuh, scan_lower_bound):
+// more rows than the kernel's K-entry lists hold lie within the summation-order error band of the k-th distance
+// (clusters of near-duplicate rows).  The query is answered in PAGES of up to 1024 candidates in ascending order of the
+// approximate key -- page j scans the rows whose key lies above page j-1's last key (ScanParams::floor64), re-scores
+// its rows with the reference's arithmetic and returns its own exact top-k -- until the bound of a page's last
+// key clears the k-th exact distance seen so far (or the rows run out).  The union of the pages' top-k lists then
+// contains the reference's top-k, whatever the size of the cluster: FlatIndex::search's answer (flat_index.rs:52-65).
+// The rare path: one scan per page, synchronous.  `res` receives (distance, id) ascending.
+int32_t prove_query(gfi_index* h, SearchCtx* c, cudaStream_t st, const float* query_host, uint32_t k,
+                    const uint64_t* d_mask, int64_t mask_bits, bool mask_by_slot,
+                    std::vector<std::pair<float, uint64_t>>* res) {
+  res->clear();
+  if (k == 0) return GFI_OK;
+  if (k > 1024u) return fail(GFI_ERR_INDEX, "k too large: the scan path supports k <= 1024");
+  IndexView iv = h->view();
+  if (mask_by_slot) iv.ids_identity = 1;
+  MaskView mv{d_mask, mask_bits};
+  // page size: the longest list the scan kernel's shared memory takes next to a ring of this row length
+  // (1024 keys for short rows, 512 at d = 768), never below the search's own list length
+  ScanGeom geo;
+  int KPG = 1024;
+  int32_t rc;
+  while ((rc = scan_geometry(h, KPG, 1, &geo)) != GFI_OK && KPG / 2 >= std::max(32, pow2_at_least((int)k))) KPG /= 2;
+  if (rc != GFI_OK) return rc;
+  const int grid_sm = h->opt_grid > 0 ? h->opt_grid : h->sm_count;
+  const int64_t nblocks = (h->n_slots + geo.R - 1) / geo.R;
+  const int scan_grid = (int)std::max<int64_t>(1, std::min<int64_t>(grid_sm, nblocks));
+  const int64_t stride = (int64_t)scan_grid * KPG;
+  CU_TRY(c->q_in.ensure((size_t)h->dim * 4));
+  CU_TRY(c->q32.ensure((size_t)h->dpad * 4));
+  CU_TRY(c->qnorm.ensure(4));
+  CU_TRY(c->qsumsq.ensure(4));
+  CU_TRY(c->ks.ensure(4));
+  CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
+  CU_TRY(c->floor.ensure(8));
+  CU_TRY(c->cand_fb.ensure((size_t)stride * 8));
+  CU_TRY(c->cand_fb_cnt.ensure(4));
+  CU_TRY(c->sel_keys.ensure((size_t)KPG * 8));
+  CU_TRY(c->sel_info.ensure(sizeof(SelInfo)));
+  CU_TRY(c->out_ids.ensure((size_t)KPG * 8));
+  CU_TRY(c->out_dist.ensure((size_t)KPG * 4));
+  CU_TRY(c->out_counts.ensure(4));
+  Ctrl* ctrl = c->ctrl.as<Ctrl>();
+  CU_TRY(cudaMemsetAsync(ctrl, 0, sizeof(Ctrl), st));
+  CU_TRY(cudaMemcpyAsync(c->q_in.p, query_host, (size_t)h->dim * 4, cudaMemcpyHostToDevice, st));
+  CU_TRY(cudaMemcpyAsync(c->ks.p, &k, 4, cudaMemcpyHostToDevice, st));
+  PrepQueriesParams pq{};
+  pq.q_in = c->q_in.as<float>();
+  pq.q32 = c->q32.as<float>();
+  pq.qnorm = c->qnorm.as<float>();
+  pq.qsumsq = c->qsumsq.as<float>();
+  pq.qmaxabs = reinterpret_cast<float*>(&ctrl->qmaxabs_bits);
+  pq.q = 1;
+  pq.qpad = 128;
+  pq.d = (int)h->dim;
+  pq.dpad = h->dpad;
+  pq.dpad16 = h->dpad16;
+  CU_TRY(launch_prep_queries(pq, st));
+  const bool gather = d_mask != nullptr || h->n_live * 10 < h->n_slots * 9;
+  if (gather) {
+    CU_TRY(c->gather.ensure(((size_t)h->n_slots + 8) * 4));
+    CU_TRY(cudaMemsetAsync(c->gather.p, 0, 16, st));
+    CU_TRY(launch_compact_eligible(iv, mv, c->gather.as<uint32_t>() + 4, c->gather.as<uint32_t>(), st));
+  }
+  float qn = 0.f;
+  CU_TRY(cudaMemcpyAsync(&qn, c->qnorm.p, 4, cudaMemcpyDeviceToHost, st));
+  h->n_launch += gather ? 2 : 1;
+  std::vector<uint64_t> pids(k);
+  std::vector<float> pdist(k);
+  uint64_t floor_key = 0;
+  const int64_t max_pages = h->n_slots / KPG + 2;
+  for (int64_t page = 0; page < max_pages; ++page) {
+    if (page > 0) CU_TRY(cudaMemcpyAsync(c->floor.p, &floor_key, 8, cudaMemcpyHostToDevice, st));
+    ScanParams sp{};
+    sp.iv = iv;
+    sp.mask = mv;
+    sp.q32 = c->q32.as<float>();
+    sp.qnorm = c->qnorm.as<float>();
+    sp.nq = 1;
+    sp.K = KPG;
+    sp.floor64 = page > 0 ? c->floor.as<uint64_t>() : nullptr;
+    sp.cand = c->cand_fb.as<uint64_t>();
+    sp.cand_cnt = c->cand_fb_cnt.as<uint32_t>();
+    sp.cand_stride = stride;
+    sp.flags = &ctrl->flags;
+    sp.gather_list = gather ? c->gather.as<uint32_t>() + 4 : nullptr;
+    sp.gather_count = gather ? c->gather.as<uint32_t>() : nullptr;
+    sp.rows_per_stage = geo.R;
+    sp.seg_floats = geo.segf;
+    sp.nseg = geo.nseg;
+    sp.lanes_per_row = geo.lpr;
+    sp.nstages = geo.nstages;
+    sp.stage_floats = geo.stage_floats;
+    CU_TRY(launch_scan(sp, geo.QT, scan_grid, st));
+    SelectParams sl{};
+    sl.iv = iv;
+    sl.sel_keys = c->sel_keys.as<uint64_t>();
+    sl.sel_info = c->sel_info.as<SelInfo>();
+    sl.nq_max = 1;
+    sl.nq = 1;
+    sl.q32 = c->q32.as<float>();
+    sl.qnorm = c->qnorm.as<float>();
+    sl.qsumsq = c->qsumsq.as<float>();
+    sl.ks = c->ks.as<uint32_t>();
+    sl.cand = c->cand_fb.as<uint64_t>();
+    sl.cand_cnt = c->cand_fb_cnt.as<uint32_t>();
+    sl.cand_stride = stride;
+    sl.KP = KPG;
+    sl.list_len = KPG;
+    sl.xnorm_max = h->xnorm_max;
+    sl.out_ids = c->out_ids.as<uint64_t>();
+    sl.out_dist = c->out_dist.as<float>();
+    sl.out_counts = c->out_counts.as<uint32_t>();
+    sl.kstride = KPG;
+    sl.flags = &ctrl->flags;
+    CU_TRY(launch_select_rerank(sl, 1, st));
+    h->n_launch += 3;
+    SelInfo info{};
+    uint32_t cnt = 0;
+    CU_TRY(cudaMemcpyAsync(&info, c->sel_info.p, sizeof(SelInfo), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&cnt, c->out_counts.p, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pids.data(), c->out_ids.p, (size_t)k * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(pdist.data(), c->out_dist.p, (size_t)k * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    for (uint32_t j = 0; j < std::min(cnt, k); ++j) res->emplace_back(pdist[j] + 0.0f, pids[j]);
+    std::sort(res->begin(), res->end());  // (distance, id): the reference's order with "lower id wins"
+    if (res->size() > k) res->resize(k);
+    if (info.kpeff < (uint32_t)KPG) return GFI_OK;  // the rows have run out
+    uint32_t hi = (uint32_t)(info.pivot >> 32);
+    hi = (hi & 0x80000000u) ? (hi & 0x7fffffffu) : ~hi;  // key_f32 (common.cuh)
+    float a_s;
+    memcpy(&a_s, &hi, 4);
+    if (res->size() >= k && a_s == a_s &&
+        scan_lower_bound(h->metric, a_s, qn, h->xnorm_max, (int)h->dim) > (*res)[k - 1].first)
+      return GFI_OK;
+    floor_key = info.pivot;
+  }
+  return fail(GFI_ERR_INDEX, "internal: paging did not terminate");
 }
 
 int32_t flags_to_status(uint32_t fl) {
@@ -1389,6 +1559,30 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     memcpy(out_ids + i * kstride, hids + (size_t)i * kout, (size_t)hcnt[i] * 8);
     memcpy(out_dist + i * kstride, hdist + (size_t)i * kout, (size_t)hcnt[i] * 4);
   }
+  if (hc->unproven > 0) {
+    // scan-path answers the device could not prove exact (near-duplicate clusters): proven here, query by query
+    const uint32_t n_up = std::min<uint32_t>(hc->unproven, (uint32_t)q);
+    std::vector<uint32_t> up(n_up);
+    rel.in_flight = true;
+    CU_TRY(cudaMemcpyAsync(up.data(), c->up_list.p, (size_t)n_up * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<std::pair<float, uint64_t>> res;
+    for (uint32_t qi : up) {
+      if (qi >= (uint32_t)q) continue;
+      if ((rc = prove_query(h, c, st, queries + (size_t)qi * dim, ks[qi], a.d_mask, a.mask_bits, a.mask_by_slot,
+                            &res)) != GFI_OK) {
+        cudaStreamSynchronize(st);
+        return rc;
+      }
+      out_counts[qi] = (uint32_t)res.size();
+      for (size_t j = 0; j < res.size(); ++j) {
+        out_dist[qi * kstride + (int64_t)j] = res[j].first;
+        out_ids[qi * kstride + (int64_t)j] = res[j].second;
+      }
+    }
+    rel.in_flight = false;
+    h->n_paged_q += n_up;
+  }
   if (host_trace)
     fprintf(stderr, "[gfi trace] q=%lld enqueue %.1f us, wait %.1f us, unpack %.1f us\n", (long long)q, t_enq - t_begin,
             t_sync - t_enq, now_us() - t_sync);
@@ -1866,7 +2060,11 @@ int32_t gfi_search_status(gfi_index* h) {
     const int64_t aq = (h->auto_q += c->auto_tensor_q), af = (h->auto_fb += hc->uncertified);
     if (aq >= 32 && af * 4 > aq) h->auto_tensor_off = true;
   }
-  return flags_to_status(hc->flags);
+  if ((rc = flags_to_status(hc->flags)) != GFI_OK) return rc;
+  if (hc->unproven)
+    return fail(GFI_ERR_UNPROVEN, std::to_string(hc->unproven) + " quer(ies) since the last status could not be proven "
+                "exact on the device (near-duplicate rows around the k-th distance): re-run them through gfi_search");
+  return GFI_OK;
 }
 
 int32_t gfi_merge_topk_device(const uint64_t* d_ids, const float* d_dist, const uint32_t* d_counts, int32_t G,
@@ -2036,6 +2234,7 @@ int32_t gfi_get_stats(gfi_index* h, gfi_stats* out) {
   out->tensor_kernel_count = h->prof_cnt[1];
   out->coalesced_batches = h->n_co_batches;
   out->coalesced_requests = h->n_co_requests;
+  out->paged_queries = h->n_paged_q;
   return GFI_OK;
 }
 
@@ -2062,6 +2261,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "coalesce") h->opt_coalesce = (int)value;
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
   else if (n == "scan_stages") h->opt_scan_stages = (int)value;
+  else if (n == "scan_certify") h->opt_scan_certify = (int)value;
   else return fail(GFI_ERR_INDEX, "unknown option: " + n);
   return GFI_OK;
 }

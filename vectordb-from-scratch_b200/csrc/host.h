@@ -77,6 +77,8 @@ struct PinBuf {
 // control block of one search call (device memory, zeroed per call)
 struct Ctrl {
   uint32_t flags;
+  uint32_t unproven;    // queries whose scan-path answer could not be proven exact on the device (listed in up_list);
+                        // like `flags`, sticky across uncollected device searches
   uint32_t fb_count;
   uint32_t uncertified;
   uint32_t qmaxabs_bits;
@@ -86,14 +88,14 @@ struct Ctrl {
   uint32_t routed_scan;
   uint32_t elig_count;  // population of the mask + 1 when a gather scan or the route kernel saw it, else 0
   uint32_t scan_done;   // CTAs of a fused-tail scan that have finished (ScanParams::done_ctr)
-  uint32_t pad_[3];
+  uint32_t pad_[2];
 };
 static_assert(sizeof(Ctrl) == kCtrlWords * 4, "host result blocks reserve 64 bytes: Ctrl + the done word");
 
 struct SearchCtx {
   cudaStream_t stream = nullptr;
   DevBuf q_in, q32, q16, qnorm, qsumsq, ks, mask, cand, cand_cnt, slice_cnt, cand_fb, cand_fb_cnt, thresh, seeds, ctrl,
-      fb_list, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
+      fb_list, up_list, floor, out_ids, out_dist, out_counts, sel_keys, sel_info, gather;
   PinBuf h_q, h_ks, h_ids, h_dist, h_counts, h_ctrl, h_out;
   bool zc_pending = false;   // the search enqueued last publishes its results in h_out itself (latency mode)
   uint32_t zc_seq = 0;
@@ -109,7 +111,7 @@ struct SearchCtx {
   size_t ev_used = 0;
   void release() {
     for (DevBuf* b : {&q_in, &q32, &q16, &qnorm, &qsumsq, &ks, &mask, &cand, &cand_cnt, &slice_cnt, &cand_fb, &cand_fb_cnt,
-                      &thresh, &seeds, &ctrl, &fb_list, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
+                      &thresh, &seeds, &ctrl, &fb_list, &up_list, &floor, &out_ids, &out_dist, &out_counts, &sel_keys, &sel_info, &gather})
       b->release();
     for (PinBuf* b : {&h_q, &h_ks, &h_ids, &h_dist, &h_counts, &h_ctrl, &h_out}) b->release();
     out_blk.release();
@@ -255,7 +257,7 @@ struct gfi_index {
   int64_t st_n = 0, st_cap = 0;
 
   // stats / options
-  std::atomic<int64_t> n_search{0}, n_queries{0}, n_scan_q{0}, n_tensor_q{0}, n_fallback_q{0}, n_launch{0};
+  std::atomic<int64_t> n_search{0}, n_queries{0}, n_scan_q{0}, n_tensor_q{0}, n_fallback_q{0}, n_launch{0}, n_paged_q{0};
   int opt_tensor_min_q = 16;
   int opt_kp = 0;          // 0 = auto
   int opt_hits = 0;        // 0 = auto
@@ -269,6 +271,7 @@ struct gfi_index {
                              // gain -- the pass is power-limited either way -- so off by default
   int opt_short_k = 1;       // dpad16 <= 128: row-tile-stationary main pass (0 = the k-ring kernel, for A/B timing)
   int opt_short_k_min_tiles = 4;  // ... for batches of at least this many 128-query tiles
+  int opt_scan_certify = 1;  // 0: scan-path answers are not certified (A/B timing, tests of the proof itself)
   int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
   std::atomic<int64_t> last_mask_pop{-1};     // population of the last device-resident mask searched (route predictor)
   std::atomic<bool> auto_tensor_off{false};   // set when such searches keep falling back (uncertifiable data)

@@ -72,6 +72,8 @@ struct ScanParams {
   const uint32_t* d_ctrl;   // the device control block
   uint64_t* h_out_ids; float* h_out_dist; uint32_t* h_out_counts;
   uint32_t done_seq;
+  // certification of the fused tail's answers (exact.cuh, scan_lower_bound): unproven queries are listed
+  uint32_t* up_count; uint32_t* up_list; uint32_t up_base, up_cap; float xnorm_max;
 };
 constexpr int kCtrlWords = 12, kCtrlDoneWord = 15;  // layout of the 64-byte control area of a host result block
 size_t scan_fused_tail_bytes(int grid, int K, int dpad);
@@ -133,7 +135,8 @@ struct SelectParams {
   int slice_gather;           // 1: read the slices' valid prefixes; 0: cand is sentinel-filled, scan it whole
   int sel_cap;                // candidate keys staged in shared memory per query (0 = kSelectStageKeys; <= 16384)
   // certification (tensor path): every row that is not a candidate has approx score >= cutoff
-  int certify;                // 0 = scan path (never falls back), 1 = tensor path
+  int certify;                // 0 = none, 1 = tensor path (fp16 error bound; failures -> fb_list, re-run on the scan),
+                              // 2 = scan path (fp32 summation-order bound; failures -> up_list, proven by the host)
   const float* thresh;        // per-query score threshold used by the tensor kernel
   float eps_rel;              // relative error bound of the approximate dot product
   const float* qmaxabs;       // batch max |q| (fp16 common scale), tensor path
@@ -142,6 +145,7 @@ struct SelectParams {
   uint64_t* out_ids; float* out_dist; uint32_t* out_counts; int64_t kstride;
   uint32_t* flags;
   uint32_t* uncertified;      // counter (stats)
+  uint32_t* up_count; uint32_t* up_list; uint32_t up_base, up_cap;  // certify == 2: unproven queries (index + up_base)
 };
 cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t st);
 

@@ -98,6 +98,7 @@ __device__ __noinline__ void scan_fused_tail(const ScanParams& p, int nq, const 
   uint64_t& s_bound = ctl[0];
   uint32_t& s_n = reinterpret_cast<uint32_t*>(ctl + 1)[0];
   uint32_t& s_m = reinterpret_cast<uint32_t*>(ctl + 1)[1];
+  float& s_tau = reinterpret_cast<float*>(ctl + 3)[0];  // exact k-th distance of the query being finished
   const IndexView& iv = p.iv;
   const int K = p.K, L = (int)gridDim.x, dpad = iv.dpad, LK = L * K;
   const int lane = tid & 31, warp = tid >> 5;
@@ -188,11 +189,27 @@ __device__ __noinline__ void scan_fused_tail(const ScanParams& p, int nq, const 
           p.h_out_ids[(size_t)qg * p.kstride + below] = iv.ids[(uint32_t)(key & 0xffffffffu)];
           p.h_out_dist[(size_t)qg * p.kstride + below] = key_f32((uint32_t)(key >> 32));
         }
+        if (below == kq - 1) s_tau = key_f32((uint32_t)(key >> 32));
       }
     }
+    __syncthreads();
     if (tid == 0) {
       p.out_counts[qg] = kq;
       if (p.h_ctrl) p.h_out_counts[qg] = kq;
+      // certification, as in rerank_finalize_kernel: rows were dropped only if K or more keys existed, and then
+      // every dropped row's approximate key is >= sel[K-1] (exact.cuh, scan_lower_bound)
+      const uint32_t k = p.ks[qg];
+      if (p.up_list && k > 0 && nvalid >= (uint32_t)K) {
+        bool ok = kq == k;
+        if (ok) {
+          const float a_s = key_f32((uint32_t)(sel[K - 1] >> 32));
+          ok = (a_s == a_s) && scan_lower_bound(METRIC, a_s, qn, p.xnorm_max, iv.d) > s_tau;
+        }
+        if (!ok) {
+          const uint32_t pos = atomicAdd(p.up_count, 1u);
+          if (pos < p.up_cap) p.up_list[pos] = qg + p.up_base;
+        }
+      }
     }
     __syncthreads();
   }

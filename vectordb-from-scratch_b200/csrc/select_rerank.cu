@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 
     // ---- exact radix select of the KP-th smallest key (only when there are more than KP) ----
     uint64_t pivot = kKeySentinel - 1;  // everything valid is <= pivot
-    if (nvalid > (uint32_t)KP) pivot = radix_select(src, src_n, (uint32_t)KP, bound, hist, &s_bucket, &s_need, tid);
+    // (nvalid == KP: the pivot is the largest selected key -- the scan-path certification needs it, exact.cuh)
+    if (nvalid >= (uint32_t)KP) pivot = radix_select(src, src_n, (uint32_t)KP, bound, hist, &s_bucket, &s_need, tid);
     for (int i = tid; i < KP; i += kSelThreads) sel[i] = kKeySentinel;
     __syncthreads();
     for (uint32_t i = tid; i < src_n; i += kSelThreads) {
@@ -405,8 +406,23 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
     }
     if (lane == 0) p.out_counts[qg] = kq;
 
+    // ---- certification (scan path): rows were dropped only if some list was full, i.e. >= KP keys existed; every
+    // dropped row then has an approximate key >= the KP-th smallest one overall, the pivot (exact.cuh) ----
+    if (p.certify == 2 && lane == 0 && k > 0 && info->nvalid >= (uint32_t)p.KP) {
+      bool ok = kq == k;
+      if (ok) {
+        const float tau = key_f32((uint32_t)(sk[k - 1] >> 32));  // exact k-th distance
+        const float a_s = key_f32((uint32_t)(info->pivot >> 32));
+        const float lb = scan_lower_bound(METRIC, a_s, qn, p.xnorm_max, iv.d);
+        ok = (a_s == a_s) && lb > tau;  // strict: a tie could hide a row with a lower id
+      }
+      if (!ok) {
+        const uint32_t pos = atomicAdd(p.up_count, 1u);
+        if (pos < p.up_cap) p.up_list[pos] = qg + p.up_base;
+      }
+    }
     // ---- certification (tensor path) ----
-    if (p.certify && lane == 0 && k > 0) {
+    if (p.certify == 1 && lane == 0 && k > 0) {
       bool ok = !info->overflow && kpeff >= k;
       if (ok) {
         const float tau = key_f32((uint32_t)(sk[k - 1] >> 32));  // exact k-th distance

@@ -122,7 +122,7 @@ struct ShardedCtx {
   cudaEvent_t in_ready = nullptr;
   uint64_t seq = 0;
   bool pending_status = false;
-  cudaStream_t last_stream = nullptr;
+  std::vector<cudaStream_t> streams;  // caller streams used by the uncollected device searches (usually one or two)
   std::vector<EvPair> evs;  // option "profile": merge timing on the root stream
   size_t ev_used = 0;
 };
@@ -231,7 +231,7 @@ void drain(ShardSet* S, ShardedCtx* c) {
   for (int g = 0; g < S->G; ++g)
     if (c->sub[(size_t)g]) cudaStreamSynchronize(c->sub[(size_t)g]->stream);
   cudaStreamSynchronize(c->root_stream);
-  if (c->last_stream) cudaStreamSynchronize(c->last_stream);
+  for (cudaStream_t st : c->streams) cudaStreamSynchronize(st);
 }
 
 void prof_collect_root(ShardSet* S, ShardedCtx* c) {
@@ -588,6 +588,10 @@ int32_t sharded_set_metadata_column(gfi_index* H, const char* key, const uint64_
   });
 }
 
+static int32_t per_shard_host_search(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                                     const uint64_t* mask, int64_t mask_bits, const char* filter_json,
+                                     uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride);
+
 int32_t sharded_search(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
                        const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
                        float* out_dist, uint32_t* out_counts, int64_t kstride) {
@@ -660,13 +664,17 @@ int32_t sharded_search(gfi_index* H, const float* queries, int64_t q, int64_t di
   c->merge_recorded[0] = false;
   prof_collect_root(S, c);
   const char* hb = c->h_out.as<char>();
-  uint32_t flags = 0;
+  uint32_t flags = 0, unproven = 0;
   for (int g = 0; g < G; ++g) {
     const Ctrl* hc = reinterpret_cast<const Ctrl*>(hb + (size_t)g * 64);
     flags |= hc->flags;
+    unproven += hc->unproven;
     shard_account(S->sub[(size_t)g], c->sub[(size_t)g], *hc);
   }
   if ((rc = host_flags_to_status(flags)) != GFI_OK) return rc;
+  if (unproven)  // some shard could not prove its scan-path answer on the device: its host path does (paging)
+    return per_shard_host_search(H, queries, q, dim, ks, mask, mask_bits, filter_json, out_ids, out_dist, out_counts,
+                                 kstride);
   const uint32_t* hcnt = reinterpret_cast<const uint32_t*>(hb + rl.off_cnt);
   const float* hdist = reinterpret_cast<const float*>(hb + rl.off_dist);
   const uint64_t* hids = reinterpret_cast<const uint64_t*>(hb + rl.off_ids);
@@ -681,32 +689,29 @@ int32_t sharded_search(gfi_index* H, const float* queries, int64_t q, int64_t di
   return GFI_OK;
 }
 
-// k beyond the kernels' list capacity: every shard answers with its own exact top-k through its host path (passes of
-// 1016, api.cu search_big_k), and the G sorted lists are merged here.  The rare path, kept simple.
-int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                             uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
+// The slow path: every shard answers with its own exact top-k through its HOST entry point and the G sorted lists
+// are merged here.  Used (a) for k beyond the kernels' list capacity (passes of 1016, api.cu search_big_k) and
+// (b) when a shard could not prove its scan-path answer on the device: its host path proves it by paging
+// (api.cu prove_query).  Rare, kept simple.  The caller holds the handle's shared lock.
+static int32_t per_shard_host_search(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                                     const uint64_t* mask, int64_t mask_bits, const char* filter_json,
+                                     uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
   ShardSet* S = H->shards;
-  if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
   uint32_t kmax = 1;
-  for (int64_t i = 0; i < q; ++i) {
-    if ((int64_t)ks[i] > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
-    kmax = std::max(kmax, ks[i]);
-  }
-  int32_t rc;
-  if ((rc = ensure_flushed_all(H, false)) != GFI_OK) return rc;
-  std::shared_lock<std::shared_mutex> lk(H->mu);
-  ++S->n_search;
-  S->n_queries += q;
+  for (int64_t i = 0; i < q; ++i) kmax = std::max(kmax, ks[i]);
   const int G = S->G;
   std::vector<std::vector<uint64_t>> ids((size_t)G);
   std::vector<std::vector<float>> dist((size_t)G);
   std::vector<std::vector<uint32_t>> cnt((size_t)G);
-  rc = S->on_shards(S->all(), [&](int g) -> int32_t {
+  int32_t rc = S->on_shards(S->all(), [&](int g) -> int32_t {
     ids[(size_t)g].resize((size_t)q * kmax);
     dist[(size_t)g].resize((size_t)q * kmax);
     cnt[(size_t)g].assign((size_t)q, 0);
-    return gfi_search(S->sub[(size_t)g], queries, q, dim, ks, nullptr, 0, ids[(size_t)g].data(), dist[(size_t)g].data(),
-                      cnt[(size_t)g].data(), kmax);
+    if (filter_json)
+      return gfi_search_filtered(S->sub[(size_t)g], queries, q, dim, ks, filter_json, ids[(size_t)g].data(),
+                                 dist[(size_t)g].data(), cnt[(size_t)g].data(), kmax);
+    return gfi_search(S->sub[(size_t)g], queries, q, dim, ks, mask, mask_bits, ids[(size_t)g].data(),
+                      dist[(size_t)g].data(), cnt[(size_t)g].data(), kmax);
   });
   if (rc != GFI_OK) return rc;
   std::vector<uint32_t> pos((size_t)G);
@@ -731,6 +736,20 @@ int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int6
     out_counts[i] = produced;
   }
   return GFI_OK;
+}
+
+int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
+                             uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
+  ShardSet* S = H->shards;
+  if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
+  for (int64_t i = 0; i < q; ++i)
+    if ((int64_t)ks[i] > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
+  int32_t rc;
+  if ((rc = ensure_flushed_all(H, false)) != GFI_OK) return rc;
+  std::shared_lock<std::shared_mutex> lk(H->mu);
+  ++S->n_search;
+  S->n_queries += q;
+  return per_shard_host_search(H, queries, q, dim, ks, nullptr, 0, nullptr, out_ids, out_dist, out_counts, kstride);
 }
 
 namespace {
@@ -759,9 +778,12 @@ int32_t sharded_search_device(gfi_index* H, const float* d_queries, int64_t q, c
   }
   ShardedCtx* c = tl_sctx;
   CU_TRY(cudaSetDevice(S->root));
+  // Searches on different caller streams are independent of each other on the root GPU (each merge is ordered behind
+  // its own shards' events, and a gather block is handed over through merge_done), so two batches alternating between
+  // two streams overlap: the exchange + merge of one hides behind the main pass of the other.  On ONE stream the
+  // next batch's inputs are by definition ordered behind the previous batch's merge.
   cudaStream_t rs = stream ? (cudaStream_t)stream : c->root_stream;
-  if (c->pending_status && c->last_stream != rs) drain(S, c);  // a change of stream between uncollected searches: rare
-  c->last_stream = rs;
+  if (std::find(c->streams.begin(), c->streams.end(), rs) == c->streams.end()) c->streams.push_back(rs);
   CU_TRY(c->result.ensure((size_t)S->G * 64));  // the shards' control blocks
   CU_TRY(cudaEventRecord(c->in_ready, rs));     // queries / ks / mask are produced on the caller's stream
   ShardSearch proto;
@@ -790,22 +812,30 @@ int32_t sharded_search_status(gfi_index* H) {
   struct Releaser { ShardSet* S; ShardedCtx* c; ~Releaser() { release_sctx(S, c); } } rel{S, c};
   if (!c->pending_status) return GFI_OK;
   c->pending_status = false;
-  cudaStream_t rs = c->last_stream ? c->last_stream : c->root_stream;
-  c->last_stream = nullptr;
   CU_TRY(cudaSetDevice(S->root));
   CU_TRY(c->h_out.ensure((size_t)S->G * 64));
+  // every merge waits for its shards, so once the caller streams are idle so are the shards' pipelines
+  for (cudaStream_t st : c->streams) CU_TRY(cudaStreamSynchronize(st));
+  c->streams.clear();
+  for (int g = 0; g < S->G; ++g) CU_TRY(cudaStreamSynchronize(c->sub[(size_t)g]->stream));
+  cudaStream_t rs = c->root_stream;
   CU_TRY(cudaMemcpyAsync(c->h_out.p, c->result.p, (size_t)S->G * 64, cudaMemcpyDeviceToHost, rs));
   CU_TRY(cudaStreamSynchronize(rs));
-  for (int g = 0; g < S->G; ++g) CU_TRY(cudaStreamSynchronize(c->sub[(size_t)g]->stream));
   c->merge_recorded[0] = c->merge_recorded[1] = false;
   prof_collect_root(S, c);
-  uint32_t flags = 0;
+  uint32_t flags = 0, unproven = 0;
   for (int g = 0; g < S->G; ++g) {
     const Ctrl* hc = reinterpret_cast<const Ctrl*>(c->h_out.as<char>() + (size_t)g * 64);
     flags |= hc->flags;
+    unproven += hc->unproven;
     shard_account(S->sub[(size_t)g], c->sub[(size_t)g], *hc);
   }
-  return host_flags_to_status(flags);
+  int32_t rc = host_flags_to_status(flags);
+  if (rc != GFI_OK) return rc;
+  if (unproven)
+    return fail(GFI_ERR_UNPROVEN, "some queries since the last status could not be proven exact on the device "
+                                  "(near-duplicate rows around the k-th distance): re-run them through gfi_search");
+  return GFI_OK;
 }
 
 int32_t sharded_distances(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint64_t* cand_ids,
@@ -855,6 +885,7 @@ int32_t sharded_get_stats(gfi_index* H, gfi_stats* out) {
     out->scan_kernel_count += t.scan_kernel_count;
     out->tensor_kernel_ns += t.tensor_kernel_ns;
     out->tensor_kernel_count += t.tensor_kernel_count;
+    out->paged_queries += t.paged_queries;
   }
   out->searches = S->n_search;
   out->queries = S->n_queries;

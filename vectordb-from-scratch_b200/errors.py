@@ -33,3 +33,8 @@ class IndexError_(VectorDbError):
 class NaNDistance(IndexError_):
     """A distance is NaN.  The reference panics (`partial_cmp().unwrap()`, src/flat_index.rs:62);
     libgfi reports it as an error instead of aborting (documented deviation)."""
+
+
+class Unproven(IndexError_):
+    """gfi_search_status only (GFI_ERR_UNPROVEN): a device-resident search could not prove its answer exact
+    (more near-ties of the k-th distance than the candidate lists hold); re-run through `search`."""

@@ -10,7 +10,7 @@ import enum
 import numpy as np
 
 from . import native
-from .errors import DimensionMismatch, InvalidVector, IndexError_, NaNDistance
+from .errors import DimensionMismatch, InvalidVector, IndexError_, NaNDistance, Unproven
 
 
 class DistanceMetric(enum.IntEnum):
@@ -30,6 +30,8 @@ def _raise(L, rc):
         raise InvalidVector(msg)
     if rc == 4:
         raise NaNDistance(msg)
+    if rc == 5:
+        raise Unproven(msg)
     raise IndexError_(msg)
 
 

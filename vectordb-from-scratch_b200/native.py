@@ -40,7 +40,7 @@ class GfiStats(ctypes.Structure):
         "n_slots", "n_live", "searches", "queries", "scan_queries", "tensor_queries", "fallback_queries",
         "kernel_launches", "bytes_fp32", "bytes_fp16", "scan_kernel_ns", "scan_kernel_count",
         "tensor_kernel_ns", "tensor_kernel_count", "coalesced_batches", "coalesced_requests", "shards", "merge_ns",
-        "merge_count")]
+        "merge_count", "paged_queries")]
 
 
 def lib():
