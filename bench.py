@@ -329,6 +329,7 @@ class Bench:
         for t in tss:
             t.synchronize()
         st0 = idx.stats()
+        sh0 = self.per_shard_stats()
         sampler = ClockSampler(sampler_gpu) if sampler_gpu is not None else None
         if sampler:
             sampler.start()
@@ -336,8 +337,10 @@ class Bench:
         e0.record(ts)
         for t in tss[1:]:
             t.wait_event(e0)
+        h0 = time.perf_counter()
         for i in range(steps):
             step(i)
+        self.host_enqueue_ms = (time.perf_counter() - h0) * 1e3 / steps  # host time to enqueue one step (no sync)
         for t in tss[1:]:
             ev = torch.cuda.Event()
             ev.record(t)
@@ -349,9 +352,24 @@ class Bench:
         ms = e0.elapsed_time(e1)
         clocks = sampler.finish() if sampler else None
         st1 = idx.stats()
+        sh1 = self.per_shard_stats()
+        # dominant-kernel time per launch on every shard's GPU (the slowest shard sets the step)
+        self.shard_kernel_ms = [max(b["tensor_kernel_ns"] - a["tensor_kernel_ns"], b["scan_kernel_ns"] - a["scan_kernel_ns"]) /
+                                max(1, max(b["tensor_kernel_count"] - a["tensor_kernel_count"],
+                                           b["scan_kernel_count"] - a["scan_kernel_count"])) / 1e6 for a, b in zip(sh0, sh1)]
         dq_keep = (dq, dks, outs)
         self.keep = dq_keep
         return ms, st0, st1, clocks
+
+    def per_shard_stats(self):
+        if self.G == 1:
+            return []
+        out = []
+        for g in range(self.G):
+            self.idx.set_option("stats_shard", g)
+            out.append(self.idx.stats())
+        self.idx.set_option("stats_shard", -1)
+        return out
 
     # ---- end to end: host buffers through the public C-ABI call, copies inside the timed region ----
     def e2e_leg(self, steps):
@@ -461,13 +479,14 @@ class Bench:
                "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
                "fallback_queries": int(st1["fallback_queries"] - st0["fallback_queries"]),
                "scanned_gbs_fp32_equiv": self.n_total * self.d * 4 / (ms_per_step * 1e-3) / 1e9,
-               "index_build_s": self.build_s}
+               "index_build_s": self.build_s, "host_enqueue_ms_per_step": self.host_enqueue_ms}
         if self.G > 1:
             mc = st1["merge_count"] - st0["merge_count"]
             out["exchange"] = {"kind": "peer stores from each shard's finalize kernel into the root GPU's gather block "
                                        "over NVLink + merge kernel on the root (no collective call)",
                                "merge_ms": (st1["merge_ns"] - st0["merge_ns"]) / max(mc, 1) / 1e6, "merges": int(mc),
-                               "bytes_per_shard_per_step": int(q * self.kk * 12 + q * 4)}
+                               "bytes_per_shard_per_step": int(q * self.kk * 12 + q * 4),
+                               "kernel_ms_per_shard": [round(x, 4) for x in self.shard_kernel_ms]}
         if clocks is not None:
             out["clocks"] = clocks
         if e2e:
@@ -475,6 +494,72 @@ class Bench:
         if cpu:
             out["cpu_baseline"], _ = cpu_reference_run(wl, 1, 0, budget_s=cpu_budget_s, max_row_bytes=1.5e9)
         return out
+
+
+def ingest_bench(device=0, n=1_000_000, d=768):
+    """N3: bulk load of the reference's flat vector file (src/persistence/mmap.rs:13-15: u32 dim, u32
+    count, then count x dim little-endian f32) through gfi_add_from_file -- file -> pinned double buffer -> H2D ->
+    row_stats (exact norms, fp16 shadow rows), chunks pipelined.  Reported next to the two rates that bound it on
+    this box: a pinned-host -> device copy of the same bytes (PCIe) and the device-side pass alone on rows that are
+    already in HBM (gfi_add_generated: generator + row_stats)."""
+    import numpy as np
+    import torch
+    import vectordb_from_scratch_b200 as gfi
+    from vectordb_from_scratch_b200 import synth
+    torch.cuda.set_device(device)
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else "/tmp"
+    path = os.path.join(tmpdir, f"gfi_ingest_{os.getpid()}.bin")
+    block = synth.gen_rows(9, 0, 50_000, d, 1)
+    try:
+        with open(path, "wb") as f:
+            f.write(np.array([d, n], dtype="<u4").tobytes())
+            for o in range(0, n, block.shape[0]):
+                f.write(block[:min(block.shape[0], n - o)].tobytes())
+        nbytes = n * d * 4
+        idx = gfi.GpuFlatIndex(METRIC_ID["cosine"], dim=d, device=device)
+        idx.reserve(n)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = idx.add_from_file(path)
+        idx.flush()
+        t_file = time.perf_counter() - t0
+        assert got == n and idx.len() == n
+        row = idx.get_vector(n - 1)
+        assert np.array_equal(row, block[(n - 1) % block.shape[0]])
+        idx.close()
+    finally:
+        if os.path.exists(path):
+            os.remove(path)
+    # the PCIe bound: the same bytes from pinned host memory in 64 MB copies
+    chunk = torch.empty(64 << 20, dtype=torch.uint8).pin_memory()
+    dst = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = max(1, nbytes // (64 << 20))
+    for _ in range(reps):
+        dst.copy_(chunk, non_blocking=True)
+    torch.cuda.synchronize()
+    pcie_gbs = reps * (64 << 20) / (time.perf_counter() - t0) / 1e9
+    # the device-side pass alone (rows produced in HBM by the generator kernel)
+    n_dev = 10_000_000
+    idx = gfi.GpuFlatIndex(METRIC_ID["cosine"], dim=d, device=device)
+    idx.reserve(n_dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    idx.add_generated(9, 0, n_dev, 1, 0)
+    idx.flush()
+    t_dev = time.perf_counter() - t0
+    idx.close()
+    torch.cuda.empty_cache()
+    pk, _ = peaks()
+    dev_bytes = n_dev * d * (4 + 4 + 4 + 2)  # generator writes fp32, row_stats reads it twice (2nd: L2) and writes fp16
+    return {"name": "ingest", "metric": "rows/s bulk-loaded from the reference's flat vector file (gfi_add_from_file)",
+            "value": n / t_file, "unit": "rows/s", "config": {"workload": f"bulk ingest {n} x {d} f32 from {tmpdir}", "rows": n, "dim": d},
+            "file_gbs": nbytes / t_file / 1e9, "seconds": t_file, "pcie_pinned_h2d_gbs": pcie_gbs,
+            "frac_of_pcie": nbytes / t_file / 1e9 / pcie_gbs,
+            "device_side": {"rows": n_dev, "rows_per_s": n_dev / t_dev, "seconds": t_dev,
+                            "hbm_gbs_algorithmic": dev_bytes / t_dev / 1e9, "frac_of_hbm": dev_bytes / t_dev / 1e9 / pk["hbm_gbs"],
+                            "what": "gfi_add_generated: generator kernel + row_stats (sequential exact norms, fp16 shadow rows)"}}
 
 
 def ranks_mode(args, wl, rank, world, local_rank, warmup):
@@ -545,7 +630,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gfi", choices=["gfi", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["ingest"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--secondary", default="auto", help="'auto', 'none' or a comma list of workloads")
     ap.add_argument("--no-sustained", action="store_true")
@@ -560,6 +645,10 @@ def main():
 
     if args.impl == "reference":
         reference_arm(args, wl, rank, world)
+        return
+    if wl == "ingest":
+        if rank == 0:
+            print(json.dumps(ingest_bench(local_rank, n=2_000_000)))
         return
 
     import torch
@@ -657,7 +746,7 @@ def main():
 
     # ---- the other BASELINE.json configs, same contract per entry ----
     if args.secondary == "auto":
-        sec = (["c3a_scan", "c3a", "c3b", "c4p1", "c4f1", "c4f50", "c5", "c1"] if world == 1 else
+        sec = (["c3a_scan", "c3a", "c3b", "c4p1", "c4f1", "c4f50", "c5", "c1", "ingest"] if world == 1 else
                ["c3a_scan", "c3b", "c5"]) if wl == "c2" else []
     elif args.secondary == "none":
         sec = []
@@ -666,6 +755,9 @@ def main():
     out_sec = []
     for s in sec:
         try:
+            if s == "ingest":
+                out_sec.append(ingest_bench(devices[0]))
+                continue
             sb = Bench(s, devices if s != "c1" else devices[:1], opts if s == wl else {})
             st = max(5, min(args.steps, 20 if WORKLOADS[s][5] >= 64 or WORKLOADS[s][1] >= 1_000_000 else 200))
             r = sb.run(st, warmup, cpu=not args.no_cpu_baseline, e2e=True, sampler_gpu=None, cpu_budget_s=4.0)

@@ -52,6 +52,7 @@ def test_sharded_search_matches_oracle_scan_and_tensor_paths(layout, metric):
     rows = oracle.gen_rows(61, 0, n, d, 1)
     idx = gfi.GpuFlatIndex(M[metric], devices=devs)
     idx.set_option("shard_block", 1024)  # ids interleave over the shards in blocks of 1024
+    idx.set_option("tensor_min_rows", 256)  # (5000 rows per shard on an 8-GPU box: keep the tcgen05 path in play)
     idx.add_batch(np.arange(n, dtype=np.uint64), rows)
     assert idx.len() == n and idx.dim() == d
     idx.flush()

@@ -1243,6 +1243,55 @@ int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int
     tl_actual = dim;
     return fail(GFI_ERR_DIMENSION_MISMATCH, "Dimension mismatch");
   }
+  if (!h->shards && count > 0 && !(h->any_id && first_id <= h->max_id_seen)) {
+    // Bulk path (fresh, ascending ids -- what a load of the reference's flat file is): the file is read straight
+    // into two pinned buffers in turn, and each chunk's H2D copy, id fill and row_stats pass run on the ingest stream
+    // while the next chunk is being read; one synchronisation at the end.
+    int32_t rc;
+    if (h->dim == 0) latch_dim(h, dim);
+    if ((rc = flush_locked(h)) != GFI_OK) return rc;
+    if ((rc = grow(h, h->n_slots + (int64_t)count)) != GFI_OK) return rc;
+    const uint32_t slot0 = (uint32_t)h->n_slots;
+    const int64_t rows_per = std::max<int64_t>(1, (64ll << 20) / ((int64_t)dim * 4));
+    PinBuf bufs[2];
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    struct Cleanup {
+      PinBuf* b; cudaEvent_t* e; cudaStream_t st;
+      ~Cleanup() { cudaStreamSynchronize(st); for (int i = 0; i < 2; ++i) { b[i].release(); if (e[i]) cudaEventDestroy(e[i]); } }
+    } cleanup{bufs, ev, h->ingest_stream};
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(bufs[i].ensure((size_t)rows_per * dim * 4));
+      CU_TRY(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    int64_t done = 0;
+    for (int64_t ci = 0; done < (int64_t)count; ++ci) {
+      const int b = (int)(ci & 1);
+      const int64_t take = std::min<int64_t>(rows_per, (int64_t)count - done);
+      if (ci >= 2) CU_TRY(cudaEventSynchronize(ev[b]));  // the copy that read this buffer two chunks ago
+      if (fread(bufs[b].p, 4, (size_t)take * dim, f) != (size_t)take * dim)
+        return fail(GFI_ERR_INDEX, "flat file is shorter than its header says");
+      float* dst = h->x32.as<float>() + (size_t)(slot0 + done) * h->dpad;
+      if (h->dpad == (int)dim) {
+        CU_TRY(cudaMemcpyAsync(dst, bufs[b].p, (size_t)take * dim * 4, cudaMemcpyHostToDevice, h->ingest_stream));
+      } else {  // rows are padded to a multiple of 4 floats on the device: zero the block, copy row by row pitch
+        CU_TRY(cudaMemsetAsync(dst, 0, (size_t)take * h->dpad * 4, h->ingest_stream));
+        CU_TRY(cudaMemcpy2DAsync(dst, (size_t)h->dpad * 4, bufs[b].p, (size_t)dim * 4, (size_t)dim * 4, (size_t)take,
+                                 cudaMemcpyHostToDevice, h->ingest_stream));
+      }
+      CU_TRY(cudaEventRecord(ev[b], h->ingest_stream));
+      CU_TRY(launch_fill_ids(h->ids.as<uint64_t>() + slot0 + done, first_id + (uint64_t)done, take, h->ingest_stream));
+      if ((rc = ingest_slots(h, (int64_t)slot0 + done, take, false, 0, 0, 0)) != GFI_OK) return rc;
+      done += take;
+    }
+    CU_TRY(cudaStreamSynchronize(h->ingest_stream));
+    h->n_slots += (int64_t)count;
+    register_ids(h, nullptr, first_id, (int64_t)count, slot0);
+    if (!h->meta_values.empty()) h->meta_dirty = true;
+    if ((rc = read_counters(h)) != GFI_OK) return rc;
+    if ((rc = upload_live(h)) != GFI_OK) return rc;
+    if (out_rows) *out_rows = (int64_t)count;
+    return GFI_OK;
+  }
   const int64_t chunk = std::max<int64_t>(1, (32ll << 20) / ((int64_t)dim * 4));
   std::vector<float> buf((size_t)chunk * dim);
   std::vector<uint64_t> ids((size_t)chunk);

@@ -93,6 +93,7 @@ struct IngestParams {
   int gen; uint32_t seed; uint64_t first_row; int kind;
 };
 cudaError_t launch_ingest(const IngestParams& p, cudaStream_t st);
+cudaError_t launch_fill_ids(uint64_t* p, uint64_t first, int64_t n, cudaStream_t st);  // p[i] = first + i
 
 struct PrepQueriesParams {
   const float* q_in;   // [q][d] unpadded

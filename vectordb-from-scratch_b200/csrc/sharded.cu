@@ -140,6 +140,7 @@ struct ShardSet {
   std::vector<std::unique_ptr<ShardedCtx>> pool;
   std::atomic<int64_t> n_search{0}, n_queries{0}, n_launch{0}, merge_ns{0}, merge_cnt{0};
   int opt_profile = 0;
+  int stats_shard = -1;  // option "stats_shard": gfi_get_stats reports this shard alone (-1: the sum over shards)
 
   int shard_of(uint64_t id) const { return (int)((id / (uint64_t)block) % (uint64_t)G); }
 
@@ -869,7 +870,9 @@ int32_t sharded_distances(gfi_index* H, const float* queries, int64_t q, int64_t
 
 int32_t sharded_get_stats(gfi_index* H, gfi_stats* out) {
   ShardSet* S = H->shards;
-  for (gfi_index* s : S->sub) {
+  for (int g = 0; g < S->G; ++g) {
+    if (S->stats_shard >= 0 && g != S->stats_shard) continue;
+    gfi_index* s = S->sub[(size_t)g];
     gfi_stats t;
     int32_t rc = gfi_get_stats(s, &t);
     if (rc != GFI_OK) return rc;
@@ -907,6 +910,11 @@ int32_t sharded_set_option(gfi_index* H, const char* name, int64_t value) {
     if (sharded_len(H) != 0) return fail(GFI_ERR_INDEX, "shard_block can only change while the index is empty");
     if (value < 1) return fail(GFI_ERR_INDEX, "shard_block must be positive");
     S->block = value;
+    return GFI_OK;
+  }
+  if (n == "stats_shard") {
+    if (value < -1 || value >= S->G) return fail(GFI_ERR_INDEX, "stats_shard out of range");
+    S->stats_shard = (int)value;
     return GFI_OK;
   }
   if (n == "profile") S->opt_profile = (int)value;
