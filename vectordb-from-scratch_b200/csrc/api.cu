@@ -690,10 +690,12 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   const int64_t num_n_tiles = (h->n_slots + 255) / 256;
   const int rank = std::max(1, std::min(kSeedR, h->opt_seed_rank));
   // sample size S (rows) so that the expected number of rows below the rank-th sample score is `hits`; the
-  // sample is capped so that the per-(query, tile) seed lists stay below 64 MiB, and the expectation that results
-  // from the cap (hits_eff >= hits) is what sizes the candidate slices and picks the select path below
+  // sample is capped so that the per-(query, tile) seed lists stay below 256 MiB, and the expectation that results
+  // from the cap (hits_eff >= hits) is what sizes the candidate slices and picks the select path below.  (The cap was
+  // 64 MiB in round 1: a 12.5M-row shard with 4096 queries then got a third of the sample it asked for, three times
+  // the survivors -- 1500 per query -- and with them three times the entries into the main pass's survivor section.)
   int64_t seed_tiles = (int64_t)std::ceil((double)rank * (double)h->n_slots / (double)hits / 256.0);
-  const int64_t seed_tiles_max = std::max<int64_t>(64, std::min<int64_t>(4096, (64ll << 20) / ((int64_t)q * 2 * kSeedR * 4)));
+  const int64_t seed_tiles_max = std::max<int64_t>(64, std::min<int64_t>(4096, (256ll << 20) / ((int64_t)q * 2 * kSeedR * 4)));
   seed_tiles = std::max<int64_t>(1, std::min<int64_t>(seed_tiles, std::min<int64_t>(num_n_tiles, seed_tiles_max)));
   {
     // whole waves: trim the sample (by at most 20%) so the seed pass does not end in a mostly idle round

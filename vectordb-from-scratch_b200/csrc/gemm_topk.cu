@@ -88,24 +88,92 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
   return v;
 }
 
-// Main-pass filter of one accumulator half (128 columns) for the calling thread's query: 32 columns at a time
-// with two TMEM loads in flight.
-//  MODE 0: score = acc * a[row] + b[row] (coefficients as broadcast 128-bit shared loads), 3-input MIN
-//          trees, ONE compare per 32 values against the query's threshold.
-//  MODE 3 (cosine, rows stored pre-normalised: score = acc * c_q with one per-batch constant): compare raw
-//          accumulators with thr / c_q -- no coefficients, 3-input MAX trees; tombstoned / out-of-range
-//          rows are weeded out in the rare path.
-// Rare path, kept SMALL and warp-uniform: if any lane of the warp has a survivor in a block, the warp
-// re-reads the 8-column groups concerned from TMEM (tcgen05.ld is warp-collective) and each lane appends
-// its own survivors to the candidate slice private to this (query, unit, half): plain stores, no atomics.
-// Shared by the k-ring kernel and the short-K row-stationary kernel.
+// Main-pass filter of one accumulator half (128 columns) for the calling thread's query.
+//
+// Hot loop (every item): 32 columns at a time with two TMEM loads in flight; per 32 values ONE compare against the
+// query's threshold, whose outcome is one bit of a 4-bit block mask -- nothing else happens per block.
+//  MODE 0: score = acc * a[row] + b[row] (coefficients as broadcast 128-bit shared loads), 3-input MIN trees.
+//  MODE 3 (cosine, rows stored pre-normalised: score = acc * c_q with one per-batch constant): raw accumulators
+//          against thr_raw = thr / c_q -- no coefficients, 3-input MAX trees; tombstoned / out-of-range rows are
+//          weeded out in the survivor section with the live words `lv` the caller loaded once per row tile.
+// Survivor section (epi_survivors, ONE copy of the code behind ONE warp vote per item): the blocks some lane flagged
+// are re-read from TMEM and the flagged lanes append their survivors with plain stores to the candidate slice
+// private to this (query, unit, half) -- no atomics.
+// Round-2 profile of the previous form (a survivor path inlined after each of the four blocks, a vote per block, a
+// global load of the live word and an 8-way branch ladder per hit group; profiles/r02_ncu_gemm_sk_c5_*.txt): a
+// survivor-path entry cost ~1700 cycles and its four copies sat between the hot blocks; at C5's hit rate (one block
+// in eight) that was a third of the epilogue's time and most of the spread between the eight epilogue warps, which is
+// what the MMA issuer waits for.  Shared by the k-ring kernel and the short-K row-stationary kernel.
+template <int MODE>
+__device__ __noinline__ void epi_survivors(uint64_t* slice, const uint32_t cap, uint32_t* flags, const uint32_t taddr,
+                                           const uint32_t cs_addr, const float thr, const float thr_raw,
+                                           const float c_q, const uint32_t slot_base, unsigned short* hc,
+                                           const uint32_t bm, const uint32_t lv0, const uint32_t lv1,
+                                           const uint32_t lv2, const uint32_t lv3) {
+  // (plain scalars only: a reference to the kernel's parameter block would force a copy of it into local memory)
+  // The eight epilogue warps of a CTA release an accumulator together, so the LATENCY of this section on the one warp
+  // that takes it sets the pace of the whole item: group maxima first, then only the 8-column groups that hold a hit.
+  uint32_t wm = __reduce_or_sync(0xffffffffu, bm);
+  uint32_t cnt = bm ? *hc : 0u;
+  bool nan = false;
+#pragma unroll 1
+  while (wm) {
+    const int blk = __ffs(wm) - 1;
+    wm &= wm - 1;
+    const int c0 = blk * 32;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(taddr + c0, v);  // warp-collective: every lane takes part, flagged or not
+    tmem_ld_wait();
+    if ((bm >> blk) & 1u) {
+      const uint32_t lvw = blk == 0 ? lv0 : (blk == 1 ? lv1 : (blk == 2 ? lv2 : lv3));
+      float s[32];
+      if (MODE == 3) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) s[j] = __uint_as_float(v[j]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          const float4 k = lds128(cs_addr + (c0 + j) * 8);
+          s[j] = fmaf(__uint_as_float(v[j]), k.x, k.y);
+          s[j + 1] = fmaf(__uint_as_float(v[j + 1]), k.z, k.w);
+        }
+      }
+#pragma unroll
+      for (int g8 = 0; g8 < 4; ++g8) {
+        const float* g = s + 8 * g8;
+        // raw: larger accumulator = better; coefficient mode: smaller score = better (min/max drop NaN operands, as in
+        // the hot loop: a NaN query makes every value NaN, and that does compare as a hit)
+        const float mg = MODE == 3 ? fmax3(fmax3(g[0], g[1], g[2]), fmax3(g[3], g[4], g[5]), fmaxf(g[6], g[7]))
+                                   : fmin3(fmin3(g[0], g[1], g[2]), fmin3(g[3], g[4], g[5]), fminf(g[6], g[7]));
+        const bool ghit = MODE == 3 ? !(mg <= thr_raw) : !(mg >= thr);  // (an all-NaN group compares as a hit)
+        if (ghit) {
+          const uint32_t lvb = MODE == 3 ? (lvw >> (8 * g8)) & 0xffu : 0xffu;  // tombstones, slots beyond the index
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            const float a = g[jj];
+            const float score = MODE == 3 ? a * c_q : a;
+            const bool live = (lvb >> jj) & 1u;
+            const bool take = live && (MODE == 3 ? !(a <= thr_raw) : true) && !(score >= thr);
+            const bool is_nan = score != score;
+            nan = nan || (take && is_nan);
+            const bool keep = take && !is_nan;
+            if (keep && cnt < cap) slice[cnt] = pack_key(score, slot_base + (uint32_t)(c0 + 8 * g8 + jj));
+            cnt += keep ? 1u : 0u;  // beyond the capacity only counted: select_kernel sees the overflow and falls back
+          }
+        }
+      }
+    }
+  }
+  if (bm) *hc = (unsigned short)min(cnt, 65535u);
+  if (nan) atomicOr(flags, kFlagNaN);
+}
+
 template <int MODE>
 __device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
-                                                const float thr, const float c_q, const int qidx, const int64_t n0,
-                                                const int half, const int64_t unit, unsigned short* hitcnt) {
-  const IndexView& iv = p.iv;
-  const float thr_raw = MODE == 3 ? __fdiv_rn(thr, c_q) : 0.f;  // exact: c_q is a (negative) power of two
-  auto process = [&](const uint32_t (&r)[32], const int c0) {
+                                                const float thr, const float thr_raw, const float c_q, const int qidx,
+                                                const int64_t n0, const int half, const int64_t unit,
+                                                unsigned short* hitcnt, const uint32_t (&lv)[4]) {
+  auto block_hit = [&](const uint32_t (&r)[32], const int c0) -> bool {
     float m8[4];
 #pragma unroll
     for (int g8 = 0; g8 < 4; ++g8) {
@@ -122,81 +190,51 @@ __device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint3
         v2 = fmaf(v2, k1.x, k1.y); v3 = fmaf(v3, k1.z, k1.w);
         v4 = fmaf(v4, k2.x, k2.y); v5 = fmaf(v5, k2.z, k2.w);
         v6 = fmaf(v6, k3.x, k3.y); v7 = fmaf(v7, k3.z, k3.w);
-        // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the rare path)
+        // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the survivor section)
         m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
       }
     }
     const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
-    const bool hit_any = MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
-    if (__any_sync(0xffffffffu, hit_any && qidx < p.q) && !(p.debug & 8)) {
-#pragma unroll 1
-      for (int g8 = 0; g8 < 4; ++g8) {
-        const float mg = g8 == 0 ? m8[0] : (g8 == 1 ? m8[1] : (g8 == 2 ? m8[2] : m8[3]));
-        const bool mine = (MODE == 3 ? !(mg <= thr_raw) : !(mg >= thr)) && qidx < p.q;
-        if (!__any_sync(0xffffffffu, mine)) continue;
-        uint32_t v[8];
-        tmem_ld_32x32b_x8(taddr + c0 + 8 * g8, v);
-        const int64_t slot0 = n0 + half * (BN / 2) + c0 + 8 * g8;  // multiple of 8: one word of live bits
-        uint32_t lv = 0xffu;
-        float4 k0, k1, k2, k3;
-        if (MODE == 3) {
-          lv = 0;
-          if (mine && slot0 < iv.n_slots) lv = (__ldg(iv.live + (slot0 >> 5)) >> (slot0 & 31)) & 0xffu;
-        } else {
-          k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
-          k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
-        }
-        tmem_ld_wait();
-        if (mine) {
-          float s8[8];
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) s8[jj] = __uint_as_float(v[jj]);
-          if (MODE == 3) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-              const bool ok = !(s8[jj] <= thr_raw) && ((lv >> jj) & 1u) && slot0 + jj < iv.n_slots;
-              s8[jj] = ok ? s8[jj] * c_q : __int_as_float(0x7f800000);  // +inf never beats the threshold
-            }
-          } else {
-            s8[0] = fmaf(s8[0], k0.x, k0.y); s8[1] = fmaf(s8[1], k0.z, k0.w);
-            s8[2] = fmaf(s8[2], k1.x, k1.y); s8[3] = fmaf(s8[3], k1.z, k1.w);
-            s8[4] = fmaf(s8[4], k2.x, k2.y); s8[5] = fmaf(s8[5], k2.z, k2.w);
-            s8[6] = fmaf(s8[6], k3.x, k3.y); s8[7] = fmaf(s8[7], k3.z, k3.w);
-          }
-          unsigned short* hc = hitcnt + half * kGemmMaxQueries + qidx;
-          uint32_t cnt = *hc;
-          uint64_t* slice = p.cand + (size_t)qidx * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap;
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            const float score = s8[jj];
-            if (!(score >= thr)) {
-              if (score != score) {
-                atomicOr(p.flags, kFlagNaN);
-              } else {
-                if (cnt < p.cand_cap) slice[cnt] = pack_key(score, (uint32_t)(slot0 + jj));
-                ++cnt;  // beyond the capacity only counted: select_kernel sees the overflow and falls back
-              }
-            }
-          }
-          *hc = (unsigned short)min(cnt, 65535u);
-        }
-      }
-    }
+    return MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
   };
-  if (!(p.debug & 4)) {
+  if (p.debug & 4) return;
+  uint32_t bm = 0;
+  {
     uint32_t ra[32], rb[32];
     tmem_ld_32x32b_x32(taddr, ra);
     tmem_ld_wait();
     tmem_ld_32x32b_x32(taddr + 32, rb);
-    process(ra, 0);
+    bm |= block_hit(ra, 0) ? 1u : 0u;
     tmem_ld_wait();
     tmem_ld_32x32b_x32(taddr + 64, ra);
-    process(rb, 32);
+    bm |= block_hit(rb, 32) ? 2u : 0u;
     tmem_ld_wait();
     tmem_ld_32x32b_x32(taddr + 96, rb);
-    process(ra, 64);
+    bm |= block_hit(ra, 64) ? 4u : 0u;
     tmem_ld_wait();
-    process(rb, 96);
+    bm |= block_hit(rb, 96) ? 8u : 0u;
+  }
+  if (qidx >= p.q) bm = 0;  // padding queries (threshold -inf) never match; NaN accumulators cannot fake a hit either
+  if (!__any_sync(0xffffffffu, bm != 0) || (p.debug & 8)) return;
+  // (qidx < p.q <= kGemmMaxQueries whenever bm != 0; other lanes only take part in the warp-collective loads)
+  const int qi = bm ? qidx : 0;
+  epi_survivors<MODE>(p.cand + (size_t)qi * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap, p.cand_cap, p.flags,
+                      taddr, cs_addr, thr, thr_raw, c_q, (uint32_t)(n0 + half * (BN / 2)),
+                      hitcnt + half * kGemmMaxQueries + qi, bm, lv[0], lv[1], lv[2], lv[3]);
+}
+
+// The live words of the 128 rows [slot0, slot0 + 128) (slot0 a multiple of 128), bits of slots beyond the index cleared
+// (raw epilogue only: the coefficient epilogue gets tombstones and masks through b = +inf).
+__device__ __forceinline__ void load_live4(const IndexView& iv, const int64_t slot0, uint32_t (&lv)[4]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int64_t s = slot0 + 32 * i;
+    uint32_t w = 0;
+    if (s < iv.n_slots) {
+      w = __ldg(iv.live + (s >> 5));
+      if (s + 32 > iv.n_slots) w &= (1u << (uint32_t)(iv.n_slots - s)) - 1u;
+    }
+    lv[i] = w;
   }
 }
 
@@ -431,6 +469,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
     // raw mode: score = acc * c_q, c_q = -(1 / query scale) * 2^-14 (row scale), exact powers of two
     const uint32_t tempty_lead0 = CG == 2 ? mapa_u32(smem_u32(tempty), 0) : 0u;
     const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
+    const float inv_cq = MODE == 3 ? 1.0f / c_q : 0.f;  // exact: c_q is a (negative) power of two
     uint32_t ai = 0;
     for (int64_t w = unit; w < n_items; w += nunits, ++ai) {
       const uint32_t as = ai & 1u, aph = (ai >> 1) & 1u;
@@ -441,6 +480,8 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
       const int qidx = m_tile * BM + mrow;
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
       if ((MODE == 0 || MODE == 3) && qidx < p.q) thr = p.thresh[qidx];
+      uint32_t lv[4] = {0u, 0u, 0u, 0u};
+      if (MODE == 3) load_live4(iv, n0 + half * (BN / 2), lv);  // in flight while the accumulator is awaited
       float sd[kSeedR];
 #pragma unroll
       for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
@@ -452,7 +493,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
       if (MODE == 0 || MODE == 3) {
-        epi_filter_half<MODE>(p, taddr, cs_addr, thr, c_q, qidx, n0, half, unit, hitcnt);
+        epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv);
       } else {
         // seed pass / debug dump: one 32-column block at a time
 #pragma unroll 1
@@ -607,7 +648,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
   const int64_t ntiles = unit < p.num_n_tiles ? (p.num_n_tiles - unit + nunits - 1) / nunits : 0;
   const int64_t total = ntiles * M;                 // items of this CTA
   const bool diag = (p.debug & 32) && blockIdx.x == 0;
-  long long w_a = 0, w_b = 0, w_c = 0;              // per-role wait cycles (diag)
+  long long w_a = 0, w_b = 0, w_c = 0, w_x = 0;     // per-role wait cycles; w_x: MMA issue / epilogue filter cycles (diag)
 
   if (tid == 0) {
     for (int s = 0; s < kNA; ++s) {
@@ -696,8 +737,12 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       mbar_wait_d(&tempty[as], aph ^ 1u, diag, w_c);
       mbar_wait_d(&afull[s], u & 1u, diag, w_a);
       tc_fence_after();
+      const long long ti0 = diag ? clock64() : 0;
       const uint32_t d_tmem = tmem_base + as * BN;
       const uint32_t a_lo = a_lo_base + (uint32_t)s * (sk::kAStageBytes >> 4);
+      // (Issuing the item as two N = 128 halves, each released by its own four epilogue warps, was measured in round
+      // 2: 13.4 -> 14.4 ms on C5 -- the N = 128 MMAs and the second wait in the middle of the item cost more than the
+      // decoupling of the halves gained.)
       if (!(p.debug & 16)) {
 #pragma unroll 1
         for (int k = 0; k < nk16; ++k) {
@@ -708,6 +753,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
         }
       }
       umma_commit_elect(done0 + s * 8);
+      if (diag) w_x += clock64() - ti0;
       if (++m == M) { m = 0; ++j; }
     }
   } else if ((warp == 2 || warp == 3) && MODE != 3) {
@@ -751,6 +797,8 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     const int half = (warp - kEpiWarp0) >> 2;
     const int mrow = quarter * 32 + lane;
     const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
+    const float inv_cq = MODE == 3 ? 1.0f / c_q : 0.f;  // exact: c_q is a (negative) power of two
+    uint32_t lv[4] = {0u, 0u, 0u, 0u};
     int m = 0;
     int64_t j = 0;
     for (int64_t it = 0; it < total; ++it) {
@@ -762,12 +810,15 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       const int qidx = m * BM + mrow;
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
       if (qidx < p.q) thr = p.thresh[qidx];
+      if (MODE == 3 && m == 0) load_live4(iv, n0 + half * (BN / 2), lv);  // once per row tile
       if (MODE != 3 && m == 0) mbar_wait_d(&cfull[cb], (uint32_t)(j >> 1) & 1u, diag, w_c);
       mbar_wait_d(&done[s], u & 1u, diag, w_a);
       tc_fence_after();
+      const long long te0 = diag ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
-      epi_filter_half<MODE>(p, taddr, cs_addr, thr, c_q, qidx, n0, half, unit, hitcnt);
+      epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv);
+      if (diag) w_x += clock64() - te0;
       tc_fence_before();
       __syncwarp();
       const bool last_m = m == M - 1;
@@ -779,9 +830,9 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     }
   }
 
-  if (diag && (tid == 0 || tid == 32 || tid == kEpiWarp0 * 32))
-    printf("[gemm_topk_sk] role %d items %lld waits: A/done %lld, B %lld, tmem/coef %lld clk\n", warp, (long long)total,
-           w_a, w_b, w_c);
+  if (diag && (tid == 0 || tid == 32 || (warp >= kEpiWarp0 && lane == 0)))
+    printf("[gemm_topk_sk] warp %d items %lld waits: A/done %lld, B %lld, tmem/coef %lld clk; issue/filter %lld clk\n", warp,
+           (long long)total, w_a, w_b, w_c, w_x);
   tc_fence_before();
   __syncthreads();
   for (int i = tid; i < 2 * p.q; i += kGemmThreads) {
