@@ -397,14 +397,49 @@ class Bench:
         for _ in range(3):
             call()
         # single-query workloads: 256 calls, so that the median / p99 call latency means something
-        n_calls = 256 if q == 1 else max(3, min(steps, 50))
+        n_calls = 256 if q == 1 else max(4, min(steps, 50))
         lat = []
         t0 = time.perf_counter()
         for _ in range(n_calls):
             t1 = time.perf_counter()
             call()
             lat.append(time.perf_counter() - t1)
-        t_e2e = (time.perf_counter() - t0) / n_calls
+        t_serial = (time.perf_counter() - t0) / n_calls
+        t_e2e, callers = t_serial, 1
+        if q >= 256:
+            # Batch workloads: TWO caller threads, each making the same synchronous gfi_search calls (the reference
+            # server answers requests from many workers over one index, src/server/mod.rs:13-16).  Every call still
+            # copies its queries in and its results out; the copies of one call overlap the kernels of the other.
+            import threading
+            callers = 2
+            per = max(3, n_calls // callers)
+            gate = threading.Barrier(callers + 1)
+            errs = []
+
+            def worker():
+                try:
+                    for _ in range(3):  # untimed: the second caller's search context allocates its buffers here
+                        call()
+                    gate.wait()
+                    for _ in range(per):
+                        call()
+                except Exception as e:  # surfaced below: a failed call must fail the bench, not shorten the run
+                    errs.append(e)
+                    gate.abort()
+
+            ths = [threading.Thread(target=worker) for _ in range(callers)]
+            for t in ths:
+                t.start()
+            try:
+                gate.wait()
+            except threading.BrokenBarrierError:
+                pass
+            t0 = time.perf_counter()
+            for t in ths:
+                t.join()
+            t_e2e = (time.perf_counter() - t0) / (per * callers)
+            if errs:
+                raise errs[0]
         idx.search_status()
         idx.set_option("profile", 1)
         lat.sort()
@@ -412,6 +447,8 @@ class Bench:
         d2h = q * self.kk * 12 + q * 4 + 64 * self.G
         return {"value": self.G_units() * q / t_e2e, "unit": "queries/s", "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "ms_per_step": t_e2e * 1e3,
+                "callers": callers, "serial_ms_per_step": t_serial * 1e3,
+                "serial_value": self.G_units() * q / t_serial,
                 "call_latency_ms": {"median": lat[len(lat) // 2] * 1e3,
                                     "p99": lat[min(len(lat) - 1, int(len(lat) * 0.99))] * 1e3, "best": lat[0] * 1e3,
                                     "calls": len(lat)},
