@@ -168,21 +168,30 @@ __device__ __noinline__ void epi_survivors(uint64_t* slice, const uint32_t cap, 
   if (nan) atomicOr(flags, kFlagNaN);
 }
 
-template <int MODE>
-__device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
-                                                const float thr, const float thr_raw, const float c_q, const int qidx,
-                                                const int64_t n0, const int half, const int64_t unit,
-                                                unsigned short* hitcnt, const uint32_t (&lv)[4]) {
-  auto block_hit = [&](const uint32_t (&r)[32], const int c0) -> bool {
-    float m8[4];
+// One 32-column block of the hot loop: does any of this thread's 32 scores beat the query's threshold?
+//  UNI (coefficient mode, short-K kernel): every eligible row of the row tile has the same first coefficient `a_u`
+//  (rows of one magnitude share their power-of-two fp16 scale -- the usual case), so only b is read from shared
+//  memory: 8 broadcast LDS.128 per block instead of 16.  The coefficient loads are what bounds this loop: a
+//  warp-wide LDS.128 of one address still returns 512 bytes to the register file (~2 wavefronts), 1100 cycles of the
+//  shared-memory pipe per item with (a, b) pairs against 1024 cycles of MMAs (ncu, profiles/r02_ncu_gemm_sk_c5_*).
+template <int MODE, bool UNI>
+__device__ __forceinline__ bool epi_block_hit(const uint32_t (&r)[32], const int c0, const uint32_t cs_addr,
+                                              const uint32_t bs_addr, const float a_u, const float thr,
+                                              const float thr_raw) {
+  float m8[4];
 #pragma unroll
-    for (int g8 = 0; g8 < 4; ++g8) {
-      float v0 = __uint_as_float(r[8 * g8]), v1 = __uint_as_float(r[8 * g8 + 1]);
-      float v2 = __uint_as_float(r[8 * g8 + 2]), v3 = __uint_as_float(r[8 * g8 + 3]);
-      float v4 = __uint_as_float(r[8 * g8 + 4]), v5 = __uint_as_float(r[8 * g8 + 5]);
-      float v6 = __uint_as_float(r[8 * g8 + 6]), v7 = __uint_as_float(r[8 * g8 + 7]);
-      if (MODE == 3) {
-        m8[g8] = fmax3(fmax3(v0, v1, v2), fmax3(v3, v4, v5), fmaxf(v6, v7));
+  for (int g8 = 0; g8 < 4; ++g8) {
+    float v0 = __uint_as_float(r[8 * g8]), v1 = __uint_as_float(r[8 * g8 + 1]);
+    float v2 = __uint_as_float(r[8 * g8 + 2]), v3 = __uint_as_float(r[8 * g8 + 3]);
+    float v4 = __uint_as_float(r[8 * g8 + 4]), v5 = __uint_as_float(r[8 * g8 + 5]);
+    float v6 = __uint_as_float(r[8 * g8 + 6]), v7 = __uint_as_float(r[8 * g8 + 7]);
+    if (MODE == 3) {
+      m8[g8] = fmax3(fmax3(v0, v1, v2), fmax3(v3, v4, v5), fmaxf(v6, v7));
+    } else {
+      if (UNI) {
+        const float4 b0 = lds128(bs_addr + (c0 + 8 * g8) * 4), b1 = lds128(bs_addr + (c0 + 8 * g8 + 4) * 4);
+        v0 = fmaf(v0, a_u, b0.x); v1 = fmaf(v1, a_u, b0.y); v2 = fmaf(v2, a_u, b0.z); v3 = fmaf(v3, a_u, b0.w);
+        v4 = fmaf(v4, a_u, b1.x); v5 = fmaf(v5, a_u, b1.y); v6 = fmaf(v6, a_u, b1.z); v7 = fmaf(v7, a_u, b1.w);
       } else {
         const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
         const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
@@ -190,30 +199,47 @@ __device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint3
         v2 = fmaf(v2, k1.x, k1.y); v3 = fmaf(v3, k1.z, k1.w);
         v4 = fmaf(v4, k2.x, k2.y); v5 = fmaf(v5, k2.z, k2.w);
         v6 = fmaf(v6, k3.x, k3.y); v7 = fmaf(v7, k3.z, k3.w);
-        // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the survivor section)
-        m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
       }
+      // (min drops NaN operands; a NaN query makes every score NaN, which still reaches the survivor section)
+      m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
     }
-    const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
-    return MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
-  };
-  if (p.debug & 4) return;
-  uint32_t bm = 0;
-  {
-    uint32_t ra[32], rb[32];
-    tmem_ld_32x32b_x32(taddr, ra);
-    tmem_ld_wait();
-    tmem_ld_32x32b_x32(taddr + 32, rb);
-    bm |= block_hit(ra, 0) ? 1u : 0u;
-    tmem_ld_wait();
-    tmem_ld_32x32b_x32(taddr + 64, ra);
-    bm |= block_hit(rb, 32) ? 2u : 0u;
-    tmem_ld_wait();
-    tmem_ld_32x32b_x32(taddr + 96, rb);
-    bm |= block_hit(ra, 64) ? 4u : 0u;
-    tmem_ld_wait();
-    bm |= block_hit(rb, 96) ? 8u : 0u;
   }
+  const float mall = MODE == 3 ? fmax3(m8[0], m8[1], fmaxf(m8[2], m8[3])) : fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
+  return MODE == 3 ? !(mall <= thr_raw) : !(mall >= thr);
+}
+
+template <int MODE, bool UNI>
+__device__ __forceinline__ uint32_t epi_block_mask(const uint32_t taddr, const uint32_t cs_addr, const uint32_t bs_addr,
+                                                   const float a_u, const float thr, const float thr_raw) {
+  uint32_t bm = 0;
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(taddr, ra);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 32, rb);
+  bm |= epi_block_hit<MODE, UNI>(ra, 0, cs_addr, bs_addr, a_u, thr, thr_raw) ? 1u : 0u;
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 64, ra);
+  bm |= epi_block_hit<MODE, UNI>(rb, 32, cs_addr, bs_addr, a_u, thr, thr_raw) ? 2u : 0u;
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 96, rb);
+  bm |= epi_block_hit<MODE, UNI>(ra, 64, cs_addr, bs_addr, a_u, thr, thr_raw) ? 4u : 0u;
+  tmem_ld_wait();
+  bm |= epi_block_hit<MODE, UNI>(rb, 96, cs_addr, bs_addr, a_u, thr, thr_raw) ? 8u : 0u;
+  return bm;
+}
+
+// `uni`: the row tile's eligible rows share the coefficient a_u (warp-uniform; always false for the k-ring kernel,
+// which stages coefficients per item).  bs_addr: this half's 128 b values as a plain float array (uni only).
+template <int MODE>
+__device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
+                                                const float thr, const float thr_raw, const float c_q, const int qidx,
+                                                const int64_t n0, const int half, const int64_t unit,
+                                                unsigned short* hitcnt, const uint32_t (&lv)[4], const bool uni = false,
+                                                const uint32_t bs_addr = 0, const float a_u = 0.f) {
+  if (p.debug & 4) return;
+  uint32_t bm;
+  if (MODE == 0 && uni) bm = epi_block_mask<MODE, true>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
+  else bm = epi_block_mask<MODE, false>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
   if (qidx >= p.q) bm = 0;  // padding queries (threshold -inf) never match; NaN accumulators cannot fake a hit either
   if (!__any_sync(0xffffffffu, bm != 0) || (p.debug & 8)) return;
   // (qidx < p.q <= kGemmMaxQueries whenever bm != 0; other lanes only take part in the warp-collective loads)
@@ -603,7 +629,9 @@ constexpr int kBChunkBytes = BN * BK * 2;               // 256 rows x 64 fp16 = 
 constexpr size_t kOffB = 0;
 constexpr size_t kOffA = kOffB + 2 * (size_t)kBChunkBytes;
 constexpr size_t kOffCoef = kOffA + (size_t)kNA * kAStageBytes;
-constexpr size_t kOffBar = kOffCoef + 2 * BN * sizeof(float2);
+constexpr size_t kOffBOnly = kOffCoef + 2 * BN * sizeof(float2);   // [2 stages][BN] b alone (uniform-a hot loop)
+constexpr size_t kOffUni = kOffBOnly + 2 * BN * sizeof(float);     // [2 stages][2 stager warps] shared a, or NaN
+constexpr size_t kOffBar = kOffUni + 16;
 constexpr size_t kOffCnt = kOffBar + 24 * 8 + 16;
 constexpr size_t kSmemUsed = kOffCnt + 2 * 2 * kGemmMaxQueries;
 constexpr size_t kSmemBytes = kSmemUsed + 1024;
@@ -629,6 +657,8 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
   unsigned char* sB = smem + sk::kOffB;
   unsigned char* sA = smem + sk::kOffA;
   float2* sCoef = reinterpret_cast<float2*>(smem + sk::kOffCoef);
+  float* sBOnly = reinterpret_cast<float*>(smem + sk::kOffBOnly);
+  float* sUni = reinterpret_cast<float*>(smem + sk::kOffUni);
   uint64_t* afull = reinterpret_cast<uint64_t*>(smem + sk::kOffBar);  // TMA -> MMA: A stage loaded
   uint64_t* done = afull + kNA;    // MMA -> producer + epilogue: the item's MMAs have completed (ONE commit per item)
   uint64_t* bfull = done + kNA;    // TMA -> MMA: row tile loaded
@@ -784,10 +814,28 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
           }
         }
       }
+      // Do this warp's eligible rows share one first coefficient?  (0 = no eligible row here, NaN = they differ)
+      uint32_t abits = 0;
+      bool same = true;
+#pragma unroll
+      for (int i = 0; i < RPL; ++i) {
+        if (cv[i].y < kInf || cv[i].y != cv[i].y) {  // eligible (b finite or NaN); ineligible rows carry b = +inf
+          const uint32_t ab = __float_as_uint(cv[i].x);
+          same = same && (abits == 0 || abits == ab) && ab != 0;
+          abits = ab;
+        }
+      }
+      const uint32_t ref = __reduce_max_sync(0xffffffffu, abits);
+      same = __all_sync(0xffffffffu, same && (abits == 0 || abits == ref));
       mbar_wait(&cempty[cb], cph ^ 1u);
       float2* cs = sCoef + cb * BN;
+      float* bs = sBOnly + cb * BN;
 #pragma unroll
-      for (int i = 0; i < RPL; ++i) cs[r0 + lane + 32 * i] = cv[i];
+      for (int i = 0; i < RPL; ++i) {
+        cs[r0 + lane + 32 * i] = cv[i];
+        bs[r0 + lane + 32 * i] = cv[i].y;
+      }
+      if (lane == 0) sUni[cb * 2 + (warp - 2)] = same ? __uint_as_float(ref) : __int_as_float(0x7fc00000);
       __syncwarp();
       if (lane == 0) mbar_arrive(&cfull[cb]);
     }
@@ -799,6 +847,8 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
     const float inv_cq = MODE == 3 ? 1.0f / c_q : 0.f;  // exact: c_q is a (negative) power of two
     uint32_t lv[4] = {0u, 0u, 0u, 0u};
+    bool uni = false;
+    float a_u = 0.f;
     int m = 0;
     int64_t j = 0;
     for (int64_t it = 0; it < total; ++it) {
@@ -811,13 +861,19 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
       if (qidx < p.q) thr = p.thresh[qidx];
       if (MODE == 3 && m == 0) load_live4(iv, n0 + half * (BN / 2), lv);  // once per row tile
-      if (MODE != 3 && m == 0) mbar_wait_d(&cfull[cb], (uint32_t)(j >> 1) & 1u, diag, w_c);
+      if (MODE != 3 && m == 0) {
+        mbar_wait_d(&cfull[cb], (uint32_t)(j >> 1) & 1u, diag, w_c);
+        const float u0 = sUni[cb * 2], u1 = sUni[cb * 2 + 1];  // one word per stager warp (128 rows each)
+        uni = u0 == u0 && u1 == u1 && (u0 == u1 || u0 == 0.f || u1 == 0.f) && !(p.debug & 64);
+        a_u = u0 != 0.f ? u0 : u1;
+      }
       mbar_wait_d(&done[s], u & 1u, diag, w_a);
       tc_fence_after();
       const long long te0 = diag ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
-      epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv);
+      epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv, uni,
+                            smem_u32(sBOnly + cb * BN + half * (BN / 2)), a_u);
       if (diag) w_x += clock64() - te0;
       tc_fence_before();
       __syncwarp();
