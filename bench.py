@@ -299,9 +299,11 @@ class Bench:
     def device_leg(self, steps, warmup, sampler_gpu=None):
         torch, np, idx, q, kk = self.torch, self.np, self.idx, self.q, self.kk
         dev = self.dev
-        # A sharded index takes batches alternately on two streams: the exchange + merge of one batch then overlaps the
-        # next batch's main pass (on one stream a batch's inputs are ordered behind the previous batch's merge).
-        n_str = 2 if self.G > 1 else 1
+        # A sharded index takes batches round-robin on four streams: a batch's inputs are ordered behind the previous
+        # merge on ITS stream only, so the exchange + merge of one batch overlap the main passes of the next three
+        # (on the root GPU a merge gets SMs only between that GPU's own persistent kernels; libgfi cycles through four
+        # gather blocks to match).
+        n_str = 4 if self.G > 1 else 1
         tss = [torch.cuda.Stream(device=dev) for _ in range(n_str)]
         ts = tss[0]
         outs = []

@@ -389,7 +389,9 @@ def test_tensor_path_matches_oracle(case):
     check_batch(idx, metric, rows, queries, k, ctx=str(case))
     st = idx.stats()
     assert st["tensor_queries"] == q, st
-    assert st["fallback_queries"] <= q // 4, st   # certification normally succeeds
+    # certification normally succeeds: measured 0 fallbacks, except 11 of 130 on the uniform-data L2 case (30000 rows
+    # of [0, 1)^128: distances crowd the k-th one more closely than the fp16 bound can separate)
+    assert st["fallback_queries"] <= (16 if (metric, n) == ("euclidean", 30000) else 2), st
 
 
 def test_tensor_path_cosine_coefficient_epilogue_and_tombstones():
@@ -428,7 +430,7 @@ def test_tensor_path_cta_pair_kernel(metric):
     idx.set_option("pair", 1)
     check_batch(idx, metric, rows, queries, k, ctx="pair kernel")
     st = idx.stats()
-    assert st["tensor_queries"] == q and st["fallback_queries"] <= q // 4, st
+    assert st["tensor_queries"] == q and st["fallback_queries"] <= 2, st  # (measured: 0)
 
 
 @pytest.mark.parametrize("metric", ["euclidean", "cosine", "dot"])
