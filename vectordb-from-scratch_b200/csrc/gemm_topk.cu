@@ -105,17 +105,17 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 // in eight) that was a third of the epilogue's time and most of the spread between the eight epilogue warps, which is
 // what the MMA issuer waits for.  Shared by the k-ring kernel and the short-K row-stationary kernel.
 template <int MODE>
-__device__ __noinline__ void epi_survivors(uint64_t* slice, const uint32_t cap, uint32_t* flags, const uint32_t taddr,
+__device__ __noinline__ bool epi_survivors(uint64_t* slice, const uint32_t cap, uint32_t* flags, const uint32_t taddr,
                                            const uint32_t cs_addr, const float thr, const float thr_raw,
                                            const float c_q, const uint32_t slot_base, unsigned short* hc,
                                            const uint32_t bm, const uint32_t lv0, const uint32_t lv1,
-                                           const uint32_t lv2, const uint32_t lv3) {
+                                           const uint32_t lv2, const uint32_t lv3, const uint32_t release_bar) {
   // (plain scalars only: a reference to the kernel's parameter block would force a copy of it into local memory)
   // The eight epilogue warps of a CTA release an accumulator together, so the LATENCY of this section on the one warp
   // that takes it sets the pace of the whole item: group maxima first, then only the 8-column groups that hold a hit.
   uint32_t wm = __reduce_or_sync(0xffffffffu, bm);
   uint32_t cnt = bm ? *hc : 0u;
-  bool nan = false;
+  bool nan = false, released = false;
 #pragma unroll 1
   while (wm) {
     const int blk = __ffs(wm) - 1;
@@ -124,6 +124,14 @@ __device__ __noinline__ void epi_survivors(uint64_t* slice, const uint32_t cap, 
     uint32_t v[32];
     tmem_ld_32x32b_x32(taddr + c0, v);  // warp-collective: every lane takes part, flagged or not
     tmem_ld_wait();
+    if (wm == 0 && release_bar) {
+      // the last flagged block is in registers: this warp is done with the accumulator.  Releasing it HERE keeps
+      // the scan of the block's values and the candidate stores off the path the MMA issuer waits on.
+      tc_fence_before();
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(release_bar) : "memory");
+      released = true;
+    }
     if ((bm >> blk) & 1u) {
       const uint32_t lvw = blk == 0 ? lv0 : (blk == 1 ? lv1 : (blk == 2 ? lv2 : lv3));
       float s[32];
@@ -166,6 +174,7 @@ __device__ __noinline__ void epi_survivors(uint64_t* slice, const uint32_t cap, 
   }
   if (bm) *hc = (unsigned short)min(cnt, 65535u);
   if (nan) atomicOr(flags, kFlagNaN);
+  return released;
 }
 
 // One 32-column block of the hot loop: does any of this thread's 32 scores beat the query's threshold?
@@ -230,23 +239,26 @@ __device__ __forceinline__ uint32_t epi_block_mask(const uint32_t taddr, const u
 
 // `uni`: the row tile's eligible rows share the coefficient a_u (warp-uniform; always false for the k-ring kernel,
 // which stages coefficients per item).  bs_addr: this half's 128 b values as a plain float array (uni only).
+// Returns true when the survivor section has already arrived on `release_bar` (the accumulator stage's "drained"
+// barrier, a shared::cta address; 0: the caller releases the stage itself).
 template <int MODE>
-__device__ __forceinline__ void epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
+__device__ __forceinline__ bool epi_filter_half(const GemmParams& p, const uint32_t taddr, const uint32_t cs_addr,
                                                 const float thr, const float thr_raw, const float c_q, const int qidx,
                                                 const int64_t n0, const int half, const int64_t unit,
                                                 unsigned short* hitcnt, const uint32_t (&lv)[4], const bool uni = false,
-                                                const uint32_t bs_addr = 0, const float a_u = 0.f) {
-  if (p.debug & 4) return;
+                                                const uint32_t bs_addr = 0, const float a_u = 0.f,
+                                                const uint32_t release_bar = 0) {
+  if (p.debug & 4) return false;
   uint32_t bm;
   if (MODE == 0 && uni) bm = epi_block_mask<MODE, true>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
   else bm = epi_block_mask<MODE, false>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
   if (qidx >= p.q) bm = 0;  // padding queries (threshold -inf) never match; NaN accumulators cannot fake a hit either
-  if (!__any_sync(0xffffffffu, bm != 0) || (p.debug & 8)) return;
+  if (!__any_sync(0xffffffffu, bm != 0) || (p.debug & 8)) return false;
   // (qidx < p.q <= kGemmMaxQueries whenever bm != 0; other lanes only take part in the warp-collective loads)
   const int qi = bm ? qidx : 0;
-  epi_survivors<MODE>(p.cand + (size_t)qi * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap, p.cand_cap, p.flags,
-                      taddr, cs_addr, thr, thr_raw, c_q, (uint32_t)(n0 + half * (BN / 2)),
-                      hitcnt + half * kGemmMaxQueries + qi, bm, lv[0], lv[1], lv[2], lv[3]);
+  return epi_survivors<MODE>(p.cand + (size_t)qi * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap, p.cand_cap,
+                             p.flags, taddr, cs_addr, thr, thr_raw, c_q, (uint32_t)(n0 + half * (BN / 2)),
+                             hitcnt + half * kGemmMaxQueries + qi, bm, lv[0], lv[1], lv[2], lv[3], release_bar);
 }
 
 // The live words of the 128 rows [slot0, slot0 + 128) (slot0 a multiple of 128), bits of slots beyond the index cleared
@@ -872,14 +884,15 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       const long long te0 = diag ? clock64() : 0;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
-      epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv, uni,
-                            smem_u32(sBOnly + cb * BN + half * (BN / 2)), a_u);
+      const bool released =
+          epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv, uni,
+                                smem_u32(sBOnly + cb * BN + half * (BN / 2)), a_u, smem_u32(&tempty[as]));
       if (diag) w_x += clock64() - te0;
       tc_fence_before();
       __syncwarp();
       const bool last_m = m == M - 1;
       if (lane == 0) {
-        mbar_arrive(&tempty[as]);
+        if (!released) mbar_arrive(&tempty[as]);
         if (MODE != 3 && last_m) mbar_arrive(&cempty[cb]);
       }
       if (last_m) { m = 0; ++j; } else ++m;
