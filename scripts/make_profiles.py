@@ -60,13 +60,13 @@ if os.path.exists(rec):
     out = []
     for line in open(rec):
         if line.startswith("=== python bench.py") or line.startswith("{") or "passed" in line or line.startswith("smoke ok"):
-            out.append(line.rstrip()[:6000])
+            out.append(line.rstrip())
     open(os.path.join(P, f"{tag}_bench_lines_1gpu.log"), "w").write("\n".join(out) + "\n")
     print("wrote bench lines")
-for name in ("bench_2gpu.log", "bench_8gpu.log"):
-    p = os.path.join(G, name)
+for name, src in (("bench_2gpu.log", "r2d_n2.log"), ("bench_8gpu.log", "r2d_n8.log")):
+    p = os.path.join(G, src if os.path.exists(os.path.join(G, src)) else name)
     if os.path.exists(p):
-        keep = [l for l in open(p) if l.startswith("{")]
+        keep = [l for l in open(p) if l.startswith("{") or l.startswith("=== python") or "passed" in l]
         open(os.path.join(P, f"{tag}_{name}"), "w").writelines(keep)
 lc = os.path.join(G, "launches_bench_c2.csv")
 if os.path.exists(lc):
@@ -102,7 +102,8 @@ def traffic_bytes(rep):
 
 
 traffic = {}
-for wl, rep in (("c2", "prof_gemm_c2.ncu-rep"), ("c3a", "prof_gemm_c3a.ncu-rep"), ("c3a_scan", "prof_scan_c3a.ncu-rep")):
+for wl, rep in (("c2", "prof_gemm_c2.ncu-rep"), ("c3a", "prof_gemm_c3a.ncu-rep"), ("c3a_scan", "prof_scan_c3a.ncu-rep"),
+                ("c5", "prof_gemm_c5.ncu-rep")):
     p = os.path.join(G, rep)
     if os.path.exists(p):
         traffic[wl] = {"bytes_per_launch": traffic_bytes(p), "source": f"profiles/{tag}_ncu_*: dram__bytes_read.sum + dram__bytes_write.sum, one launch"}
@@ -112,19 +113,22 @@ if traffic:
 
 for rep, out in (("prof_gemm_c2.ncu-rep", f"{tag}_ncu_gemm_topk_c2.txt"), ("prof_scan_c3a.ncu-rep", f"{tag}_ncu_scan_topk_c3a.txt"),
                  ("prof_gemm_c3a.ncu-rep", f"{tag}_ncu_gemm_topk_c3a.txt"),
-                 ("prof_gemm_c5.ncu-rep", f"{tag}_ncu_gemm_topk_c5_2Mrows.txt"),
+                 ("prof_gemm_c5.ncu-rep", f"{tag}_ncu_gemm_topk_c5.txt"),
                  ("prof_rerank_c2.ncu-rep", f"{tag}_ncu_rerank_c2.txt")):
     p = os.path.join(G, rep)
     if os.path.exists(p):
         summarise(p, os.path.join(P, out))
 
 # in-kernel cycle / clock diagnostics (scripts/gpu_record.sh)
-for name in ("clock_diag_c2.log", "clock_diag_c2_pair.log", "clock_diag_c5_4Mrows.log"):
+for name in ("clock_diag_c2.log", "clock_diag_c2_pair.log", "clock_diag_c5_4Mrows.log", "clock_diag_c5.log"):
     src = os.path.join(G, name)
     if os.path.exists(src):
-        keep = [l for l in open(src) if l.startswith("{") or ("[gemm_topk]" in l and "ns" in l)]
+        keep = [l for l in open(src) if l.startswith("{") or (("[gemm_topk]" in l or "[gemm_topk_sk]" in l) and "clk" + "" in l + "clk")]
+        keep = [l for l in keep if l.startswith("{") or "[gemm_topk_sk]" in l or ("ns" in l and "cycles" in l)]
         # the seed pass prints too (a few ten thousand cycles); keep the main pass lines only
-        keep = [l for l in keep if l.startswith("{") or int(l.split("cycles")[1].split()[0]) > 500000]
+        keep = [l for l in keep if l.startswith("{") or "[gemm_topk_sk]" in l or int(l.split("cycles")[1].split()[0]) > 500000]
+        if name == "clock_diag_c5.log":
+            keep = keep[-11:]  # one launch: ten roles + the cycle line
         open(os.path.join(P, f"{tag}_{name}"), "w").writelines(
             ["# gemm_debug bits: 32 = print cycles/ns of CTA 0; +4 no epilogue; +7 no loads after the ring fill, no epilogue; "
              "+23 also no MMA issue (barrier handshakes only); +19 no loads, no MMA issue, epilogue ON (epilogue alone).  "
