@@ -8,6 +8,6 @@ run() { echo "=== $*" >> $log; local t0=$(date +%s); timeout ${TMO:-600} "$@" >>
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517"
 TMO=600 run python -m pytest tests/test_gpu_sharded.py -q -m gpu --timeout 300
 TMO=900 run $TR bench.py --gpus $N --steps 20 --warmup 5
-TMO=600 run $TR bench.py --gpus $N --steps 200 --warmup 5 --secondary none --no-cpu-baseline --no-sustained
+[ -z "$SKIP200" ] && TMO=600 run $TR bench.py --gpus $N --steps 200 --warmup 5 --secondary none --no-cpu-baseline --no-sustained
 [ -n "$RANKS_AB" ] && TMO=600 run $TR bench.py --gpus $N --steps 200 --warmup 5 --sharding ranks
 grep -v "^{" $log | grep -v "^\*\*\*\|OMP_NUM\|^$" | tail -40

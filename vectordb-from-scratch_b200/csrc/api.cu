@@ -1721,7 +1721,8 @@ int32_t shard_enqueue(gfi_index* h, SearchCtx* c, const ShardSearch& s) {
   if (s.wait_b) CU_TRY(cudaStreamWaitEvent(st, s.wait_b, 0));
   CU_TRY(c->ctrl.ensure(sizeof(Ctrl)));
   auto finish = [&]() -> int32_t {
-    CU_TRY(cudaMemcpyAsync(s.out_ctrl, c->ctrl.p, sizeof(Ctrl), cudaMemcpyDefault, st));
+    // (a one-warp kernel in the PDL chain: a 64-byte peer copy through the copy engine costs a stream ~15 us)
+    CU_TRY(launch_copy_words(reinterpret_cast<uint32_t*>(s.out_ctrl), c->ctrl.as<uint32_t>(), (int)(sizeof(Ctrl) / 4), st));
     if (s.done) CU_TRY(cudaEventRecord(s.done, st));
     return GFI_OK;
   };
@@ -1737,9 +1738,12 @@ int32_t shard_enqueue(gfi_index* h, SearchCtx* c, const ShardSearch& s) {
   CU_TRY(c->q_in.ensure((size_t)q * dim * 4));
   CU_TRY(c->ks.ensure((size_t)q * 4));
   if (masked) CU_TRY(c->mask.ensure(mask_words * 8 + 8));
-  // cudaMemcpyDefault: pinned host memory or the root GPU's memory alike (unified addressing)
-  CU_TRY(cudaMemcpyAsync(c->q_in.p, s.queries, (size_t)q * dim * 4, cudaMemcpyDefault, st));
-  CU_TRY(cudaMemcpyAsync(c->ks.p, s.ks, (size_t)q * 4, cudaMemcpyDefault, st));
+  // Host inputs (pinned) come in through the copy engine.  Inputs that live on a GPU -- the root's memory, a peer of
+  // every shard -- are read in place by prep_queries over NVLink (it writes the padded fp32 / fp16 copies and the
+  // per-query k locally): no copy-engine operation sits between the kernels of a device-resident search.
+  // (The per-query k -- a few KB in the sharded handle's pinned block or on the root GPU -- is always read in place.)
+  const bool direct = s.on_device;
+  if (!direct) CU_TRY(cudaMemcpyAsync(c->q_in.p, s.queries, (size_t)q * dim * 4, cudaMemcpyDefault, st));
   if (s.mask) CU_TRY(cudaMemcpyAsync(c->mask.p, s.mask, mask_words * 8, cudaMemcpyDefault, st));
   if (s.filter_json) {
     CU_TRY(cudaMemsetAsync(c->mask.p, 0, mask_words * 8 + 8, st));
@@ -1747,8 +1751,9 @@ int32_t shard_enqueue(gfi_index* h, SearchCtx* c, const ShardSearch& s) {
                               c->mask.as<uint64_t>(), st));
     ++h->n_launch;
   }
-  SearchArgs a{c->q_in.as<float>(), q, c->ks.as<uint32_t>(), s.kmax, masked ? c->mask.as<uint64_t>() : nullptr,
-               mask_bits, s.out_ids, s.out_dist, s.out_counts, s.kstride};
+  SearchArgs a{direct ? s.queries : c->q_in.as<float>(), q, c->ks.as<uint32_t>(), s.kmax,
+               masked ? c->mask.as<uint64_t>() : nullptr, mask_bits, s.out_ids, s.out_dist, s.out_counts, s.kstride};
+  a.h_ks_in = s.ks;  // prep_queries copies the per-query k into c->ks
   a.mask_by_slot = s.filter_json != nullptr;
   if (s.mask && s.mask_density >= 0.0) a.mask_popcount = (int64_t)(s.mask_density * (double)h->n_slots);
   a.keep_flags = s.keep_flags;

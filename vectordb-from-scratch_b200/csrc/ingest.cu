@@ -239,6 +239,13 @@ __global__ void fill_u32_kernel(uint32_t* p, uint32_t v, int64_t n) {
     p[i] = v;
 }
 
+// A few words from one device-accessible address to another (a shard's control block to the root GPU over NVLink):
+// a kernel in the PDL chain instead of a copy-engine operation between kernels.
+__global__ void copy_words_kernel(uint32_t* dst, const uint32_t* src, int n) {
+  griddep_wait();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = src[i];
+}
+
 // Compaction / re-ordering: out slot j <- in slot perm[j] (one warp per row).
 __global__ void gather_rows_kernel(const IndexView src, const uint32_t* perm, int64_t n_out, float* x32,
                                    __half* x16, uint64_t* ids, float* norm, float* sumsq, float2* coef) {
@@ -337,6 +344,11 @@ cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st)
   const int blocks = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
   fill_u32_kernel<<<blocks, 256, 0, st>>>(p, v, n);
   return cudaGetLastError();
+}
+
+cudaError_t launch_copy_words(uint32_t* dst, const uint32_t* src, int n, cudaStream_t st) {
+  if (n <= 0) return cudaSuccess;
+  return launch_pdl(copy_words_kernel, dim3(1), dim3(32), 0, st, dst, src, n);
 }
 
 cudaError_t launch_gather_rows(const IndexView& src, const uint32_t* perm, int64_t n_out, float* x32,

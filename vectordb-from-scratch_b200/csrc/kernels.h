@@ -238,6 +238,7 @@ cudaError_t launch_eval_filter(const FilterProgram& prog, const uint32_t* const*
 
 // misc
 cudaError_t launch_fill_u32(uint32_t* p, uint32_t v, int64_t n, cudaStream_t st);
+cudaError_t launch_copy_words(uint32_t* dst, const uint32_t* src, int n, cudaStream_t st);
 cudaError_t launch_gather_rows(const IndexView& src, const uint32_t* perm, int64_t n_out, float* x32,
                                __half* x16, uint64_t* ids, float* norm, float* sumsq, float2* coef,
                                cudaStream_t st);
