@@ -137,8 +137,8 @@ int32_t gfi_compact(gfi_index *h);
  *              own post-filter, src/storage.rs:249-290, needs no mask: the caller over-fetches).
  *   out_ids / out_dist : q x kstride, out_counts[i] = min(ks[i], eligible rows)
  * The first failing query fails the batch (collect::<Result<_>>(), storage.rs:306-309).
- * Any k is accepted without a mask (k beyond the kernels' list capacity of 1016 is served in exact passes);
- * with a mask k is limited to 1016.  Thread-safe and re-entrant; calls that arrive while another plain search
+ * Any k is accepted, with or without a mask (k beyond the kernels' list capacity of 1016 is served in exact
+ * passes over the rows not returned yet).  Thread-safe and re-entrant; calls that arrive while another plain search
  * (no mask, q <= 256) is running are combined into one batched search (group commit, option "coalesce"), each
  * caller receiving exactly the outcome -- results or error -- of its own call.
  */

@@ -996,7 +996,16 @@ def test_k_above_the_kernels_list_capacity(metric):
     eids, ed = oracle.search_batch(metric, rows[live], queries[:1], 9000, ids=ids[live])[0]
     assert c2[0] == n - 1
     assert_topk_matches(g2[0, :c2[0]], d2[0, :c2[0]], eids, ed, ctx="k > n")
-    # with a caller mask the capacity still applies, loudly
+    # with a caller mask (by internal id) the passes start from the caller's eligible rows
+    elig = (np.arange(n) % 3 != 1) & live
+    by_id = np.zeros(int(ids[-1]) + 1, dtype=bool)
+    by_id[ids[elig]] = True
+    g3, d3, c3 = idx.search_arrays(queries[:2], np.array([2200, 12], dtype=np.uint32), mask=by_id)
+    exp = oracle.search_batch(metric, rows[elig], queries[:2], [2200, 12], ids=ids[elig])
+    for i, (eids, ed) in enumerate(exp):
+        assert c3[i] == len(eids)
+        assert_topk_matches(g3[i, :c3[i]], d3[i, :c3[i]], eids, ed, ctx=f"big k + mask q{i}")
+    # a filter handed down as JSON still has the capacity, loudly (the reference's caller over-fetches and post-filters)
     with pytest.raises(gfi.IndexError_) as e:
-        idx.search_arrays(queries[:1], 1500, mask=np.ones(int(ids[-1]) + 1, dtype=bool))
+        idx.search_filtered(queries[:1], 1500, '{"op": "exists", "field": "color"}')
     assert "k too large" in str(e.value)

@@ -162,3 +162,34 @@ def test_short_k_row_stationary_kernel_matches_oracle_and_the_k_ring_kernel(case
     for i, (eids, ed) in enumerate(exp):
         assert cnt[i] == len(eids)
         assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"{case} q{i}")
+
+
+def test_short_k_uniform_coefficient_loop_selects_the_same_candidates():
+    """Row tiles whose eligible rows share their fp16 scale take a hot loop that reads b alone (gemm_topk.cu,
+    epi_block_hit<.., UNI>); gemm_debug bit 6 forces the (a, b)-pair loop.  Same scores bit for bit, hence the same
+    candidates, fallbacks and answers -- with tombstones inside uniform tiles, a tile mixing two magnitudes, and a
+    partial last tile."""
+    n, d, q, k = 41_000, 128, 512, 10
+    rows = oracle.gen_rows(910, 0, n, d, 0)
+    rows[20_000:20_300] *= np.float32(8.0)      # two magnitudes inside row tiles 78 and 79: the general loop there
+    idx = gfi.GpuFlatIndex(DM.Euclidean)
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    idx.set_option("tensor_min_rows", 256)
+    for i in range(3, n, 53):
+        idx.remove(i)
+    elig = np.ones(n, dtype=bool)
+    elig[3::53] = False
+    queries = oracle.gen_rows(911, 0, q, d, 0)
+    res = {}
+    for dbg in (0, 64):
+        idx.set_option("gemm_debug", dbg)
+        s0 = idx.stats()
+        res[dbg] = idx.search_arrays(queries, k)
+        s1 = idx.stats()
+        res[dbg] += (s1["fallback_queries"] - s0["fallback_queries"],)
+    idx.set_option("gemm_debug", 0)
+    for a, b in zip(res[0], res[64]):
+        assert np.array_equal(a, b)
+    exp = oracle.search_batch("euclidean", rows, queries[:32], k, eligible=elig, threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert_topk_matches(res[0][0][i, :res[0][2][i]], res[0][1][i, :res[0][2][i]], eids, ed, ctx=f"uniform loop q{i}")

@@ -181,6 +181,8 @@ def test_sharded_k_above_the_kernels_list_capacity(layout):
     idx.add_batch(np.arange(n, dtype=np.uint64), rows)
     queries = oracle.gen_rows(96, 0, 2, d, 0)
     check(idx, "euclidean", rows, queries, np.array([k, 20], dtype=np.uint32), ctx="big k")
+    elig = np.arange(n) % 4 != 2   # caller mask by internal id: every shard's passes start from its eligible rows
+    check(idx, "euclidean", rows, queries, np.array([k, 20], dtype=np.uint32), eligible=elig, mask=elig, ctx="big k + mask")
 
 
 @pytest.mark.parametrize("layout", layouts())

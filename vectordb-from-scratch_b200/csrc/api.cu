@@ -819,6 +819,7 @@ int32_t enqueue_search(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStre
     s.q = std::min(lim, a.q - q0);
     s.d_queries = a.d_queries + q0 * h->dim;
     s.d_ks = a.d_ks + q0;
+    if (a.h_ks_in) s.h_ks_in = a.h_ks_in + q0;
     s.d_out_ids = a.d_out_ids + q0 * a.kstride;
     s.d_out_dist = a.d_out_dist + q0 * a.kstride;
     s.d_out_counts = a.d_out_counts + q0;
@@ -1556,7 +1557,7 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
       q_src = c->h_q.p;
     }
     CU_TRY(cudaMemcpyAsync(c->q_in.p, q_src, (size_t)q * dim * 4, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(c->ks.p, c->h_ks.p, (size_t)q * 4, cudaMemcpyHostToDevice, st));
+    // (the per-query k is read by prep_queries straight from the pinned staging block: one copy-engine op fewer)
   }
   if (mask) CU_TRY(cudaMemcpyAsync(c->mask.p, mask, mask_words * 8, cudaMemcpyHostToDevice, st));
   if (filter_json) {
@@ -1579,9 +1580,9 @@ static int32_t search_impl(gfi_index* h, const float* queries, int64_t q, int64_
     for (size_t w = 0; w < full; w += 64, ++seen) pc += __builtin_popcountll(mask[w]);
     a.mask_popcount = seen ? (int64_t)((double)pc / (double)(seen * 64) * (double)mask_bits) : 0;
   }
+  a.h_ks_in = c->h_ks.as<uint32_t>();
   if (zero_copy) {
     char* hb0 = c->h_out.as<char>();
-    a.h_ks_in = c->h_ks.as<uint32_t>();
     a.h_ctrl = reinterpret_cast<uint32_t*>(hb0);
     a.h_out_counts = reinterpret_cast<uint32_t*>(hb0 + off_cnt);
     a.h_out_dist = reinterpret_cast<float*>(hb0 + off_dist);
@@ -1775,7 +1776,10 @@ extern "C" {
 // is the exact ascending top-k.  ceil(k / kMaxListK) scans per such query -- the rare path, kept simple.
 constexpr uint32_t kMaxListK = 1016;
 static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                            uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
+                            const uint64_t* cmask, int64_t cmask_bits, uint64_t* out_ids, float* out_dist,
+                            uint32_t* out_counts, int64_t kstride) {
+  // cmask: the caller's eligibility mask by internal id (or null).  The passes work on a SLOT-indexed mask, so the
+  // caller's bits are carried over slot by slot through the id runs before the first pass.
   if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
   std::vector<int64_t> small, big;
   for (int64_t i = 0; i < q; ++i) {
@@ -1794,8 +1798,8 @@ static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64
       memcpy(qs.data() + j * dim, queries + small[j] * dim, (size_t)dim * 4);
       k2[j] = ks[small[j]];
     }
-    rc = search_impl(h, qs.data(), (int64_t)small.size(), dim, k2.data(), nullptr, 0, nullptr, ids.data(), dist.data(),
-                     cnt.data(), km);
+    rc = search_impl(h, qs.data(), (int64_t)small.size(), dim, k2.data(), cmask, cmask_bits, nullptr, ids.data(),
+                     dist.data(), cnt.data(), km);
     if (rc != GFI_OK) return rc;
     for (size_t j = 0; j < small.size(); ++j) {
       const int64_t i = small[j];
@@ -1815,7 +1819,18 @@ static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64
         std::shared_lock<std::shared_mutex> g(h->mu);
         n_slots = h->n_slots;
       }
-      std::vector<uint64_t> mask((size_t)(n_slots + 63) / 64 + 1, ~0ull);
+      std::vector<uint64_t> mask((size_t)(n_slots + 63) / 64 + 1, cmask ? 0ull : ~0ull);
+      if (cmask) {
+        std::shared_lock<std::shared_mutex> g(h->mu);
+        for (const auto& kv : h->runs) {
+          uint64_t id = kv.first;
+          for (uint32_t j = 0; j < kv.second.n; ++j, ++id) {
+            const uint32_t sl = kv.second.slot0 + j;
+            if ((int64_t)sl < n_slots && id < (uint64_t)cmask_bits && ((cmask[id >> 6] >> (id & 63)) & 1ull))
+              mask[sl >> 6] |= 1ull << (sl & 63);
+          }
+        }
+      }
       uint32_t got = 0;
       bool stale = false;
       while (got < ks[i]) {
@@ -1903,12 +1918,12 @@ static void run_coalesced(gfi_index* h, std::vector<gfi_index::CoReq*>& batch) {
 int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
                    const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
                    uint32_t* out_counts, int64_t kstride) {
-  if (h && !mask && q > 0 && ks) {
+  if (h && q > 0 && ks) {
     bool bigk = false;
     for (int64_t i = 0; i < q; ++i) bigk = bigk || ks[i] > kMaxListK;
     if (bigk)
-      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride)
-                       : search_big_k(h, queries, q, dim, ks, out_ids, out_dist, out_counts, kstride);
+      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, mask, mask_bits, out_ids, out_dist, out_counts, kstride)
+                       : search_big_k(h, queries, q, dim, ks, mask, mask_bits, out_ids, out_dist, out_counts, kstride);
   }
   // masked searches, large batches and malformed calls take the direct path
   // (indexes below 32 MB are launch-latency-bound: independent calls on separate streams overlap on the GPU and

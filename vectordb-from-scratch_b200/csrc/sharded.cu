@@ -746,7 +746,8 @@ static int32_t per_shard_host_search(gfi_index* H, const float* queries, int64_t
 }
 
 int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                             uint64_t* out_ids, float* out_dist, uint32_t* out_counts, int64_t kstride) {
+                             const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
+                             uint32_t* out_counts, int64_t kstride) {
   ShardSet* S = H->shards;
   if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
   for (int64_t i = 0; i < q; ++i)
@@ -756,7 +757,7 @@ int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int6
   std::shared_lock<std::shared_mutex> lk(H->mu);
   ++S->n_search;
   S->n_queries += q;
-  return per_shard_host_search(H, queries, q, dim, ks, nullptr, 0, nullptr, out_ids, out_dist, out_counts, kstride);
+  return per_shard_host_search(H, queries, q, dim, ks, mask, mask_bits, nullptr, out_ids, out_dist, out_counts, kstride);
 }
 
 namespace {
