@@ -776,6 +776,47 @@ def test_bulk_ingest_from_reference_flat_file(tmp_path):
         other.add_from_file(path)
 
 
+def test_bulk_ingest_many_chunks_padded_rows_appends_overwrites_and_short_files(tmp_path):
+    """The pipelined bulk path of gfi_add_from_file (two pinned buffers, parallel preads, one H2D + row_stats per
+    64 MB chunk): a dimension that is not a multiple of 4 (rows are padded on the device: pitched copies), several
+    chunks, a second file appended behind the first, a file whose ids overlap stored ones (FlatIndex::add overwrites,
+    src/flat_index.rs:38-41: the staged path), and a file shorter than its header says."""
+    import struct
+    d, n1, n2 = 50, 700_000, 1000
+    rows1 = oracle.gen_rows(97, 0, n1, d, 1)
+    rows2 = oracle.gen_rows(98, 0, n2, d, 1)
+
+    def write(name, rows, count=None):
+        path = tmp_path / name
+        with open(path, "wb") as f:
+            f.write(struct.pack("<II", d, rows.shape[0] if count is None else count))
+            f.write(rows.tobytes())
+        return path
+
+    idx = gfi.GpuFlatIndex(DM.Euclidean)
+    assert idx.add_from_file(write("a.bin", rows1), first_id=0) == n1      # 140 MB: three chunks
+    assert idx.add_from_file(write("b.bin", rows2), first_id=n1 + 10) == n2  # appended (ids stay ascending)
+    assert idx.len() == n1 + n2 and idx.dim() == d
+    for i in (0, 335_543, 335_544, 671_087, 671_088, n1 - 1):                                  # around the chunk boundaries
+        assert np.array_equal(idx.get_vector(i), rows1[i])
+    assert np.array_equal(idx.get_vector(n1 + 10 + 999), rows2[999])
+    ids = np.concatenate([np.arange(n1, dtype=np.uint64), np.arange(n1 + 10, n1 + 10 + n2, dtype=np.uint64)])
+    allrows = np.concatenate([rows1, rows2])
+    q = oracle.gen_rows(99, 0, 4, d, 1)
+    check_batch(idx, "euclidean", allrows, q, 10, ids=ids, ctx="bulk chunks")
+    # overlapping ids: rows 5..14 are replaced by the first ten rows of the second file
+    assert idx.add_from_file(write("c.bin", rows2[:10]), first_id=5) == 10
+    assert idx.len() == n1 + n2
+    allrows[5:15] = rows2[:10]
+    assert np.array_equal(idx.get_vector(7), rows2[2])
+    check_batch(idx, "euclidean", allrows, np.concatenate([q, rows2[3:4]]), 10, ids=ids, ctx="bulk overwrite")
+    # a truncated file fails loudly and adds nothing
+    with pytest.raises(gfi.IndexError_) as e:
+        idx.add_from_file(write("short.bin", rows2[:100], count=5000), first_id=10_000_000)
+    assert "shorter" in str(e.value) and idx.len() == n1 + n2
+    check_batch(idx, "euclidean", allrows, q[:1], 10, ids=ids, ctx="after a failed load")
+
+
 # ---------------------------------------------------------------- more full-size checks (BASELINE.json configs)
 def test_full_size_c5_shard_l2_batch4096_against_oracle_subset():
     """C5 shard: 12.5M x 128 Euclidean, batch 4096, k = 10 (one GPU's share of the 100M index).  The
