@@ -859,43 +859,41 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     const float c_q = MODE == 3 ? -pow2_scale_inv(*p.qmaxabs) * 6.103515625e-05f : 0.f;
     const float inv_cq = MODE == 3 ? 1.0f / c_q : 0.f;  // exact: c_q is a (negative) power of two
     uint32_t lv[4] = {0u, 0u, 0u, 0u};
-    bool uni = false;
-    float a_u = 0.f;
-    int m = 0;
-    int64_t j = 0;
-    for (int64_t it = 0; it < total; ++it) {
-      const int s = (int)(it & (kNA - 1));
-      const uint32_t u = (uint32_t)(it / kNA);
-      const uint32_t as = (uint32_t)it & 1u;
-      const uint32_t cb = (uint32_t)j & 1u;
-      const int64_t n0 = (unit + j * nunits) * BN;
-      const int qidx = m * BM + mrow;
-      float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
-      if (qidx < p.q) thr = p.thresh[qidx];
-      if (MODE == 3 && m == 0) load_live4(iv, n0 + half * (BN / 2), lv);  // once per row tile
-      if (MODE != 3 && m == 0) {
-        mbar_wait_d(&cfull[cb], (uint32_t)(j >> 1) & 1u, diag, w_c);
+    const uint32_t lane_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * (BN / 2);
+    uint32_t it = 0;  // item counter of this CTA (< 2^31: launch_gemm_topk checks the item count)
+    // (row tile, then query tile: everything that depends on the row tile only is set up once per 32 items)
+    for (uint32_t j = 0; j < (uint32_t)ntiles; ++j) {
+      const uint32_t cb = j & 1u;
+      const int64_t n0 = (unit + (int64_t)j * nunits) * BN;
+      const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
+      const uint32_t bs_addr = smem_u32(sBOnly + cb * BN + half * (BN / 2));
+      bool uni = false;
+      float a_u = 0.f;
+      if (MODE == 3) load_live4(iv, n0 + half * (BN / 2), lv);
+      if (MODE != 3) {
+        mbar_wait_d(&cfull[cb], (j >> 1) & 1u, diag, w_c);
         const float u0 = sUni[cb * 2], u1 = sUni[cb * 2 + 1];  // one word per stager warp (128 rows each)
         uni = u0 == u0 && u1 == u1 && (u0 == u1 || u0 == 0.f || u1 == 0.f) && !(p.debug & 64);
         a_u = u0 != 0.f ? u0 : u1;
       }
-      mbar_wait_d(&done[s], u & 1u, diag, w_a);
-      tc_fence_after();
-      const long long te0 = diag ? clock64() : 0;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
-      const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
-      const bool released =
-          epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv, uni,
-                                smem_u32(sBOnly + cb * BN + half * (BN / 2)), a_u, smem_u32(&tempty[as]));
-      if (diag) w_x += clock64() - te0;
-      tc_fence_before();
-      __syncwarp();
-      const bool last_m = m == M - 1;
-      if (lane == 0) {
-        if (!released) mbar_arrive(&tempty[as]);
-        if (MODE != 3 && last_m) mbar_arrive(&cempty[cb]);
+      int qidx = mrow;
+#pragma unroll 1
+      for (int m = 0; m < M; ++m, ++it, qidx += BM) {
+        const uint32_t s = it & (uint32_t)(kNA - 1), as = it & 1u;
+        float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
+        if (qidx < p.q) thr = p.thresh[qidx];
+        mbar_wait_d(&done[s], (it / kNA) & 1u, diag, w_a);
+        tc_fence_after();
+        const long long te0 = diag ? clock64() : 0;
+        const bool released =
+            epi_filter_half<MODE>(p, lane_addr + as * BN, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt,
+                                  lv, uni, bs_addr, a_u, smem_u32(&tempty[as]));
+        if (diag) w_x += clock64() - te0;
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0 && !released) mbar_arrive(&tempty[as]);
       }
-      if (last_m) { m = 0; ++j; } else ++m;
+      if (MODE != 3 && lane == 0) mbar_arrive(&cempty[cb]);  // (after the tile's last __syncwarp)
     }
   }
 
