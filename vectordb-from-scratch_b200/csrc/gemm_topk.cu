@@ -247,13 +247,14 @@ __device__ __forceinline__ bool epi_filter_half(const GemmParams& p, const uint3
                                                 const int64_t n0, const int half, const int64_t unit,
                                                 unsigned short* hitcnt, const uint32_t (&lv)[4], const bool uni = false,
                                                 const uint32_t bs_addr = 0, const float a_u = 0.f,
-                                                const uint32_t release_bar = 0) {
-  if (p.debug & 4) return false;
+                                                const uint32_t release_bar = 0, const int dbg = -1) {
+  const int debug = dbg < 0 ? p.debug : dbg;  // (the short-K kernel's production instance passes 0: no per-item loads)
+  if (debug & 4) return false;
   uint32_t bm;
   if (MODE == 0 && uni) bm = epi_block_mask<MODE, true>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
   else bm = epi_block_mask<MODE, false>(taddr, cs_addr, bs_addr, a_u, thr, thr_raw);
   if (qidx >= p.q) bm = 0;  // padding queries (threshold -inf) never match; NaN accumulators cannot fake a hit either
-  if (!__any_sync(0xffffffffu, bm != 0) || (p.debug & 8)) return false;
+  if (!__any_sync(0xffffffffu, bm != 0) || (debug & 8)) return false;
   // (qidx < p.q <= kGemmMaxQueries whenever bm != 0; other lanes only take part in the warp-collective loads)
   const int qi = bm ? qidx : 0;
   return epi_survivors<MODE>(p.cand + (size_t)qi * p.cand_stride + (size_t)(unit * 2 + half) * p.cand_cap, p.cand_cap,
@@ -658,7 +659,7 @@ __device__ __forceinline__ void mbar_wait_d(uint64_t* bar, uint32_t parity, bool
   acc += clock64() - t0;
 }
 
-template <int MODE>
+template <int MODE, bool DIAG>
 __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const CUtensorMap& tmq, const GemmParams& p) {
   static_assert(MODE == 0 || MODE == 3, "main-pass modes only");
   constexpr int kNA = sk::kNA;
@@ -689,7 +690,9 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
   // this CTA's row tiles: unit, unit + nunits, ...
   const int64_t ntiles = unit < p.num_n_tiles ? (p.num_n_tiles - unit + nunits - 1) / nunits : 0;
   const int64_t total = ntiles * M;                 // items of this CTA
-  const bool diag = (p.debug & 32) && blockIdx.x == 0;
+  // (in-kernel timers live in their own instantiation: even predicated off they cost the item loops a branch or two)
+  const bool diag = DIAG && (p.debug & 32) && blockIdx.x == 0;
+  const int debug = DIAG ? p.debug : 0;  // timing-experiment switches exist in the DIAG instantiation only
   long long w_a = 0, w_b = 0, w_c = 0, w_x = 0;     // per-role wait cycles; w_x: MMA issue / epilogue filter cycles (diag)
 
   if (tid == 0) {
@@ -731,7 +734,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     auto load_b = [&](int64_t j) {
       if (lane == 0) {
         const int n_row0 = (int)((unit + j * nunits) * BN);
-        if (p.debug & 2) { mbar_arrive(bfull); return; }
+        if (debug & 2) { mbar_arrive(bfull); return; }
         mbar_arrive_expect_tx(bfull, (uint32_t)KS * sk::kBChunkBytes);
         for (int kc = 0; kc < KS; ++kc) tma_load_2d(sB + (size_t)kc * sk::kBChunkBytes, &tmx, kc * BK, n_row0, bfull);
       }
@@ -744,7 +747,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       const uint32_t u = (uint32_t)(it / kNA);
       if (it >= kNA) mbar_wait_d(&done[s], (u - 1u) & 1u, diag, w_a);
       if (lane == 0) {
-        if ((p.debug & 1) && it >= kNA) {
+        if ((debug & 1) && it >= kNA) {
           mbar_arrive(&afull[s]);
         } else {
           mbar_arrive_expect_tx(&afull[s], (uint32_t)KS * kABytes);
@@ -785,7 +788,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       // (Issuing the item as two N = 128 halves, each released by its own four epilogue warps, was measured in round
       // 2: 13.4 -> 14.4 ms on C5 -- the N = 128 MMAs and the second wait in the middle of the item cost more than the
       // decoupling of the halves gained.)
-      if (!(p.debug & 16)) {
+      if (!(debug & 16)) {
 #pragma unroll 1
         for (int k = 0; k < nk16; ++k) {
           // chunk k >> 2 (16 / 32 KB further), K step k & 3 (32 bytes further)
@@ -873,7 +876,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       if (MODE != 3) {
         mbar_wait_d(&cfull[cb], (j >> 1) & 1u, diag, w_c);
         const float u0 = sUni[cb * 2], u1 = sUni[cb * 2 + 1];  // one word per stager warp (128 rows each)
-        uni = u0 == u0 && u1 == u1 && (u0 == u1 || u0 == 0.f || u1 == 0.f) && !(p.debug & 64);
+        uni = u0 == u0 && u1 == u1 && (u0 == u1 || u0 == 0.f || u1 == 0.f) && !(debug & 64);
         a_u = u0 != 0.f ? u0 : u1;
       }
       int qidx = mrow;
@@ -887,7 +890,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
         const long long te0 = diag ? clock64() : 0;
         const bool released =
             epi_filter_half<MODE>(p, lane_addr + as * BN, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt,
-                                  lv, uni, bs_addr, a_u, smem_u32(&tempty[as]));
+                                  lv, uni, bs_addr, a_u, smem_u32(&tempty[as]), debug);
         if (diag) w_x += clock64() - te0;
         tc_fence_before();
         __syncwarp();
@@ -919,13 +922,13 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
   }
 }
 
-template <int MODE>
+template <int MODE, bool DIAG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_sk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                     const GemmParams p) {
   griddep_wait();
   if (p.skip && *p.skip) return;
-  gemm_topk_sk_body<MODE>(tmx, tmq, p);
+  gemm_topk_sk_body<MODE, DIAG>(tmx, tmq, p);
 }
 
 // CTA-pair instance: clusters of two CTAs (the two SMs of a TPC), tcgen05.mma.cta_group::2.
@@ -1067,8 +1070,11 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk::kSmemBytes);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sk::kSmemBytes);
+    const int c = (int)sk::kSmemBytes;
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
     if (e != cudaSuccess) return e;
     attr_set[dev & 15] = true;
   }
@@ -1078,8 +1084,12 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   const dim3 g(grid), b(kGemmThreads);
   if (p.short_k) {
     if (pair || p.iv.dpad16 > 2 * BK || (p.seed_mode != 0 && p.seed_mode != 3)) return cudaErrorInvalidValue;
-    if (p.seed_mode == 0) return launch_pdl(gemm_topk_sk_kernel<0>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
-    return launch_pdl(gemm_topk_sk_kernel<3>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
+    const bool diag = p.debug != 0;  // any timing-experiment switch: the instrumented instantiation
+    if (p.seed_mode == 0)
+      return diag ? launch_pdl(gemm_topk_sk_kernel<0, true>, g, b, sk::kSmemBytes, st, *tx, *tq, p)
+                  : launch_pdl(gemm_topk_sk_kernel<0, false>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
+    return diag ? launch_pdl(gemm_topk_sk_kernel<3, true>, g, b, sk::kSmemBytes, st, *tx, *tq, p)
+                : launch_pdl(gemm_topk_sk_kernel<3, false>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
   }
   if (pair && p.seed_mode == 0) return launch_pdl(gemm_topk_pair_kernel<0>, g, b, sm2, st, *tx, *tq, p);
   if (pair) return launch_pdl(gemm_topk_pair_kernel<3>, g, b, sm2, st, *tx, *tq, p);
