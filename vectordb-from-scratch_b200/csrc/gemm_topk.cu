@@ -296,8 +296,9 @@ __device__ __forceinline__ void item_tiles(const GemmParams& p, int64_t w, uint3
 // 2: debug dump of all scores, 3: main pass with the raw epilogue (cosine, no mask).
 // One instance per mode keeps the hot instance's code small: the epilogue is sensitive to instruction-cache
 // misses (a 4x larger unrolled epilogue ran 3x slower).
-template <int MODE, int CG>
+template <int MODE, int CG, bool DIAG>
 __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUtensorMap& tmq, const GemmParams& p) {
+  const int debug = DIAG ? p.debug : 0;  // timing-experiment switches exist in the DIAG instantiation only
   using G = Geo<CG>;
   constexpr int kStages = G::kStages;
   constexpr int kBBytes = G::kBBytes;
@@ -358,7 +359,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   long long dbg_c0 = 0, dbg_t0 = 0;
-  if ((p.debug & 32) && tid == 0 && blockIdx.x == 0) {
+  if ((debug & 32) && tid == 0 && blockIdx.x == 0) {
     dbg_c0 = clock64();
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(dbg_t0));
   }
@@ -377,10 +378,10 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
       for (int kb = 0; kb < num_kb; ++kb, ++it) {
         mbar_wait(&empty[s], ph ^ 1u);
         if (lane == 0) {
-          // p.debug (timing experiments only, results invalid): bit0 / bit1 stop re-loading A / B once the
+          // debug (timing experiments only, results invalid): bit0 / bit1 stop re-loading A / B once the
           // ring has been filled once, to separate the load path from the MMA and epilogue cost.
-          const bool ldA = !((p.debug & 1) && it >= (uint32_t)kStages);
-          const bool ldB = !((p.debug & 2) && it >= (uint32_t)kStages);
+          const bool ldA = !((debug & 1) && it >= (uint32_t)kStages);
+          const bool ldB = !((debug & 2) && it >= (uint32_t)kStages);
           const uint32_t bytes = (ldA ? kABytes : 0) + (ldB ? kBBytes : 0);
           if (CG == 2) {
             if (rank == 0) {
@@ -422,7 +423,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
         tc_fence_after();
         const uint32_t a_lo = a_lo_base + (uint32_t)s * (kABytes >> 4);
         const uint32_t b_lo = b_lo_base + (uint32_t)s * (kBBytes >> 4);
-        if (!(p.debug & 16)) {  // bit4 (timing experiments): barrier handshakes only, no MMA
+        if (!(debug & 16)) {  // bit4 (timing experiments): barrier handshakes only, no MMA
           if (CG == 2) {
             umma_f16_elect_pair(d_tmem, a_lo, b_lo, desc_hi, kIdesc, kb != 0 ? 1u : 0u);
             umma_f16_elect_pair(d_tmem, a_lo + 2, b_lo + 2, desc_hi, kIdesc, 1u);
@@ -532,11 +533,11 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + as * BN + half * (BN / 2);
       const uint32_t cs_addr = smem_u32(sCoef + as * BN + half * (BN / 2));
       if (MODE == 0 || MODE == 3) {
-        epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv);
+        epi_filter_half<MODE>(p, taddr, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt, lv, false, 0, 0.f, 0, debug);
       } else {
         // seed pass / debug dump: one 32-column block at a time
 #pragma unroll 1
-        for (int c0 = 0; c0 < ((p.debug & 4) ? 0 : BN / 2); c0 += 32) {
+        for (int c0 = 0; c0 < ((debug & 4) ? 0 : BN / 2); c0 += 32) {
           uint32_t r[32];
           tmem_ld_32x32b_x32(taddr + c0, r);
           float4 cf[16];
@@ -599,7 +600,7 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
         p.slice_cnt[(size_t)(unit * 2 + hf) * p.q + qi] = hitcnt[hf * kGemmMaxQueries + qi];
     }
   }
-  if ((p.debug & 32) && tid == 0 && blockIdx.x == 0) {
+  if ((debug & 32) && tid == 0 && blockIdx.x == 0) {
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
     const long long c1 = clock64();
@@ -612,13 +613,13 @@ __device__ __forceinline__ void gemm_topk_body(const CUtensorMap& tmx, const CUt
   }
 }
 
-template <int MODE>
+template <int MODE, bool DIAG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_topk_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmq,
                  const GemmParams p) {
   griddep_wait();
   if (p.skip && *p.skip) return;  // device-side route: the scan answers this batch
-  gemm_topk_body<MODE, 1>(tmx, tmq, p);
+  gemm_topk_body<MODE, 1, DIAG>(tmx, tmq, p);
 }
 
 // =====================================================================================================
@@ -938,7 +939,7 @@ gemm_topk_pair_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_cons
                       const GemmParams p) {
   griddep_wait();
   if (p.skip && *p.skip) return;
-  gemm_topk_body<MODE, 2>(tmx, tmq, p);
+  gemm_topk_body<MODE, 2, true>(tmx, tmq, p);
 }
 
 // One warp per query: the rank-th smallest of the query's seed scores becomes its threshold.
@@ -1064,10 +1065,13 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   cudaGetDevice(&dev);
   if (!attr_set[dev & 15]) {  // once per device: the driver call is not free
     const int a = (int)Geo<1>::kSmemBytes, b = (int)Geo<2>::kSmemBytes;
-    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    cudaError_t e = cudaFuncSetAttribute(gemm_topk_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_pair_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, b);
     const int c = (int)sk::kSmemBytes;
@@ -1093,10 +1097,17 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   }
   if (pair && p.seed_mode == 0) return launch_pdl(gemm_topk_pair_kernel<0>, g, b, sm2, st, *tx, *tq, p);
   if (pair) return launch_pdl(gemm_topk_pair_kernel<3>, g, b, sm2, st, *tx, *tq, p);
-  if (p.seed_mode == 0) return launch_pdl(gemm_topk_kernel<0>, g, b, sm1, st, *tx, *tq, p);
-  if (p.seed_mode == 1) return launch_pdl(gemm_topk_kernel<1>, g, b, sm1, st, *tx, *tq, p);
-  if (p.seed_mode == 3) return launch_pdl(gemm_topk_kernel<3>, g, b, sm1, st, *tx, *tq, p);
-  return launch_pdl(gemm_topk_kernel<2>, g, b, sm1, st, *tx, *tq, p);
+  const bool diag = p.debug != 0;  // any timing-experiment switch: the instrumented instantiation
+  if (p.seed_mode == 0)
+    return diag ? launch_pdl(gemm_topk_kernel<0, true>, g, b, sm1, st, *tx, *tq, p)
+                : launch_pdl(gemm_topk_kernel<0, false>, g, b, sm1, st, *tx, *tq, p);
+  if (p.seed_mode == 1)
+    return diag ? launch_pdl(gemm_topk_kernel<1, true>, g, b, sm1, st, *tx, *tq, p)
+                : launch_pdl(gemm_topk_kernel<1, false>, g, b, sm1, st, *tx, *tq, p);
+  if (p.seed_mode == 3)
+    return diag ? launch_pdl(gemm_topk_kernel<3, true>, g, b, sm1, st, *tx, *tq, p)
+                : launch_pdl(gemm_topk_kernel<3, false>, g, b, sm1, st, *tx, *tq, p);
+  return launch_pdl(gemm_topk_kernel<2, false>, g, b, sm1, st, *tx, *tq, p);
 }
 
 cudaError_t launch_seed_finalize(const SeedFinalizeParams& p, cudaStream_t st) {
