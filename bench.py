@@ -524,6 +524,9 @@ class Bench:
             out["exchange"] = {"kind": "peer stores from each shard's finalize kernel into the root GPU's gather block "
                                        "over NVLink + merge kernel on the root (no collective call)",
                                "merge_ms": (st1["merge_ns"] - st0["merge_ns"]) / max(mc, 1) / 1e6, "merges": int(mc),
+                               "merge_ms_is": "CUDA-event time on the root GPU's stream from the last shard's arrival to the "
+                                              "end of the merge kernel: includes waiting for SMs next to the root shard's "
+                                              "own persistent kernels (the kernel itself runs ~15 us)",
                                "bytes_per_shard_per_step": int(q * self.kk * 12 + q * 4),
                                "kernel_ms_per_shard": [round(x, 4) for x in self.shard_kernel_ms]}
         if clocks is not None:
