@@ -76,8 +76,9 @@ int32_t gfi_destroy(gfi_index *h);
  *     single-GPU pipeline on its own GPU, and each shard's finalize kernel stores its k candidates straight into
  *     the root GPU's gather block over NVLink (peer stores: no collective, no staging copy); the root merges the
  *     per-shard lists by (distance, id) with one kernel and returns one result block;
- *   - gfi_search_device takes queries/results in the ROOT GPU's memory and double-buffers the gather block, so the
- *     exchange + merge of one batch overlaps the next batch's main pass;
+ *   - gfi_search_device takes queries/results in the ROOT GPU's memory (the shards read them in place over NVLink)
+ *     and cycles through four gather blocks: batches issued round-robin on a few streams run back to back on every
+ *     shard while the root merges earlier ones;
  *   - gfi_debug_tensor_scores is single-GPU only.
  * A device may be listed more than once (several shards on one GPU: used by the single-GPU tests).
  * All listed GPUs must be able to access the root GPU's memory (NVLink / NVSwitch peers).

@@ -28,6 +28,7 @@
 #include <unordered_map>
 #include <vector>
 
+#include <sys/stat.h>
 #include <unistd.h>
 
 #include "host.h"
@@ -1253,6 +1254,14 @@ int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int
     // into two pinned buffers in turn, and each chunk's H2D copy, id fill and row_stats pass run on the ingest stream
     // while the next chunk is being read; one synchronisation at the end.
     int32_t rc;
+    {
+      // a file shorter than its header says must add nothing: checked before the first chunk reaches the GPU (the
+      // per-chunk row statistics feed index-wide counters that cannot be taken back)
+      struct stat sb;
+      if (fstat(fileno(f), &sb) == 0 && S_ISREG(sb.st_mode) &&
+          (uint64_t)sb.st_size < 8ull + (uint64_t)count * (uint64_t)dim * 4ull)
+        return fail(GFI_ERR_INDEX, "flat file is shorter than its header says");
+    }
     if (h->dim == 0) latch_dim(h, dim);
     if ((rc = flush_locked(h)) != GFI_OK) return rc;
     if ((rc = grow(h, h->n_slots + (int64_t)count)) != GFI_OK) return rc;
@@ -1314,6 +1323,8 @@ int32_t gfi_add_from_file(gfi_index* h, const char* path, uint64_t first_id, int
     }
     CU_TRY(cudaStreamSynchronize(h->ingest_stream));
     h->n_slots += (int64_t)count;
+    if (!h->odd_dim_rows.empty())  // ids recorded earlier with another dimension are replaced, as FlatIndex::add would
+      for (uint64_t id = first_id; id < first_id + (uint64_t)count; ++id) h->odd_dim_rows.erase(id);
     register_ids(h, nullptr, first_id, (int64_t)count, slot0);
     if (!h->meta_values.empty()) h->meta_dirty = true;
     if ((rc = read_counters(h)) != GFI_OK) return rc;

@@ -10,8 +10,10 @@
 //            through peer pointers straight into the ROOT GPU's gather block -- posted stores over NVLink/NVSwitch,
 //            fused into the kernel that produces them.  The root's stream waits on one event per shard, merges the
 //            G sorted lists per query by (distance, id) with merge_topk_kernel and returns ONE block to the host.
-//   overlap  device-resident searches (gfi_search_device) double-buffer the gather block: shard g may write batch
-//            i+1's candidates while the root still merges batch i, so exchange + merge hide behind the next main pass.
+//   overlap  device-resident searches (gfi_search_device) cycle through kGather gather blocks: shard g may write the
+//            candidates of batches i+1 .. i+3 while the root still merges batch i, so exchange + merge hide behind the
+//            next main passes.  No copy-engine operation sits between a shard's kernels: inputs on the root GPU are
+//            read in place over NVLink, the control block goes back through a one-warp kernel.
 // Everything that defines results (scoring, exact re-scoring, certification, tie order) is the single-GPU code; the
 // merge orders by (distance, lower internal id), the same total order every shard already uses.
 #include <algorithm>
@@ -787,9 +789,9 @@ int32_t sharded_search_device(gfi_index* H, const float* d_queries, int64_t q, c
   ShardedCtx* c = tl_sctx;
   CU_TRY(cudaSetDevice(S->root));
   // Searches on different caller streams are independent of each other on the root GPU (each merge is ordered behind
-  // its own shards' events, and a gather block is handed over through merge_done), so two batches alternating between
-  // two streams overlap: the exchange + merge of one hides behind the main pass of the other.  On ONE stream the
-  // next batch's inputs are by definition ordered behind the previous batch's merge.
+  // its own shards' events, and a gather block is handed over through merge_done), so batches issued round-robin on
+  // a few streams overlap: the exchange + merge of one hides behind the main passes of the next ones.  On ONE stream
+  // the next batch's inputs are by definition ordered behind the previous batch's merge.
   cudaStream_t rs = stream ? (cudaStream_t)stream : c->root_stream;
   if (std::find(c->streams.begin(), c->streams.end(), rs) == c->streams.end()) c->streams.push_back(rs);
   CU_TRY(c->result.ensure((size_t)S->G * 64));  // the shards' control blocks
