@@ -756,9 +756,11 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   gp.seed_stride = seed_stride;
   gp.skip = device_route ? &ctrl->skip_tensor : nullptr;
   gp.debug = h->opt_gemm_debug;
-  // seed pass
+  // seed pass (short rows: the row-tile-stationary instance, a CTA per sample tile)
   gp.seed_mode = 1;
-  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq, (int)std::min<int64_t>(grid_sm, seed_tiles * num_m_tiles), st));
+  gp.short_k = (short_k && h->opt_short_k_seed) ? 1 : 0;
+  CU_TRY(launch_gemm_topk(gp, &tmx, &tmq,
+                          (int)std::min<int64_t>(grid_sm, gp.short_k ? seed_tiles : seed_tiles * num_m_tiles), st));
   SeedFinalizeParams sf{c->seeds.as<float>(), q, seed_tiles, rank, c->thresh.as<float>(), gp.skip};
   CU_TRY(launch_seed_finalize(sf, st));
   // main pass
@@ -2364,6 +2366,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "pair") h->opt_pair = (int)value;
   else if (n == "short_k") h->opt_short_k = (int)value;
   else if (n == "short_k_min_tiles") h->opt_short_k_min_tiles = (int)value;
+  else if (n == "short_k_seed") h->opt_short_k_seed = (int)value;
   else if (n == "tensor_auto") { h->opt_tensor_auto = (int)value; h->auto_tensor_off = false; h->auto_q = 0; h->auto_fb = 0; }
   else if (n == "profile") h->opt_profile = (int)value;
   else if (n == "coalesce") h->opt_coalesce = (int)value;

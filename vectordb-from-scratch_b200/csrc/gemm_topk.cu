@@ -262,6 +262,54 @@ __device__ __forceinline__ bool epi_filter_half(const GemmParams& p, const uint3
                              hitcnt + half * kGemmMaxQueries + qi, bm, lv[0], lv[1], lv[2], lv[3], release_bar);
 }
 
+// Seed pass of one accumulator half for the calling thread's query (short-K kernel): the kSeedR smallest 32-row
+// block minima of the 128 scores, ascending.  Seed statistic as in the k-ring kernel's MODE 1: the rank-th smallest
+// block minimum is >= the rank-th smallest score, with equality unless two of the sample's `rank` best rows share a
+// block -- a slightly looser threshold then, never a wrong one.
+__device__ __forceinline__ void epi_seed_half(const uint32_t taddr, const uint32_t cs_addr, float (&sd)[kSeedR],
+                                              const bool skip) {
+  const float kInf = __int_as_float(0x7f800000);
+#pragma unroll
+  for (int i = 0; i < kSeedR; ++i) sd[i] = kInf;
+  if (skip) return;
+  auto block_min = [&](const uint32_t (&r)[32], const int c0) {
+    float m8[4];
+#pragma unroll
+    for (int g8 = 0; g8 < 4; ++g8) {
+      const float4 k0 = lds128(cs_addr + (c0 + 8 * g8) * 8), k1 = lds128(cs_addr + (c0 + 8 * g8 + 2) * 8);
+      const float4 k2 = lds128(cs_addr + (c0 + 8 * g8 + 4) * 8), k3 = lds128(cs_addr + (c0 + 8 * g8 + 6) * 8);
+      const float v0 = fmaf(__uint_as_float(r[8 * g8]), k0.x, k0.y), v1 = fmaf(__uint_as_float(r[8 * g8 + 1]), k0.z, k0.w);
+      const float v2 = fmaf(__uint_as_float(r[8 * g8 + 2]), k1.x, k1.y), v3 = fmaf(__uint_as_float(r[8 * g8 + 3]), k1.z, k1.w);
+      const float v4 = fmaf(__uint_as_float(r[8 * g8 + 4]), k2.x, k2.y), v5 = fmaf(__uint_as_float(r[8 * g8 + 5]), k2.z, k2.w);
+      const float v6 = fmaf(__uint_as_float(r[8 * g8 + 6]), k3.x, k3.y), v7 = fmaf(__uint_as_float(r[8 * g8 + 7]), k3.z, k3.w);
+      m8[g8] = fmin3(fmin3(v0, v1, v2), fmin3(v3, v4, v5), fminf(v6, v7));
+    }
+    const float m = fmin3(m8[0], m8[1], fminf(m8[2], m8[3]));
+    if (m < sd[kSeedR - 1]) {
+      sd[kSeedR - 1] = m;
+#pragma unroll
+      for (int i = kSeedR - 1; i > 0; --i) {
+        const float lo = fminf(sd[i - 1], sd[i]), hi = fmaxf(sd[i - 1], sd[i]);
+        sd[i - 1] = lo;
+        sd[i] = hi;
+      }
+    }
+  };
+  uint32_t ra[32], rb[32];
+  tmem_ld_32x32b_x32(taddr, ra);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 32, rb);
+  block_min(ra, 0);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 64, ra);
+  block_min(rb, 32);
+  tmem_ld_wait();
+  tmem_ld_32x32b_x32(taddr + 96, rb);
+  block_min(ra, 64);
+  tmem_ld_wait();
+  block_min(rb, 96);
+}
+
 // The live words of the 128 rows [slot0, slot0 + 128) (slot0 a multiple of 128), bits of slots beyond the index cleared
 // (raw epilogue only: the coefficient epilogue gets tombstones and masks through b = +inf).
 __device__ __forceinline__ void load_live4(const IndexView& iv, const int64_t slot0, uint32_t (&lv)[4]) {
@@ -662,7 +710,7 @@ __device__ __forceinline__ void mbar_wait_d(uint64_t* bar, uint32_t parity, bool
 
 template <int MODE, bool DIAG>
 __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const CUtensorMap& tmq, const GemmParams& p) {
-  static_assert(MODE == 0 || MODE == 3, "main-pass modes only");
+  static_assert(MODE == 0 || MODE == 1 || MODE == 3, "main pass (0: coefficients, 3: raw) or seed pass (1)");
   constexpr int kNA = sk::kNA;
   constexpr uint32_t kIdesc = Geo<1>::kIdesc;
   extern __shared__ unsigned char smem_raw[];
@@ -688,8 +736,11 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
   const int nk16 = (iv.dpad16 + 15) / 16;           // K = 16 MMA steps per item (<= 8)
   const int64_t unit = blockIdx.x, nunits = gridDim.x;
   const int M = p.num_m_tiles;
-  // this CTA's row tiles: unit, unit + nunits, ...
-  const int64_t ntiles = unit < p.num_n_tiles ? (p.num_n_tiles - unit + nunits - 1) / nunits : 0;
+  // this CTA's row tiles: unit, unit + nunits, ... of the index -- or, for the seed pass, of the evenly strided sample
+  // (sample tile t is row tile t * seed_stride)
+  const int64_t tiles_all = MODE == 1 ? p.seed_tiles : p.num_n_tiles;
+  const int64_t tstride = MODE == 1 ? p.seed_stride : 1;
+  const int64_t ntiles = unit < tiles_all ? (tiles_all - unit + nunits - 1) / nunits : 0;
   const int64_t total = ntiles * M;                 // items of this CTA
   // (in-kernel timers live in their own instantiation: even predicated off they cost the item loops a branch or two)
   const bool diag = DIAG && (p.debug & 32) && blockIdx.x == 0;
@@ -734,7 +785,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     // (its stage) to have completed, B(j) those of the last item of row tile j - 1 (the single row-tile buffer).
     auto load_b = [&](int64_t j) {
       if (lane == 0) {
-        const int n_row0 = (int)((unit + j * nunits) * BN);
+        const int n_row0 = (int)((unit + j * nunits) * tstride * BN);
         if (debug & 2) { mbar_arrive(bfull); return; }
         mbar_arrive_expect_tx(bfull, (uint32_t)KS * sk::kBChunkBytes);
         for (int kc = 0; kc < KS; ++kc) tma_load_2d(sB + (size_t)kc * sk::kBChunkBytes, &tmx, kc * BK, n_row0, bfull);
@@ -812,7 +863,7 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     const bool by_slot = has_mask && iv.ids_identity;
     for (int64_t j = 0; j < ntiles; ++j) {
       const uint32_t cb = (uint32_t)j & 1u, cph = (uint32_t)(j >> 1) & 1u;
-      const int64_t n0 = (unit + j * nunits) * BN;
+      const int64_t n0 = (unit + j * nunits) * tstride * BN;
       float2 cv[RPL];
 #pragma unroll
       for (int i = 0; i < RPL; ++i) {
@@ -868,7 +919,8 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
     // (row tile, then query tile: everything that depends on the row tile only is set up once per 32 items)
     for (uint32_t j = 0; j < (uint32_t)ntiles; ++j) {
       const uint32_t cb = j & 1u;
-      const int64_t n0 = (unit + (int64_t)j * nunits) * BN;
+      const int64_t nt_idx = unit + (int64_t)j * nunits;  // (sample) tile index
+      const int64_t n0 = nt_idx * tstride * BN;
       const uint32_t cs_addr = smem_u32(sCoef + cb * BN + half * (BN / 2));
       const uint32_t bs_addr = smem_u32(sBOnly + cb * BN + half * (BN / 2));
       bool uni = false;
@@ -885,17 +937,29 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
       for (int m = 0; m < M; ++m, ++it, qidx += BM) {
         const uint32_t s = it & (uint32_t)(kNA - 1), as = it & 1u;
         float thr = __int_as_float(0xff800000);  // -inf: padding queries never match
-        if (qidx < p.q) thr = p.thresh[qidx];
+        if (MODE != 1 && qidx < p.q) thr = p.thresh[qidx];
         mbar_wait_d(&done[s], (it / kNA) & 1u, diag, w_a);
         tc_fence_after();
         const long long te0 = diag ? clock64() : 0;
-        const bool released =
-            epi_filter_half<MODE>(p, lane_addr + as * BN, cs_addr, thr, thr * inv_cq, c_q, qidx, n0, half, unit, hitcnt,
-                                  lv, uni, bs_addr, a_u, smem_u32(&tempty[as]), debug);
+        bool released = false;
+        float sd[kSeedR];
+        if (MODE == 1) {
+          epi_seed_half(lane_addr + as * BN, cs_addr, sd, (debug & 4) != 0);
+        } else {
+          released = epi_filter_half<MODE == 1 ? 0 : MODE>(p, lane_addr + as * BN, cs_addr, thr, thr * inv_cq, c_q, qidx,
+                                                           n0, half, unit, hitcnt, lv, uni, bs_addr, a_u,
+                                                           smem_u32(&tempty[as]), debug);
+        }
         if (diag) w_x += clock64() - te0;
         tc_fence_before();
         __syncwarp();
         if (lane == 0 && !released) mbar_arrive(&tempty[as]);
+        if (MODE == 1 && qidx < p.q) {  // the thread's kSeedR smallest 32-row block minima of this (query, tile, half)
+          float4* out = reinterpret_cast<float4*>(p.seeds + (((size_t)qidx * p.seed_tiles + nt_idx) * 2 + half) * kSeedR);
+          static_assert(kSeedR == 8, "two 16-byte stores");
+          out[0] = make_float4(sd[0], sd[1], sd[2], sd[3]);
+          out[1] = make_float4(sd[4], sd[5], sd[6], sd[7]);
+        }
       }
       if (MODE != 3 && lane == 0) mbar_arrive(&cempty[cb]);  // (after the tile's last __syncwarp)
     }
@@ -906,10 +970,11 @@ __device__ __forceinline__ void gemm_topk_sk_body(const CUtensorMap& tmx, const 
            (long long)total, w_a, w_b, w_c, w_x);
   tc_fence_before();
   __syncthreads();
-  for (int i = tid; i < 2 * p.q; i += kGemmThreads) {
-    const int hf = i >= p.q ? 1 : 0, qi = i - hf * p.q;
-    p.slice_cnt[(size_t)(unit * 2 + hf) * p.q + qi] = hitcnt[hf * kGemmMaxQueries + qi];
-  }
+  if (MODE != 1)
+    for (int i = tid; i < 2 * p.q; i += kGemmThreads) {
+      const int hf = i >= p.q ? 1 : 0, qi = i - hf * p.q;
+      p.slice_cnt[(size_t)(unit * 2 + hf) * p.q + qi] = hitcnt[hf * kGemmMaxQueries + qi];
+    }
   if (diag && tid == 0) {
     long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
@@ -1077,6 +1142,8 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
     const int c = (int)sk::kSmemBytes;
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_topk_sk_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, c);
     if (e != cudaSuccess) return e;
@@ -1087,8 +1154,11 @@ cudaError_t launch_gemm_topk(const GemmParams& p, const void* tmap_x_host, const
   const size_t sm1 = Geo<1>::kSmemBytes, sm2 = Geo<2>::kSmemBytes;
   const dim3 g(grid), b(kGemmThreads);
   if (p.short_k) {
-    if (pair || p.iv.dpad16 > 2 * BK || (p.seed_mode != 0 && p.seed_mode != 3)) return cudaErrorInvalidValue;
+    if (pair || p.iv.dpad16 > 2 * BK || p.seed_mode == 2) return cudaErrorInvalidValue;
     const bool diag = p.debug != 0;  // any timing-experiment switch: the instrumented instantiation
+    if (p.seed_mode == 1)
+      return diag ? launch_pdl(gemm_topk_sk_kernel<1, true>, g, b, sk::kSmemBytes, st, *tx, *tq, p)
+                  : launch_pdl(gemm_topk_sk_kernel<1, false>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
     if (p.seed_mode == 0)
       return diag ? launch_pdl(gemm_topk_sk_kernel<0, true>, g, b, sk::kSmemBytes, st, *tx, *tq, p)
                   : launch_pdl(gemm_topk_sk_kernel<0, false>, g, b, sk::kSmemBytes, st, *tx, *tq, p);
