@@ -193,3 +193,50 @@ def test_short_k_uniform_coefficient_loop_selects_the_same_candidates():
     exp = oracle.search_batch("euclidean", rows, queries[:32], k, eligible=elig, threads=8)
     for i, (eids, ed) in enumerate(exp):
         assert_topk_matches(res[0][0][i, :res[0][2][i]], res[0][1][i, :res[0][2][i]], eids, ed, ctx=f"uniform loop q{i}")
+
+
+# ---------------------------------------------------------------- rerank cut (select_kernel)
+RERANK_CUT_CASES = [  # metric, n, d, kind, q, k
+    ("cosine", 50000, 192, 1, 96, 10),
+    ("euclidean", 60000, 128, 0, 512, 10),     # short-K kernel
+    ("dot", 40000, 200, 1, 64, 100),           # KP = 512
+    ("euclidean", 30000, 96, 1, 48, 1),
+    ("cosine", 20000, 64, 0, 40, 33),          # all-positive rows: every distance within a narrow band
+]
+
+
+@pytest.mark.parametrize("case", RERANK_CUT_CASES, ids=lambda c: "%s_n%d_d%d_q%d_k%d" % (c[0], c[1], c[2], c[4], c[5]))
+def test_rerank_cut_never_changes_an_answer(case):
+    """select_kernel re-scores only the candidates whose fp16 error interval reaches the k-th best one's
+    (option rerank_cut, default 1).  Same ids and bit-identical distances with the cut off (0), on, and in the test mode
+    that cuts right behind the k-th candidate (2), where the certification has to send almost every query to the
+    exact scan; half of the queries are stored rows (k-th distances next to zero, exact duplicates of the query)."""
+    metric, n, d, kind, q, k = case
+    M = {"euclidean": DM.Euclidean, "cosine": DM.Cosine, "dot": DM.DotProduct}
+    rows = oracle.gen_rows(700 + d, 0, n, d, kind)
+    rows[1000:1040] = rows[77]                      # 40 exact copies of one row
+    queries = oracle.gen_rows(800 + d, 0, q, d, kind)
+    queries[::2] = rows[np.arange(0, q, 2) * 37 % n]
+    queries[4] = rows[77]
+    idx = gfi.GpuFlatIndex(M[metric])
+    idx.add_batch(np.arange(n, dtype=np.uint64), rows)
+    idx.set_option("tensor_min_rows", 256)
+    res, fb = {}, {}
+    for mode in (1, 0, 2):
+        idx.set_option("rerank_cut", mode)
+        s0 = idx.stats()
+        res[mode] = idx.search_arrays(queries, k)
+        s1 = idx.stats()
+        assert s1["tensor_queries"] - s0["tensor_queries"] == q, (mode, s0, s1)
+        fb[mode] = s1["fallback_queries"] - s0["fallback_queries"]
+    for mode in (0, 2):
+        for a, b in zip(res[1], res[mode]):
+            assert np.array_equal(a, b), (mode, fb)
+    # a rigorous cut costs no extra fallbacks; the test mode falls back wherever the (k+1)-th row is inside the band
+    assert fb[1] <= fb[0] + 1, fb
+    assert fb[2] >= fb[1], fb
+    got_ids, got_d, cnt = res[1]
+    exp = oracle.search_batch(metric, rows, queries[:40], k, threads=8)
+    for i, (eids, ed) in enumerate(exp):
+        assert cnt[i] == len(eids)
+        assert_topk_matches(got_ids[i, :cnt[i]], got_d[i, :cnt[i]], eids, ed, ctx=f"{case} q{i}")

@@ -784,6 +784,7 @@ int32_t enqueue_chunk(gfi_index* h, SearchCtx* c, const SearchArgs& a, cudaStrea
   s.nq_dev = device_route ? &ctrl->tensor_nq : nullptr;  // 0 when the device-side route chose the scan
   s.nq = device_route ? 0 : q;
   s.certify = 1;
+  s.rerank_cut = h->opt_rerank_cut;
   s.thresh = c->thresh.as<float>();
   const float dd = (float)h->dim;
   s.eps_rel = 9.765625e-4f + 9.5367432e-07f + 2.f * std::sqrt(dd) * 1.4901161e-08f + (dd + 8.f) * 1.1920929e-07f;
@@ -2373,6 +2374,7 @@ int32_t gfi_set_option(gfi_index* h, const char* name, int64_t value) {
   else if (n == "gemm_debug") h->opt_gemm_debug = (int)value;
   else if (n == "scan_stages") h->opt_scan_stages = (int)value;
   else if (n == "scan_certify") h->opt_scan_certify = (int)value;
+  else if (n == "rerank_cut") h->opt_rerank_cut = (int)value;
   else return fail(GFI_ERR_INDEX, "unknown option: " + n);
   return GFI_OK;
 }

@@ -273,6 +273,7 @@ struct gfi_index {
   int opt_short_k = 1;       // dpad16 <= 128: row-tile-stationary main pass (0 = the k-ring kernel, for A/B timing)
   int opt_short_k_min_tiles = 4;  // ... for batches of at least this many 128-query tiles
   int opt_short_k_seed = 1;  // the seed pass of a short-K search runs on the row-tile-stationary kernel too
+  int opt_rerank_cut = 1;    // tensor path: re-score only candidates whose fp16 error interval reaches the k-th one's
   int opt_scan_certify = 1;  // 0: scan-path answers are not certified (A/B timing, tests of the proof itself)
   int opt_tensor_auto = 1;   // small batches on large indexes take the tensor path when the cost model says so
   std::atomic<int64_t> last_mask_pop{-1};     // population of the last device-resident mask searched (route predictor)

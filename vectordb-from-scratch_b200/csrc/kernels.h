@@ -116,6 +116,8 @@ struct SelInfo {  // per query, written by select_kernel, consumed by rerank_fin
   uint32_t kpeff;   // candidates selected for rerank = min(KP, nvalid)
   uint32_t overflow;
   uint32_t done;    // warps of this query that finished their rerank share
+  uint32_t has_cut; // tensor path: kpeff was shortened by the rerank cut (select_kernel); cut_key is then the
+  uint32_t cut_key; // orderable approximate score of the best candidate that is NOT re-scored
 };
 struct SelectParams {
   IndexView iv;
@@ -139,6 +141,7 @@ struct SelectParams {
   int certify;                // 0 = none, 1 = tensor path (fp16 error bound; failures -> fb_list, re-run on the scan),
                               // 2 = scan path (fp32 summation-order bound; failures -> up_list, proven by the host)
   const float* thresh;        // per-query score threshold used by the tensor kernel
+  int rerank_cut;             // 1: re-score only candidates whose error interval reaches the k-th best one's
   float eps_rel;              // relative error bound of the approximate dot product
   const float* qmaxabs;       // batch max |q| (fp16 common scale), tensor path
   float xnorm_max;            // max ||x|| over rows ever inserted

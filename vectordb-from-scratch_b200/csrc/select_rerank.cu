@@ -204,14 +204,54 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
       }
     }
     __syncthreads();
-    for (int i = tid; i < KP; i += kSelThreads) p.sel_keys[(size_t)qg * p.KP + i] = sel[i];
+    // ---- rerank cut (tensor path): which of the selected rows are worth re-scoring? ----
+    // The k best approximate scores are k real rows, so the exact k-th distance is at most ub(a_k) (exact.cuh
+    // tensor_bounds); a candidate with lb(a) > ub(a_k) cannot belong to the top-k.  At the benchmark sizes the fp16
+    // error interval is a tenth of the gap between the k-th and the KP-th score: 12-15 of 64 candidates remain, and
+    // the rerank -- random 128-byte pieces of HBM rows, its bytes are its time -- shrinks with them.  The keys are put
+    // in ascending order by counting ranks (they are unique: each carries its slot), the re-scored set is a prefix,
+    // and the FIRST key behind it replaces the pivot in the certification, which still compares against the exact
+    // k-th distance: a cut that is too tight makes the query fall back, it cannot change an answer.
+    uint32_t kp_out = kpeff, cut_key = 0, has_cut = 0;
+    const uint32_t kq = p.ks[qg];
+    if (p.certify == 1 && p.rerank_cut && KP <= 512 && kq > 0 && kpeff > kq && !overflow) {
+      uint64_t* sorted = keys;  // the staging area is free again (KP <= 512 <= kSelCap)
+      for (int t = tid; t < KP; t += kSelThreads) {
+        const uint64_t key = sel[t];
+        if (key == kKeySentinel) continue;
+        uint32_t rank = 0;
+        for (int j = 0; j < KP; ++j) rank += sel[j] < key;
+        sorted[rank] = key;
+      }
+      // (s_need is free here) first index that need not be re-scored; rerank_cut == 2 is the test mode "cut right
+      // behind the k-th key", which the certification must answer by falling back
+      if (tid == 0) s_need = p.rerank_cut == 2 ? kq : kpeff;
+      __syncthreads();
+      TensorBoundIn tb{p.qnorm[qg], p.qsumsq[qg], p.eps_rel, *p.qmaxabs, p.xnorm_max, p.iv.d};
+      float lb_k, ub_k;
+      tensor_bounds(p.iv.metric, key_f32((uint32_t)(sorted[kq - 1] >> 32)), tb, &lb_k, &ub_k);
+      for (uint32_t t = kq + tid; t < kpeff && p.rerank_cut != 2; t += kSelThreads) {
+        float lb_t, ub_t;
+        tensor_bounds(p.iv.metric, key_f32((uint32_t)(sorted[t] >> 32)), tb, &lb_t, &ub_t);
+        if (lb_t > ub_k) { atomicMin(&s_need, t); break; }  // (ascending: the thread's later keys are behind it too)
+      }
+      __syncthreads();
+      kp_out = s_need;
+      if (kp_out < kpeff) { has_cut = 1; cut_key = (uint32_t)(sorted[kp_out] >> 32); }
+      for (int i = tid; i < KP; i += kSelThreads)
+        p.sel_keys[(size_t)qg * p.KP + i] = (uint32_t)i < kpeff ? sorted[i] : kKeySentinel;
+    } else {
+      for (int i = tid; i < KP; i += kSelThreads) p.sel_keys[(size_t)qg * p.KP + i] = sel[i];
+    }
     if (tid == 0) {
       SelInfo info;
       info.pivot = pivot;
       info.nvalid = nvalid;
-      info.kpeff = kpeff;
+      info.kpeff = kp_out;
       info.overflow = overflow ? 1u : 0u;
       info.done = 0;
+      info.has_cut = has_cut;
+      info.cut_key = cut_key;
       p.sel_info[qg] = info;
     }
     __syncthreads();
@@ -220,15 +260,17 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 
 // ---- K3b: reference-exact rerank (one warp per 32 candidates) + finalize by the last warp ----------
 constexpr int kRrWarps = 4;                       // warps per block
-constexpr int kRrCW = 32;                         // floats per row chunk staged per step
-constexpr int kRrTile = 32 * (kRrCW + 1);         // one warp tile: 32 rows, odd stride
+constexpr int kRrCW = 32;                         // floats per row chunk (one 128-byte line)
+constexpr int kRrRPW = 8;                         // bulk mode: candidate rows per warp (4 lanes per row)
+constexpr int kRrDepth = 4;                       // bulk mode: chunks of loads in flight per lane
+constexpr int kRrTile = 32 * (kRrCW + 1);         // per-warp scratch: the latency mode's row + query, the final sort
 static_assert(2 * kRrTile * 4 >= kMaxKP * 8, "the finalizing warp sorts in its tile buffers");
 
 __device__ __forceinline__ void warp_bitonic_sort(uint64_t* arr, int N, int lane) {
   for (int k = 2; k <= N; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       for (int t = lane; t < N / 2; t += 32) {
-        const int i = ((t / j) * 2 * j) + (t % j);
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // j is a power of two: (t / j) * 2j + t % j
         const int l = i + j;
         const bool up = ((i & k) == 0);
         const uint64_t a = arr[i], b = arr[l];
@@ -246,20 +288,27 @@ template <int METRIC>
 __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const SelectParams p) {
   griddep_wait();
   __shared__ __align__(16) float s_tiles[kRrWarps][2 * kRrTile];
-  __shared__ float s_q[kRrWarps][2][32];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const IndexView& iv = p.iv;
   const int nq = p.nq_dev ? (int)*p.nq_dev : p.nq;
-  const int groups = p.warp_per_candidate ? p.KP : p.KP / 32;  // warps per query
+  const int rpw = p.warp_per_candidate ? 1 : kRrRPW;  // candidate rows per warp
+  const int groups = p.KP / rpw;                       // warps per query
   const int64_t gw = (int64_t)blockIdx.x * kRrWarps + wib;
   const int64_t total = (int64_t)nq * groups;
   float* tile = s_tiles[wib];
 
   for (int64_t wq = gw; wq < total; wq += (int64_t)gridDim.x * kRrWarps) {
-    const int qq = (int)(wq / groups), gi = (int)(wq - (int64_t)qq * groups);
+    // group-major: the first nq warps take group 0 of every query, the next nq group 1, ...  Warps that have rows
+    // sit next to each other, so whole blocks of the late groups exit at once and the live ones fit one wave (query-
+    // major, a block held two live and two idle warps and the kernel ran in two waves at a quarter of the occupancy)
+    const int gi = (int)(wq / nq), qq = (int)(wq - (int64_t)gi * nq);
     const uint32_t qg = p.qlist ? p.qlist[qq] : (uint32_t)qq;
     SelInfo* info = p.sel_info + qg;
     const uint32_t kpeff = info->kpeff;
+    // warps that have rows to re-score (at least one, which finalizes a query without candidates); the others have
+    // nothing to do with this query at all -- with the rerank cut that is most of them
+    const int ga = max(1, ((int)kpeff + rpw - 1) / rpw);
+    if (gi >= ga) continue;
     uint64_t* skeys = p.sel_keys + (size_t)qg * p.KP;
     const float qn = p.qnorm[qg];
     const float* qv = p.q32 + (size_t)qg * iv.dpad;
@@ -289,97 +338,73 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
         }
         __syncwarp();
       }
-    } else {
-    const int ci = gi * 32 + lane;
-    const bool have = (uint32_t)ci < kpeff;
-    const uint32_t slot = have ? (uint32_t)(skeys[ci] & 0xffffffffu) : 0xffffffffu;
-
-    if ((uint32_t)(gi * 32) < kpeff) {
-      // rows staged through the warp's private tiles with coalesced loads (8 lanes per 128-byte row
-      // chunk); every lane then walks its own candidate's chunk in order: a sequential f32 chain
+    } else if (gi < ga && kpeff > 0) {
+      // Bulk mode.  Four lanes per candidate row, eight rows per warp.  A chunk is one 128-byte line of each row:
+      // lane (r, c8) loads ITS 8 consecutive floats of row r straight into registers (two 128-bit loads: the four
+      // lanes of a row cover the line, no shared-memory transpose) together with the matching 8 query floats, and
+      // forms the eight terms q*x (or (q-x)^2) -- separately rounded, independent of each other.  The reference's
+      // left-to-right sum (src/distance.rs:37-44,67-73) is the only sequential part: the running sum travels as a
+      // token through the four lanes of the row (one shuffle per hand-over), each adding its eight terms in order,
+      // and wraps around to the first lane for the next chunk.  kRrDepth chunks of loads are in flight per lane.
+      // Round 2's first form staged 32 rows per warp through shared memory and let every lane walk one row: ~250
+      // instructions per chunk on ONE warp's critical path; with the rerank cut leaving 10-20 rows per query that
+      // single warp set the kernel's time (ncu: 58 us for 48 MB, 9 % of the warp slots occupied).
+      const int r = lane >> 2, c8 = lane & 3;
+      const int ci = gi * kRrRPW + r;
+      const bool have = (uint32_t)ci < kpeff;
+      uint32_t slot = have ? (uint32_t)(skeys[ci] & 0xffffffffu) : 0u;
+      const uint32_t slot0 = __shfl_sync(0xffffffffu, slot, 0);
+      if (!have) slot = slot0;  // absent rows alias the warp's first row: same lines, results never stored
+      const float* xrow = iv.x32 + (size_t)slot * iv.dpad;
       const int nchunk = (iv.d + kRrCW - 1) / kRrCW;
-      float4 stage[8];
-      float qstage;
-      float* qt = tile + 2 * kRrTile - 64;  // two 32-float query chunks live in the pad columns' tail
-      auto load_chunk = [&](int c) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
-          const uint32_t rs = __shfl_sync(0xffffffffu, slot, row);
-          const int col = c * kRrCW + 4 * c4;
-          stage[i] = (rs != 0xffffffffu && col < iv.dpad)
-                         ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)rs * iv.dpad + col))
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        qstage = (c * kRrCW + lane < iv.dpad) ? __ldg(qv + c * kRrCW + lane) : 0.f;
+      const int col_last = iv.dpad - 4;
+      float4 xa[kRrDepth], xb[kRrDepth], qa[kRrDepth], qb[kRrDepth];
+      auto issue = [&](int j, int c) {
+        const int col = c * kRrCW + 8 * c8;
+        const int ca = min(col, col_last), cb = min(col + 4, col_last);
+        xa[j] = __ldg(reinterpret_cast<const float4*>(xrow + ca));
+        xb[j] = __ldg(reinterpret_cast<const float4*>(xrow + cb));
+        qa[j] = __ldg(reinterpret_cast<const float4*>(qv + ca));
+        qb[j] = __ldg(reinterpret_cast<const float4*>(qv + cb));
       };
-      auto store_chunk = [&](float* t, int buf) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
-          float* dst = t + row * (kRrCW + 1) + 4 * c4;
-          dst[0] = stage[i].x; dst[1] = stage[i].y; dst[2] = stage[i].z; dst[3] = stage[i].w;
-        }
-        s_q[wib][buf][lane] = qstage;
-      };
-      (void)qt;
-      float acc = -0.0f;
-      auto chain = [&](int c) {
-        const float* row = tile + (c & 1) * kRrTile + lane * (kRrCW + 1);
-        const float* qc = s_q[wib][c & 1];
-        const int c0 = c * kRrCW;
-        const int lim = min(kRrCW, iv.d - c0);
-        if (lim == kRrCW) {
-#pragma unroll
-          for (int i = 0; i < kRrCW; ++i) acc = exact_step<METRIC>(acc, qc[i], row[i]);
-        } else {
-          for (int i = 0; i < lim; ++i) acc = exact_step<METRIC>(acc, qc[i], row[i]);
-        }
-      };
-      // software pipeline, two chunks of global loads in flight: while chunk c is walked from shared
-      // memory, chunk c+1 sits in registers (stored right after) and chunk c+2 is being fetched
-      float4 stage2[8];
-      float qstage2 = 0.f;
-      auto load_chunk2 = [&](int c) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
-          const uint32_t rs = __shfl_sync(0xffffffffu, slot, row);
-          const int col = c * kRrCW + 4 * c4;
-          stage2[i] = (rs != 0xffffffffu && col < iv.dpad)
-                          ? __ldg(reinterpret_cast<const float4*>(iv.x32 + (size_t)rs * iv.dpad + col))
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        qstage2 = (c * kRrCW + lane < iv.dpad) ? __ldg(qv + c * kRrCW + lane) : 0.f;
-      };
-      auto store_chunk2 = [&](float* t, int buf) {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int row = i * 4 + (lane >> 3), c4 = lane & 7;
-          float* dst = t + row * (kRrCW + 1) + 4 * c4;
-          dst[0] = stage2[i].x; dst[1] = stage2[i].y; dst[2] = stage2[i].z; dst[3] = stage2[i].w;
-        }
-        s_q[wib][buf][lane] = qstage2;
-      };
-      load_chunk(0);
-      store_chunk(tile, 0);
-      if (nchunk > 1) load_chunk(1);
-      __syncwarp();
-      for (int c = 0; c < nchunk; c += 2) {
-        // even step: registers `stage` hold chunk c+1
-        if (c + 2 < nchunk) load_chunk2(c + 2);
-        chain(c);
-        if (c + 1 < nchunk) store_chunk(tile + kRrTile, 1);
-        __syncwarp();
-        if (c + 1 >= nchunk) break;
-        // odd step: registers `stage2` hold chunk c+2
-        if (c + 3 < nchunk) load_chunk(c + 3);
-        chain(c + 1);
-        if (c + 2 < nchunk) store_chunk2(tile, 0);
-        __syncwarp();
+      for (int j = 0; j < kRrDepth; ++j) {
+        xa[j] = xb[j] = qa[j] = qb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nchunk) issue(j, j);
       }
-      if (have) skeys[ci] = pack_key(finish_distance(acc, slot), slot);
-    }
+      const int src_lane = (lane & ~3) | ((lane + 3) & 3);  // previous lane of the row (the first takes from the last)
+      float acc = -0.0f;
+      for (int c0 = 0; c0 < nchunk; c0 += kRrDepth) {
+#pragma unroll
+        for (int j = 0; j < kRrDepth; ++j) {
+          const int c = c0 + j;
+          if (c < nchunk) {  // warp-uniform
+            const float4 x0 = xa[j], x1 = xb[j], q0 = qa[j], q1 = qb[j];
+            if (c + kRrDepth < nchunk) issue(j, c + kRrDepth);
+            float t[8];
+            t[0] = exact_term<METRIC>(q0.x, x0.x); t[1] = exact_term<METRIC>(q0.y, x0.y);
+            t[2] = exact_term<METRIC>(q0.z, x0.z); t[3] = exact_term<METRIC>(q0.w, x0.w);
+            t[4] = exact_term<METRIC>(q1.x, x1.x); t[5] = exact_term<METRIC>(q1.y, x1.y);
+            t[6] = exact_term<METRIC>(q1.z, x1.z); t[7] = exact_term<METRIC>(q1.w, x1.w);
+            // terms behind position d do not exist (the sum stops at d): they become the neutral element -0.0, which
+            // leaves every value it is added to unchanged, bit for bit (including -0.0, infinities and NaN)
+            const int nv = iv.d - (c * kRrCW + 8 * c8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) t[e] = e < nv ? t[e] : -0.0f;
+            // branch-free hand-over: every lane adds its terms to the incoming token, only the lane whose turn it is
+            // keeps the result (a divergent `if (c8 == ph)` cost a BSSY/BSYNC pair per phase on the critical path)
+#pragma unroll
+            for (int ph = 0; ph < 4; ++ph) {
+              float v = __shfl_sync(0xffffffffu, acc, src_lane);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v = __fadd_rn(v, t[e]);
+              acc = c8 == ph ? v : acc;
+            }
+          }
+        }
+      }
+      // the finished sum sits in the row's last lane (lanes behind position d passed the token on unchanged)
+      if (have && c8 == 3) skeys[ci] = pack_key(finish_distance(acc, slot), slot);
     }
     // ---- the last warp of a query to get here sorts, emits and certifies ----
     __threadfence();
@@ -387,7 +412,7 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
     uint32_t prev = 0;
     if (lane == 0) prev = atomicAdd(&info->done, 1u);
     prev = __shfl_sync(0xffffffffu, prev, 0);
-    if (prev != (uint32_t)groups - 1) continue;
+    if (prev != (uint32_t)ga - 1) continue;
     __threadfence();
     if (METRIC == kMetricCos && info->nvalid > 0 && qn == 0.f && lane == 0) atomicOr(p.flags, kFlagZeroNorm);
     uint64_t* sk = reinterpret_cast<uint64_t*>(tile);
@@ -426,28 +451,13 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
       bool ok = !info->overflow && kpeff >= k;
       if (ok) {
         const float tau = key_f32((uint32_t)(sk[k - 1] >> 32));  // exact k-th distance
-        // every row that was not reranked has approximate score >= a_s
-        const float a_s = (info->nvalid > (uint32_t)p.KP) ? key_f32((uint32_t)(info->pivot >> 32)) : p.thresh[qg];
-        const float dd = (float)iv.d;
-        const float gamma = (dd + 8.f) * 5.9604645e-08f;  // (d+8) * 2^-24: sequential-sum rounding
-        const float qmax = *p.qmaxabs;
-        const float eta_q = 3.7252903e-09f * qmax;         // 2^-28 * max|q|: flushed fp16 query elements
-        const float e_dot = (p.eps_rel * qn + eta_q * sqrtf(dd)) * p.xnorm_max;
-        float lb;  // lower bound on the reference-arithmetic distance of any non-reranked row
-        if (METRIC == kMetricDot) {
-          lb = a_s - e_dot - gamma * qn * p.xnorm_max;
-        } else if (METRIC == kMetricCos) {
-          const float e_s = p.eps_rel * qn + eta_q * sqrtf(dd) + 9.5367432e-07f * qn;
-          lb = 1.0f + (a_s - e_s) / qn - 3.f * gamma - 9.5367432e-07f;
-        } else {
-          const float qs = p.qsumsq[qg];
-          const float xs = p.xnorm_max * p.xnorm_max;
-          // a_s uses the PRECOMPUTED sequential sums sum x^2 and sum q^2, each off by up to gamma relatively
-          // (ADVICE r1), plus the epilogue's own fp32 rounding (2^-22 of the magnitudes involved)
-          float d2 = a_s + qs - 2.f * e_dot - (gamma + 2.3841858e-07f) * (xs + qs);
-          d2 = fmaxf(d2, 0.f);
-          lb = sqrtf(d2) * (1.f - gamma) - 1e-30f;
-        }
+        // every row that was not reranked has approximate score >= a_s: the first selected key behind the rerank
+        // cut if select_kernel shortened the set, else the selection's pivot, else the tensor pass's threshold
+        const float a_s = info->has_cut ? key_f32(info->cut_key)
+                          : (info->nvalid > (uint32_t)p.KP) ? key_f32((uint32_t)(info->pivot >> 32)) : p.thresh[qg];
+        const TensorBoundIn tb{qn, METRIC == kMetricL2 ? p.qsumsq[qg] : 0.f, p.eps_rel, *p.qmaxabs, p.xnorm_max, iv.d};
+        float lb, ub;  // lb: lower bound on the reference-arithmetic distance of any non-reranked row
+        tensor_bounds(METRIC, a_s, tb, &lb, &ub);
         ok = lb > tau;  // strict: a tie could hide a row with a lower id
         if (!(a_s == a_s)) ok = false;
       }
@@ -610,7 +620,7 @@ cudaError_t launch_select_rerank(const SelectParams& p, int grid, cudaStream_t s
   const int nq_max = p.nq_dev ? p.nq_max : p.nq;
   pp.few_candidates = (int64_t)nq_max * p.KP <= 4096 ? 1 : 0;
   pp.warp_per_candidate = ((int64_t)nq_max * p.KP <= 2048 && 2 * p.iv.dpad <= 2 * kRrTile) ? 1 : 0;
-  const int64_t warps = (int64_t)nq_max * (pp.warp_per_candidate ? p.KP : p.KP / 32);
+  const int64_t warps = (int64_t)nq_max * (pp.warp_per_candidate ? p.KP : p.KP / kRrRPW);
   const int blocks = (int)std::min<int64_t>((warps + kRrWarps - 1) / kRrWarps, 148 * 16);
   switch (p.iv.metric) {
     case kMetricL2: return launch_pdl(rerank_finalize_kernel<kMetricL2>, dim3(blocks), dim3(kRrWarps * 32), 0, st, pp);
