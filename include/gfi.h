@@ -155,7 +155,9 @@ int32_t gfi_search(gfi_index *h, const float *queries, int64_t q, int64_t dim, c
  * given key/value pairs and kept as dictionary-encoded columns in HBM.  gfi_search_filtered takes the
  * reference's own JSON form of MetadataFilter (serde tag "op": eq / ne / exists / and / or,
  * storage.rs:44-58), evaluates it on the GPU into an eligibility bitmask and runs FlatIndex::search over the
- * matching rows (exact pre-filter; truth table of storage.rs:62-70).
+ * matching rows (exact pre-filter; truth table of storage.rs:62-70).  Any k, as for gfi_search: beyond the kernels'
+ * list capacity the filter is evaluated once over the host mirror of the columns and the passes run over the
+ * matching rows not returned yet.
  */
 int32_t gfi_set_metadata(gfi_index *h, uint64_t id, int32_t n_fields, const char *const *keys,
                          const char *const *values);

@@ -1046,7 +1046,17 @@ def test_k_above_the_kernels_list_capacity(metric):
     for i, (eids, ed) in enumerate(exp):
         assert c3[i] == len(eids)
         assert_topk_matches(g3[i, :c3[i]], d3[i, :c3[i]], eids, ed, ctx=f"big k + mask q{i}")
-    # a filter handed down as JSON still has the capacity, loudly (the reference's caller over-fetches and post-filters)
-    with pytest.raises(gfi.IndexError_) as e:
-        idx.search_filtered(queries[:1], 1500, '{"op": "exists", "field": "color"}')
-    assert "k too large" in str(e.value)
+    # a filter handed down as JSON: evaluated once on the host mirror of the metadata columns, then the same passes
+    for i in range(0, n, 2):
+        idx.set_metadata(int(ids[i]), {"color": "red" if i % 4 == 0 else "blue"})
+    has_color = (np.arange(n) % 2 == 0) & live
+    red = (np.arange(n) % 4 == 0) & live
+    cases = [('{"op": "exists", "field": "color"}', has_color, [1500, 7]),
+             ('{"op": "ne", "field": "color", "value": "red"}', live & ~red, [20, 3000]),
+             ('{"op": "eq", "field": "color", "value": "red"}', red, [2000, 1100])]      # 1250 red rows: k > matches
+    for flt, elig, kk in cases:
+        g4, d4, c4 = idx.search_filtered(queries[:2], np.array(kk, dtype=np.uint32), flt)
+        exp = oracle.search_batch(metric, rows[elig], queries[:2], kk, ids=ids[elig])
+        for i, (eids, ed) in enumerate(exp):
+            assert c4[i] == len(eids), (flt, c4[i], len(eids))
+            assert_topk_matches(g4[i, :c4[i]], d4[i, :c4[i]], eids, ed, ctx=f"big k + filter {flt} q{i}")

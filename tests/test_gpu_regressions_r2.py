@@ -202,6 +202,7 @@ RERANK_CUT_CASES = [  # metric, n, d, kind, q, k
     ("dot", 40000, 200, 1, 64, 100),           # KP = 512
     ("euclidean", 30000, 96, 1, 48, 1),
     ("cosine", 20000, 64, 0, 40, 33),          # all-positive rows: every distance within a narrow band
+    ("euclidean", 30000, 64, 1, 32, 200),      # KP = 1024
 ]
 
 

@@ -183,6 +183,16 @@ def test_sharded_k_above_the_kernels_list_capacity(layout):
     check(idx, "euclidean", rows, queries, np.array([k, 20], dtype=np.uint32), ctx="big k")
     elig = np.arange(n) % 4 != 2   # caller mask by internal id: every shard's passes start from its eligible rows
     check(idx, "euclidean", rows, queries, np.array([k, 20], dtype=np.uint32), eligible=elig, mask=elig, ctx="big k + mask")
+    # and with a JSON filter: every shard evaluates it over its own metadata columns before its passes
+    for i in range(0, n, 2):
+        idx.set_metadata(i, {"tag": "a"})
+    tagged = np.arange(n) % 2 == 0
+    ks = [k, 20]
+    g, dd, c = idx.search_filtered(queries, np.array(ks, dtype=np.uint32), '{"op": "exists", "field": "tag"}')
+    exp = oracle.search_batch("euclidean", rows[tagged], queries, ks, ids=np.arange(n, dtype=np.uint64)[tagged])
+    for i, (eids, ed) in enumerate(exp):
+        assert c[i] == len(eids)
+        assert_topk_matches(g[i, :c[i]], dd[i, :c[i]], eids, ed, ctx=f"big k + filter q{i}")
 
 
 @pytest.mark.parametrize("layout", layouts())

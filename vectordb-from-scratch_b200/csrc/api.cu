@@ -1789,11 +1789,37 @@ extern "C" {
 // exact search over the rows not returned yet (slot-indexed eligibility mask), so the concatenation of the passes
 // is the exact ascending top-k.  ceil(k / kMaxListK) scans per such query -- the rare path, kept simple.
 constexpr uint32_t kMaxListK = 1016;
+// The metadata filter on the host, for the large-k passes only: same postfix program and truth table as
+// eval_filter_kernel (filter.cu), over the host mirror of the field columns.
+static bool eval_filter_host(const FilterProgram& prog, const std::vector<std::vector<uint32_t>>& cols, int64_t s) {
+  bool stack[kFilterMaxDepth];
+  int sp = 0;
+  for (int i = 0; i < prog.n; ++i) {
+    const FilterOp& op = prog.ops[i];
+    if (op.kind <= kFilterExists) {
+      uint32_t code = 0u;  // no column (yet) or a slot beyond it: the field is absent
+      if (op.field >= 0 && (size_t)op.field < cols.size() && (size_t)s < cols[(size_t)op.field].size())
+        code = cols[(size_t)op.field][(size_t)s];
+      stack[sp++] = op.kind == kFilterEq ? (code != 0u && code == op.code)
+                    : op.kind == kFilterNe ? !(code != 0u && code == op.code) : code != 0u;
+    } else {
+      bool acc = op.kind == kFilterAnd;
+      for (uint32_t c = 0; c < op.code; ++c) {
+        const bool v = stack[--sp];
+        acc = op.kind == kFilterAnd ? (acc && v) : (acc || v);
+      }
+      stack[sp++] = acc;
+    }
+  }
+  return sp > 0 ? stack[sp - 1] : true;
+}
+
 static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                            const uint64_t* cmask, int64_t cmask_bits, uint64_t* out_ids, float* out_dist,
-                            uint32_t* out_counts, int64_t kstride) {
+                            const uint64_t* cmask, int64_t cmask_bits, const char* filter_json, uint64_t* out_ids,
+                            float* out_dist, uint32_t* out_counts, int64_t kstride) {
   // cmask: the caller's eligibility mask by internal id (or null).  The passes work on a SLOT-indexed mask, so the
-  // caller's bits are carried over slot by slot through the id runs before the first pass.
+  // caller's bits are carried over slot by slot through the id runs before the first pass.  filter_json (instead
+  // of a mask): the filter is evaluated once per query over the host mirror of the metadata columns.
   if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
   std::vector<int64_t> small, big;
   for (int64_t i = 0; i < q; ++i) {
@@ -1812,7 +1838,7 @@ static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64
       memcpy(qs.data() + j * dim, queries + small[j] * dim, (size_t)dim * 4);
       k2[j] = ks[small[j]];
     }
-    rc = search_impl(h, qs.data(), (int64_t)small.size(), dim, k2.data(), cmask, cmask_bits, nullptr, ids.data(),
+    rc = search_impl(h, qs.data(), (int64_t)small.size(), dim, k2.data(), cmask, cmask_bits, filter_json, ids.data(),
                      dist.data(), cnt.data(), km);
     if (rc != GFI_OK) return rc;
     for (size_t j = 0; j < small.size(); ++j) {
@@ -1826,14 +1852,32 @@ static int32_t search_big_k(gfi_index* h, const float* queries, int64_t q, int64
   std::vector<float> tmp_dist(kMaxListK);
   for (int64_t i : big) {
     for (int attempt = 0;; ++attempt) {
-      if ((rc = ensure_flushed(h)) != GFI_OK) return rc;
+      if ((rc = ensure_flushed(h, filter_json != nullptr)) != GFI_OK) return rc;
       const uint64_t gen = h->layout_gen.load();
       int64_t n_slots;
       {
         std::shared_lock<std::shared_mutex> g(h->mu);
         n_slots = h->n_slots;
       }
-      std::vector<uint64_t> mask((size_t)(n_slots + 63) / 64 + 1, cmask ? 0ull : ~0ull);
+      std::vector<uint64_t> mask((size_t)(n_slots + 63) / 64 + 1, (cmask || filter_json) ? 0ull : ~0ull);
+      bool meta_stale = false;
+      if (filter_json) {
+        std::shared_lock<std::shared_mutex> g(h->mu);
+        if (h->meta_dirty || h->n_slots != n_slots) {
+          meta_stale = true;  // a writer slipped in between the flush and this lock: flush again
+        } else {
+          FilterProgram prog{};
+          std::string err;
+          if (!compile_filter(filter_json, h->meta_fields, h->meta_values, &prog, &err))
+            return fail(GFI_ERR_INDEX, "bad filter: " + err);
+          for (int64_t sl = 0; sl < n_slots; ++sl)
+            if (eval_filter_host(prog, h->meta_cols, sl)) mask[(size_t)sl >> 6] |= 1ull << (sl & 63);
+        }
+      }
+      if (meta_stale) {
+        if (attempt >= 3) return fail(GFI_ERR_INDEX, "index kept changing during a large-k filtered search");
+        continue;
+      }
       if (cmask) {
         std::shared_lock<std::shared_mutex> g(h->mu);
         for (const auto& kv : h->runs) {
@@ -1936,8 +1980,8 @@ int32_t gfi_search(gfi_index* h, const float* queries, int64_t q, int64_t dim, c
     bool bigk = false;
     for (int64_t i = 0; i < q; ++i) bigk = bigk || ks[i] > kMaxListK;
     if (bigk)
-      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, mask, mask_bits, out_ids, out_dist, out_counts, kstride)
-                       : search_big_k(h, queries, q, dim, ks, mask, mask_bits, out_ids, out_dist, out_counts, kstride);
+      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, mask, mask_bits, nullptr, out_ids, out_dist, out_counts, kstride)
+                       : search_big_k(h, queries, q, dim, ks, mask, mask_bits, nullptr, out_ids, out_dist, out_counts, kstride);
   }
   // masked searches, large batches and malformed calls take the direct path
   // (indexes below 32 MB are launch-latency-bound: independent calls on separate streams overlap on the GPU and
@@ -2003,6 +2047,13 @@ int32_t gfi_search_filtered(gfi_index* h, const float* queries, int64_t q, int64
                             const char* filter_json, uint64_t* out_ids, float* out_dist, uint32_t* out_counts,
                             int64_t kstride) {
   if (!filter_json) return fail(GFI_ERR_INDEX, "null filter");
+  if (h && q > 0 && ks) {  // k beyond the kernels' list capacity: exact passes over the rows not returned yet
+    bool bigk = false;
+    for (int64_t i = 0; i < q; ++i) bigk = bigk || ks[i] > kMaxListK;
+    if (bigk)
+      return h->shards ? sharded_search_big_k(h, queries, q, dim, ks, nullptr, 0, filter_json, out_ids, out_dist, out_counts, kstride)
+                       : search_big_k(h, queries, q, dim, ks, nullptr, 0, filter_json, out_ids, out_dist, out_counts, kstride);
+  }
   return search_impl(h, queries, q, dim, ks, nullptr, 0, filter_json, out_ids, out_dist, out_counts, kstride);
 }
 

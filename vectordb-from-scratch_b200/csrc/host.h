@@ -186,8 +186,8 @@ int32_t sharded_search(gfi_index* h, const float* queries, int64_t q, int64_t di
                        const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
                        float* out_dist, uint32_t* out_counts, int64_t kstride);
 int32_t sharded_search_big_k(gfi_index* h, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                             const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
-                             uint32_t* out_counts, int64_t kstride);
+                             const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
+                             float* out_dist, uint32_t* out_counts, int64_t kstride);
 int32_t sharded_search_device(gfi_index* h, const float* d_queries, int64_t q, const uint32_t* d_ks, uint32_t kmax,
                               const uint64_t* d_mask, int64_t mask_bits, uint64_t* d_out_ids, float* d_out_dist,
                               uint32_t* d_out_counts, int64_t kstride, void* stream);

@@ -214,8 +214,8 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
     // k-th distance: a cut that is too tight makes the query fall back, it cannot change an answer.
     uint32_t kp_out = kpeff, cut_key = 0, has_cut = 0;
     const uint32_t kq = p.ks[qg];
-    if (p.certify == 1 && p.rerank_cut && KP <= 512 && kq > 0 && kpeff > kq && !overflow) {
-      uint64_t* sorted = keys;  // the staging area is free again (KP <= 512 <= kSelCap)
+    if (p.certify == 1 && p.rerank_cut && (uint32_t)KP <= kSelCap && kq > 0 && kpeff > kq && !overflow) {
+      uint64_t* sorted = keys;  // the staging area is free again
       for (int t = tid; t < KP; t += kSelThreads) {
         const uint64_t key = sel[t];
         if (key == kKeySentinel) continue;

@@ -748,18 +748,18 @@ static int32_t per_shard_host_search(gfi_index* H, const float* queries, int64_t
 }
 
 int32_t sharded_search_big_k(gfi_index* H, const float* queries, int64_t q, int64_t dim, const uint32_t* ks,
-                             const uint64_t* mask, int64_t mask_bits, uint64_t* out_ids, float* out_dist,
-                             uint32_t* out_counts, int64_t kstride) {
+                             const uint64_t* mask, int64_t mask_bits, const char* filter_json, uint64_t* out_ids,
+                             float* out_dist, uint32_t* out_counts, int64_t kstride) {
   ShardSet* S = H->shards;
   if (!queries || !ks || !out_counts || !out_ids || !out_dist) return fail(GFI_ERR_INDEX, "bad arguments");
   for (int64_t i = 0; i < q; ++i)
     if ((int64_t)ks[i] > kstride) return fail(GFI_ERR_INDEX, "kstride smaller than max k");
   int32_t rc;
-  if ((rc = ensure_flushed_all(H, false)) != GFI_OK) return rc;
+  if ((rc = ensure_flushed_all(H, filter_json != nullptr)) != GFI_OK) return rc;
   std::shared_lock<std::shared_mutex> lk(H->mu);
   ++S->n_search;
   S->n_queries += q;
-  return per_shard_host_search(H, queries, q, dim, ks, mask, mask_bits, nullptr, out_ids, out_dist, out_counts, kstride);
+  return per_shard_host_search(H, queries, q, dim, ks, mask, mask_bits, filter_json, out_ids, out_dist, out_counts, kstride);
 }
 
 namespace {
