@@ -28,8 +28,12 @@ constexpr int kMaxKP = 1024;
 constexpr int kTileFloats = 4096;  // rerank tile: GC candidates x CW floats, GC * CW = 4096
 
 // Exact 64-bit radix select: returns the `need`-th smallest (1-based) of the valid keys in src[0..cnt).
+// After the four passes over the score half of the keys the remaining group usually holds ONE key (scores tie only
+// among duplicate rows): that key is the answer, and the four passes over the slot half are skipped.
 __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t cnt, uint32_t need, uint64_t bound,
                                                  uint32_t* hist, uint32_t* s_bucket, uint32_t* s_need, int tid) {
+  __shared__ uint32_t s_group;
+  __shared__ unsigned long long s_only;
   uint64_t prefix = 0, mask = 0;
   for (int pass = 0; pass < 8; ++pass) {
     const int shift = 56 - 8 * pass;
@@ -54,7 +58,7 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
       if (before < need && need <= incl) {
 #pragma unroll
         for (int b = 0; b < 8; ++b) {
-          if (need <= before + h[b]) { *s_bucket = tid * 8 + b; *s_need = need - before; break; }
+          if (need <= before + h[b]) { *s_bucket = tid * 8 + b; *s_need = need - before; s_group = h[b]; break; }
           before += h[b];
         }
       }
@@ -63,7 +67,18 @@ __device__ __forceinline__ uint64_t radix_select(const uint64_t* src, uint32_t c
     prefix |= (uint64_t)(*s_bucket) << shift;
     mask |= 0xffull << shift;
     need = *s_need;
+    const bool single = pass == 3 && s_group == 1;  // block-uniform
     __syncthreads();
+    if (single) {
+      for (uint32_t i = tid; i < cnt; i += kSelThreads) {
+        const uint64_t key = src[i];
+        if (key <= bound && (key & mask) == prefix) s_only = key;
+      }
+      __syncthreads();
+      const uint64_t only = s_only;
+      __syncthreads();
+      return only;
+    }
   }
   return prefix;
 }
@@ -262,7 +277,9 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
 constexpr int kRrWarps = 4;                       // warps per block
 constexpr int kRrCW = 32;                         // floats per row chunk (one 128-byte line)
 constexpr int kRrRPW = 8;                         // bulk mode: candidate rows per warp (4 lanes per row)
-constexpr int kRrDepth = 4;                       // bulk mode: chunks of loads in flight per lane
+constexpr int kRrDepth = 8;                       // bulk mode: row chunks in flight per lane
+constexpr int kRrDepthQ = 2;                      // bulk mode: query chunks in flight per lane (kRrDepth % kRrDepthQ == 0)
+static_assert(kRrDepth % kRrDepthQ == 0, "query slots are addressed by chunk index modulo kRrDepthQ");
 constexpr int kRrTile = 32 * (kRrCW + 1);         // per-warp scratch: the latency mode's row + query, the final sort
 static_assert(2 * kRrTile * 4 >= kMaxKP * 8, "the finalizing warp sorts in its tile buffers");
 
@@ -358,19 +375,28 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
       const float* xrow = iv.x32 + (size_t)slot * iv.dpad;
       const int nchunk = (iv.d + kRrCW - 1) / kRrCW;
       const int col_last = iv.dpad - 4;
-      float4 xa[kRrDepth], xb[kRrDepth], qa[kRrDepth], qb[kRrDepth];
-      auto issue = [&](int j, int c) {
+      // row pieces come from HBM (random rows: ~2000 cycles under load) and are fetched kRrDepth chunks ahead; the
+      // query pieces are shared by the warp's rows and by every warp of the query (L1/L2 hits): kRrDepthQ ahead
+      float4 xa[kRrDepth], xb[kRrDepth], qa[kRrDepthQ], qb[kRrDepthQ];
+      auto issue_x = [&](int j, int c) {
         const int col = c * kRrCW + 8 * c8;
-        const int ca = min(col, col_last), cb = min(col + 4, col_last);
-        xa[j] = __ldg(reinterpret_cast<const float4*>(xrow + ca));
-        xb[j] = __ldg(reinterpret_cast<const float4*>(xrow + cb));
-        qa[j] = __ldg(reinterpret_cast<const float4*>(qv + ca));
-        qb[j] = __ldg(reinterpret_cast<const float4*>(qv + cb));
+        xa[j] = __ldg(reinterpret_cast<const float4*>(xrow + min(col, col_last)));
+        xb[j] = __ldg(reinterpret_cast<const float4*>(xrow + min(col + 4, col_last)));
+      };
+      auto issue_q = [&](int j, int c) {
+        const int col = c * kRrCW + 8 * c8;
+        qa[j] = __ldg(reinterpret_cast<const float4*>(qv + min(col, col_last)));
+        qb[j] = __ldg(reinterpret_cast<const float4*>(qv + min(col + 4, col_last)));
       };
 #pragma unroll
       for (int j = 0; j < kRrDepth; ++j) {
-        xa[j] = xb[j] = qa[j] = qb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (j < nchunk) issue(j, j);
+        xa[j] = xb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nchunk) issue_x(j, j);
+      }
+#pragma unroll
+      for (int j = 0; j < kRrDepthQ; ++j) {
+        qa[j] = qb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (j < nchunk) issue_q(j, j);
       }
       const int src_lane = (lane & ~3) | ((lane + 3) & 3);  // previous lane of the row (the first takes from the last)
       float acc = -0.0f;
@@ -379,8 +405,9 @@ __global__ void __launch_bounds__(kRrWarps * 32) rerank_finalize_kernel(const Se
         for (int j = 0; j < kRrDepth; ++j) {
           const int c = c0 + j;
           if (c < nchunk) {  // warp-uniform
-            const float4 x0 = xa[j], x1 = xb[j], q0 = qa[j], q1 = qb[j];
-            if (c + kRrDepth < nchunk) issue(j, c + kRrDepth);
+            const float4 x0 = xa[j], x1 = xb[j], q0 = qa[j % kRrDepthQ], q1 = qb[j % kRrDepthQ];
+            if (c + kRrDepth < nchunk) issue_x(j, c + kRrDepth);
+            if (c + kRrDepthQ < nchunk) issue_q(j % kRrDepthQ, c + kRrDepthQ);
             float t[8];
             t[0] = exact_term<METRIC>(q0.x, x0.x); t[1] = exact_term<METRIC>(q0.y, x0.y);
             t[2] = exact_term<METRIC>(q0.z, x0.z); t[3] = exact_term<METRIC>(q0.w, x0.w);
