@@ -273,7 +273,7 @@ __global__ void __launch_bounds__(kSelThreads) select_kernel(const SelectParams 
   }
 }
 
-// ---- K3b: reference-exact rerank (one warp per 32 candidates) + finalize by the last warp ----------
+// ---- K3b: reference-exact rerank (bulk: 8 candidates per warp; latency mode: one) + finalize by the last warp ----
 constexpr int kRrWarps = 4;                       // warps per block
 constexpr int kRrCW = 32;                         // floats per row chunk (one 128-byte line)
 constexpr int kRrRPW = 8;                         // bulk mode: candidate rows per warp (4 lanes per row)
