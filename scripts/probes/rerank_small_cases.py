@@ -1,6 +1,6 @@
 """Small-case probe (also usable under compute-sanitizer where that is open): a few small tensor-path searches (select with the rerank cut + bulk rerank, odd row
 lengths so the clamped last-chunk loads are exercised), checked against the oracle.
-usage: compute-sanitizer --tool memcheck python scripts/probes/sanitize_rerank.py"""
+usage: compute-sanitizer --tool memcheck python scripts/probes/rerank_small_cases.py"""
 import os
 import sys
 
